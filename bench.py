@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py — training voxels/s of the 3D ResUNet hot path on synthetic 128^3 volumes (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One "step" = the body of the reference's train_epoch (train_ddp.py:171-215): zero_grad -> autocast fwd ->
+CE+Dice -> GradScaler backward (+DDP all-reduce) -> AdamW -> EMA.  Prints ONE JSON line (rank 0).
+  value     : voxels/s with inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       : same through the public API from pinned HOST buffers (H2D inside the timed region) plus the
+              per-step loss.item() D2H the reference loop does (train_ddp.py:213)
+  roofline  : dominant kernel (conv3d forward of the costliest layer shape) timed alone with CUDA events
+  cpu_baseline : the reference-pinned oracle (oracle/) on the host cores, bounded sample
+--impl reference times the oracle port on the host CPU (the reference is pure Python/PyTorch).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scale list, kernel list, classes, ce weight, (B, D, H, W))
+    "resunet_acdc_128": ([[1, 2, 2], [1, 2, 2], [2, 2, 2], [2, 2, 2]],
+                         [[1, 3, 3], [1, 3, 3], [3, 3, 3], [3, 3, 3], [3, 3, 3]], 4, [0.5, 1, 1, 1], (1, 128, 128, 128)),
+    "resunet_iso_128": ([[2, 2, 2]] * 4, [[3, 3, 3]] * 5, 4, [0.5, 1, 1, 1], (1, 128, 128, 128)),
+    "resunet_kits_160": ([[2, 2, 2]] * 4, [[3, 3, 3]] * 5, 3, [0.5, 1, 2], (2, 160, 160, 80)),
+}
+BASE = 32
+METRIC = "3D-UNet (ResBasicBlock) training voxels/sec, synthetic 128^3"
+
+
+def conv_layers(scale, kernel, classes, B, D, H, W, base=BASE):
+    """(Cin, Cout, k, D, H, W, count) of every conv3d of the ResUNet, with fused conv1+shortcut listed apart."""
+    ch = [base, 2 * base, 4 * base, 8 * base, 10 * base]
+    dims = [(D, H, W)]
+    for s in scale:
+        d = dims[-1]
+        dims.append((d[0] // s[0], d[1] // s[1], d[2] // s[2]))
+    L = []
+
+    def block(ci, co, k, dm):
+        L.append((ci, co, k, dm))
+        L.append((co, co, k, dm))
+        if ci != co:
+            L.append((ci, co, k, dm))
+    L.append((1, base, kernel[0], dims[0]))
+    block(base, base, kernel[0], dims[0])
+    for i in range(4):
+        block(ch[i], ch[i + 1], kernel[i + 1], dims[i + 1])
+        block(ch[i + 1], ch[i + 1], kernel[i + 1], dims[i + 1])
+    for j in range(4):
+        ci, co = ch[4 - j], ch[3 - j]
+        block(ci + co, co, kernel[3 - j], dims[3 - j])
+        block(co, co, kernel[3 - j], dims[3 - j])
+    L.append((base, classes, [1, 1, 1], dims[0]))
+    return L
+
+
+def conv_flops(L, B):
+    return sum(2.0 * B * d[0] * d[1] * d[2] * ci * co * k[0] * k[1] * k[2] for ci, co, k, d in L)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return model, os.cpu_count()
+
+
+# --------------------------------------------------------------------------- CPU (reference) arm
+def oracle_step_fn(scale, kernel, classes, weight):
+    import torch
+    from oracle import losses as olosses
+    from oracle import unet3d as ounet
+    shapes = ounet.unet_param_shapes(1, BASE, classes, kernel, "BasicBlock")
+    sd = {k: v.requires_grad_(True) for k, v in ounet.make_state_dict(shapes, seed=7).items()}
+    params = list(sd.values())
+    opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.999), weight_decay=0.05, eps=1e-5)
+    w = torch.tensor(weight, dtype=torch.float32)
+
+    def step(img, lab):
+        opt.zero_grad(set_to_none=True)
+        loss = olosses.total_loss(ounet.unet_forward(sd, img, scale, kernel, "BasicBlock"), lab, w)
+        loss.backward()
+        opt.step()
+        return loss.item()
+    return step
+
+
+def cpu_sample_shape(scale, budget_s, steps_total, step, classes):
+    """Pick the largest depth-crop of the workload whose (steps_total) steps fit in budget_s."""
+    import torch
+    from oracle.synth import make_volume
+    dmin = 1
+    for s in scale:
+        dmin *= s[0]
+    dmin = max(dmin * 2, 8)
+    img, lab = make_volume(1, dmin, 64, 64, classes, seed=1)
+    step(img, lab)
+    t0 = time.time(); step(img, lab); t = time.time() - t0
+    rate = dmin * 64 * 64 / t
+    return dmin, rate
+
+
+def run_reference(args, wl):
+    import torch
+    from oracle.synth import make_volume
+    scale, kernel, classes, weight, (B, D, H, W) = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    step = oracle_step_fn(scale, kernel, classes, weight)
+    dmin, rate = cpu_sample_shape(scale, 0, 0, step, classes)
+    total = args.steps + args.warmup
+    budget = 150.0
+    d = dmin
+    while d * 2 <= D and (d * 2) * H * W * total / rate <= budget:
+        d *= 2
+    img, lab = make_volume(1, d, H, W, classes, seed=2023)
+    for _ in range(args.warmup):
+        step(img, lab)
+    t0 = time.time()
+    for _ in range(args.steps):
+        step(img, lab)
+    dt = time.time() - t0
+    vps = args.steps * d * H * W / dt
+    model, _ = host_info()
+    sample = "depth-crop %dx%dx%d of the %dx%dx%d volume, batch 1, fp32, oracle port of the reference modules" % (d, H, W, D, H, W)
+    out = {"impl": "reference", "metric": METRIC, "value": vps, "unit": "voxels/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": args.workload, "model": "ResUNet-3D base32 BasicBlock IN", "sample": sample},
+           "cpu_baseline": {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample,
+                            "cpu": model},
+           "e2e": {"value": vps, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------- B200 arm
+def run_b200(args, wl):
+    import torch
+    import torch.distributed as dist
+    import b200seg
+    from b200seg import _lib, ops
+    from b200seg.train import TrainStep
+    from oracle.synth import make_volume
+    from oracle import unet3d as ounet
+
+    scale, kernel, classes, weight, (B, D, H, W) = wl
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert _lib.load().b200seg_check_device() == 0, "not an sm_100 device"
+
+    def make_net():
+        n = b200seg.UNet(1, BASE, scale=scale, kernel_size=kernel, num_classes=classes, block="BasicBlock", norm="in")
+        shapes = ounet.unet_param_shapes(1, BASE, classes, kernel, "BasicBlock")
+        n.load_state_dict(ounet.make_state_dict(shapes, seed=7))
+        return n.to(dev)
+    net, ema = make_net(), make_net()
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        net = DDP(net, device_ids=[local], find_unused_parameters=True)      # train_ddp.py:353
+    for p in ema.parameters():
+        p.requires_grad_(False)                                             # train_ddp.py:360-361
+    ts = TrainStep(net, ema, ce_weight=torch.tensor(weight), amp=True)
+
+    img_h, lab_h = make_volume(B, D, H, W, classes, seed=2023 + rank)
+    img_h, lab_h = img_h.pin_memory(), lab_h.pin_memory()
+    img, lab = img_h.to(dev), lab_h.to(dev)
+    vox = B * D * H * W
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        ts(img, lab)
+    torch.cuda.synchronize()
+    c0 = _lib.launch_count
+    with ClockSampler(local) as cs:
+        ms = timed(lambda: ts(img, lab), args.steps)
+    launches = (_lib.launch_count - c0) // args.steps
+    clocks = cs.summary()
+
+    def e2e_step():
+        i = img_h.to(dev, non_blocking=True)                 # train_ddp.py:173-174
+        l = lab_h.to(dev, non_blocking=True)
+        return ts(i, l).item()                               # train_ddp.py:213
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    peak_mem = torch.cuda.max_memory_allocated() / 2**30
+
+    out = {"metric": METRIC, "value": world * vox * args.steps / (ms / 1e3), "unit": "voxels/s", "n_gpus": world,
+           "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+           "config": {"workload": args.workload, "model": "ResUNet-3D base32 BasicBlock IN (reference UNet(1,32,...,block='BasicBlock',norm='in'))",
+                      "per_gpu_batch": B, "volume": [D, H, W], "classes": classes, "parallelism": "dp%d" % world,
+                      "amp": "autocast fp16 + GradScaler", "optimizer": "AdamW(fused)+EMA",
+                      "l2": "working set (%.1f GiB activations/step) >> 126 MB L2, no explicit flush" % peak_mem},
+           "clocks": clocks,
+           "e2e": {"value": world * vox * args.steps / (ms_e2e / 1e3), "unit": "voxels/s",
+                   "h2d_bytes_per_step": img_h.numel() * 4 + lab_h.numel() * 8, "d2h_bytes_per_step": 4,
+                   "ms_per_step": ms_e2e / args.steps},
+           "gpu_launches": launches, "peak_mem_gib": peak_mem}
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel: conv3d forward on the costliest layer shape
+        L = conv_layers(scale, kernel, classes, B, D, H, W)
+        fl_step = 3 * conv_flops(L, B) - conv_flops(L[:1], B)
+        out["config"]["algorithmic_gflop_per_step"] = fl_step / 1e9
+        out["achieved_tflops_step"] = fl_step / (ms / args.steps / 1e3) / 1e12
+        groups = {}
+        for ci, co, k, d in L:
+            groups[(ci, co, tuple(k), d)] = groups.get((ci, co, tuple(k), d), 0) + conv_flops([(ci, co, k, d)], B)
+        (ci, co, k, d), _ = max(groups.items(), key=lambda kv: kv[1])
+        x = torch.randn(B, d[0], d[1], d[2], ci, device=dev).half()
+        st = ops.instnorm_stats(x, 0, ci)
+        wp = torch.randn(k[0] * k[1] * k[2] * co * ci, device=dev).half() * 0.05
+        for _ in range(3):
+            ops.conv3d_fwd(x, 0, ci, st, ops.ACT_RELU, wp, co, k)
+        torch.cuda.synchronize()
+        reps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ops.conv3d_fwd(x, 0, ci, st, ops.ACT_RELU, wp, co, k)
+        e1.record()
+        torch.cuda.synchronize()
+        kms = e0.elapsed_time(e1) / reps
+        kfl = conv_flops([(ci, co, list(k), d)], B)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops", 1590.0)
+        out["roofline"] = {"bound": "tensor", "achieved": kfl / (kms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                           "frac": kfl / (kms / 1e3) / 1e12 / peak, "traffic": None,
+                           "peak_source": "measured (MEASURED_PEAKS.json, burst)" if peaks else "fallback 1.59 PF",
+                           "kernel": "conv3d_fwd %d->%d k%s @%s (IN+ReLU loader, IN-sums epilogue)" % (ci, co, list(k), list(d)),
+                           "ms": kms, "step_frac_of_sustained_peak": out["achieved_tflops_step"] / peaks.get("bf16_tflops_sustained", 1400.0)}
+        del x, wp
+        # ---- CPU baseline: oracle port on the host cores, bounded sample
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count()
+            torch.set_num_threads(cores)
+            step = oracle_step_fn(scale, kernel, classes, weight)
+            dmin, rate = cpu_sample_shape(scale, 0, 0, step, classes)
+            dd = dmin
+            while dd * 2 <= D and (dd * 2) * H * W * 2 / rate <= 25.0:
+                dd *= 2
+            ci_, cl_ = make_volume(1, dd, H, W, classes, seed=3)
+            step(ci_, cl_)
+            t0 = time.time(); step(ci_, cl_); dt = time.time() - t0
+            out["cpu_baseline"] = {"value": dd * H * W / dt, "unit": "voxels/s", "cores": cores, "kind": "port",
+                                   "cpu": host_info()[0],
+                                   "sample": "1 timed step (after 1 warm-up) on a %dx%dx%d depth-crop, batch 1, fp32, all host threads" % (dd, H, W)}
+        # ---- the bar to beat: the same algorithm through stock PyTorch + cuDNN on this GPU (AMP)
+        if world == 1 and not args.no_cudnn:
+            try:
+                out["torch_cudnn_same_gpu"] = cudnn_baseline(scale, kernel, classes, weight, img, lab, args.steps)
+            except Exception as e:       # noqa
+                out["torch_cudnn_same_gpu"] = {"error": str(e)[:200]}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cudnn_baseline(scale, kernel, classes, weight, img, lab, steps):
+    """Stock PyTorch (+cuDNN) evaluation of the reference's algorithm on the same GPU, AMP fp16, same step."""
+    import torch
+    from oracle import losses as olosses
+    from oracle import unet3d as ounet
+    dev = img.device
+    shapes = ounet.unet_param_shapes(1, BASE, classes, kernel, "BasicBlock")
+    sd = {k: v.to(dev).requires_grad_(True) for k, v in ounet.make_state_dict(shapes, seed=7).items()}
+    ema = [v.detach().clone() for v in sd.values()]
+    opt = torch.optim.AdamW(list(sd.values()), lr=1e-3, betas=(0.9, 0.999), weight_decay=0.05, eps=1e-5, fused=True)
+    scaler = torch.amp.GradScaler("cuda")
+    w = torch.tensor(weight, device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            loss = olosses.total_loss(ounet.unet_forward(sd, img, scale, kernel, "BasicBlock"), lab, w)
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        torch._foreach_mul_(ema, 0.99)
+        torch._foreach_add_(ema, [v.detach() for v in sd.values()], alpha=0.01)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": img.shape[0] * img[0, 0].numel() / (ms / 1e3), "unit": "voxels/s", "ms_per_step": ms,
+            "what": "oracle modules (reference algorithm) via stock torch %s + cuDNN, autocast fp16" % torch.__version__}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="resunet_acdc_128", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cudnn", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

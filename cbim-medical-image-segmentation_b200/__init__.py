@@ -1,0 +1,12 @@
+"""b200seg — Blackwell-native (sm_100a) training hot path for the 3D segmentation models of
+yhygao/CBIM-Medical-Image-Segmentation, behind the reference's own interfaces:
+``get_model(args)`` (model/utils.py:6), the module/state_dict contract, ``DiceLoss`` (training/losses.py:8).
+Importing this package never touches the GPU; every op fails loudly without libb200seg.so + a B200."""
+from . import _lib
+from ._lib import B200SegError, EXPORTED_SYMBOLS, LIB_PATH
+from .factory import get_model
+from .losses import CrossEntropyLoss, DiceCELoss, DiceLoss
+from .unet3d import UNet
+
+__all__ = ["get_model", "UNet", "DiceLoss", "DiceCELoss", "CrossEntropyLoss", "B200SegError",
+           "EXPORTED_SYMBOLS", "LIB_PATH"]

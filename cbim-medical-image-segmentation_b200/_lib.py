@@ -1,0 +1,89 @@
+"""ctypes binding of libb200seg.so (the C ABI declared in include/b200seg.h).
+
+The library is the product: if it is missing or the device is not sm_100 every op raises — there is no
+PyTorch/CPU fallback anywhere in this package (SURVEY.md §8b "Errors")."""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200seg.so")
+
+F32, F16 = 0, 1
+ALGO_AUTO, ALGO_DIRECT, ALGO_TC = 0, 1, 2
+ACT_NONE, ACT_RELU = 0, 1
+
+P = c_void_p
+I = c_int
+L = c_int64
+F = c_float
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/b200seg.h 1:1
+_PROTOS = {
+    "b200seg_version": [],
+    "b200seg_strerror": [I],
+    "b200seg_last_cuda_error": [],
+    "b200seg_check_device": [],
+    "b200seg_dice_ce_fwd": [P, I, L, L, L, P, I, P, I, L, I, F, F, P, P, P],
+    "b200seg_dice_ce_bwd": [P, I, L, L, L, P, I, P, I, L, I, F, F, P, P, P, P],
+    "b200seg_instnorm_stats": [P, I, I, I, I, L, I, P, P],
+    "b200seg_instnorm_apply": [P, I, I, I, P, F, I, P, I, I, I, L, I, P],
+    "b200seg_instnorm_bwd_reduce": [P, I, I, P, I, I, I, P, F, I, P, I, I, P, I, L, I, P],
+    "b200seg_instnorm_bwd_apply": [P, I, I, P, I, I, I, P, P, F, P, I, I, P, I, I, I, L, I, P],
+    "b200seg_pack_weight": [P, I, I, I, P, I, I, I, I, P],
+    "b200seg_conv3d_fwd": [P, I, I, P, F, I, P, P, P, I, I, P, I, I, P, P, I, I, P, F, I,
+                           I, I, I, I, I, I, I, I, I, I, I, P],
+    "b200seg_conv3d_wgrad": [P, I, I, P, F, I, P, I, I, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
+    "b200seg_maxpool3d_fwd": [P, I, I, P, I, I, P, P, I, I, I, I, I, I, I, I, I, P],
+    "b200seg_maxpool3d_bwd": [P, I, I, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
+    "b200seg_upsample_trilinear_fwd": [P, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P],
+    "b200seg_upsample_trilinear_bwd": [P, I, I, P, I, I, I, I, I, I, I, I, I, I, I, I, P],
+    "b200seg_copy_channels": [P, I, I, I, P, I, I, I, I, L, I, P],
+}
+_RESTYPES = {"b200seg_strerror": c_char_p, "b200seg_last_cuda_error": c_char_p}
+
+EXPORTED_SYMBOLS = tuple(_PROTOS)
+
+_lib = None
+
+
+class B200SegError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200SegError(
+                "libb200seg.so not found at %s — run `python __graft_entry__.py build` "
+                "(there is no fallback path)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in _PROTOS.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int)
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        lib = load()
+        msg = lib.b200seg_strerror(rc).decode()
+        if rc == -3:
+            msg += " (" + lib.b200seg_last_cuda_error().decode() + ")"
+        raise B200SegError("%s failed: %s" % (what, msg))
+
+
+# kernels launched per entry point (dice fwd = reduce + finalize; its memset is not ours)
+_KERNELS = {"b200seg_dice_ce_fwd": 2}
+launch_count = 0
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point and raise on a non-zero code."""
+    global launch_count
+    check(getattr(load(), name)(*args), name)
+    launch_count += _KERNELS.get(name, 1)

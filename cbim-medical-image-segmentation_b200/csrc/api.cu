@@ -1,0 +1,74 @@
+// api.cu — C-ABI entry points that dispatch between the CUDA-core and tcgen05 conv paths, plus
+// version / error plumbing.  No CPU fallback exists anywhere in this library: an unsupported
+// shape or a non-sm_100 device is a hard error (SURVEY.md §8b "Errors").
+#include "common.cuh"
+#include "conv_args.h"
+#include <stdio.h>
+#include <string.h>
+
+thread_local char g_b200seg_cuda_err[256] = "";
+
+int b200seg_record_cuda(cudaError_t e, const char* what) {
+  snprintf(g_b200seg_cuda_err, sizeof(g_b200seg_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+  return B200SEG_ECUDA;
+}
+
+extern "C" int b200seg_version(void) { return B200SEG_VERSION; }
+
+extern "C" const char* b200seg_strerror(int code) {
+  switch (code) {
+    case B200SEG_OK: return "ok";
+    case B200SEG_EINVAL: return "invalid argument";
+    case B200SEG_EUNSUPPORTED: return "shape/dtype not supported by the requested algorithm";
+    case B200SEG_ECUDA: return "CUDA runtime error";
+    case B200SEG_ENODEVICE: return "device is not sm_100 (B200); this library has no fallback path";
+    default: return "unknown error";
+  }
+}
+
+extern "C" const char* b200seg_last_cuda_error(void) { return g_b200seg_cuda_err; }
+
+extern "C" int b200seg_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { b200seg_record_cuda(e, "cudaGetDevice"); return B200SEG_ENODEVICE; }
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) { b200seg_record_cuda(e, "cudaDeviceGetAttribute"); return B200SEG_ENODEVICE; }
+  return major == 10 ? B200SEG_OK : B200SEG_ENODEVICE;
+}
+
+extern "C" int b200seg_conv3d_fwd(const void* x, int x_ld, int x_coff, const double* x_stats, float eps, int act,
+                                  const void* w_packed, const float* bias, const void* residual, int r_ld,
+                                  int r_coff, void* y, int y_ld, int y_coff, double* y_stats,
+                                  const void* dgrad_x, int dx_ld, int dx_coff, const double* dgrad_stats,
+                                  float dgrad_eps, int dgrad_act, int B, int D, int H, int W, int Cin, int Cout,
+                                  int kd, int kh, int kw, int dtype, int algo, void* stream) {
+  if (!x || !w_packed || !y || B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return B200SEG_EINVAL;
+  if (kd <= 0 || kh <= 0 || kw <= 0 || !(kd & 1) || !(kh & 1) || !(kw & 1)) return B200SEG_EUNSUPPORTED;
+  if (dtype != B200SEG_F16 && dtype != B200SEG_F32) return B200SEG_EINVAL;
+  if (dgrad_x && !dgrad_stats) return B200SEG_EINVAL;
+  if (dgrad_x && (residual || bias)) return B200SEG_EINVAL;
+  ConvArgs a{x, x_ld, x_coff, x_stats, eps, act, w_packed, bias, residual, r_ld, r_coff, y, y_ld, y_coff, y_stats,
+             dgrad_x, dx_ld, dx_coff, dgrad_stats, dgrad_eps, dgrad_act, B, D, H, W, Cin, Cout, kd, kh, kw};
+  cudaStream_t st = as_stream(stream);
+  if (algo == B200SEG_ALGO_TC) return conv3d_fwd_tc(a, dtype, st);
+  if (algo == B200SEG_ALGO_AUTO && conv3d_fwd_tc_supported(a, dtype)) return conv3d_fwd_tc(a, dtype, st);
+  if (algo != B200SEG_ALGO_AUTO && algo != B200SEG_ALGO_DIRECT) return B200SEG_EINVAL;
+  return conv3d_fwd_direct(a, dtype, st);
+}
+
+extern "C" int b200seg_conv3d_wgrad(const void* x, int x_ld, int x_coff, const double* x_stats, float eps, int act,
+                                    const void* dy, int dy_ld, int dy_coff, float* dw, float* dbias, int B, int D,
+                                    int H, int W, int Cin, int Cout, int kd, int kh, int kw, int dtype, int algo,
+                                    void* stream) {
+  if (!x || !dy || !dw || B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return B200SEG_EINVAL;
+  if (kd <= 0 || kh <= 0 || kw <= 0 || !(kd & 1) || !(kh & 1) || !(kw & 1)) return B200SEG_EUNSUPPORTED;
+  if (dtype != B200SEG_F16 && dtype != B200SEG_F32) return B200SEG_EINVAL;
+  WgradArgs a{x, x_ld, x_coff, x_stats, eps, act, dy, dy_ld, dy_coff, dw, dbias, B, D, H, W, Cin, Cout, kd, kh, kw, 0};
+  cudaStream_t st = as_stream(stream);
+  if (algo == B200SEG_ALGO_TC) return conv3d_wgrad_tc(a, dtype, st);
+  if (algo == B200SEG_ALGO_AUTO && conv3d_wgrad_tc_supported(a, dtype)) return conv3d_wgrad_tc(a, dtype, st);
+  if (algo != B200SEG_ALGO_AUTO && algo != B200SEG_ALGO_DIRECT) return B200SEG_EINVAL;
+  return conv3d_wgrad_direct(a, dtype, st);
+}

@@ -1,0 +1,17 @@
+"""``get_model(args, pretrain=False)`` with the reference's dispatch (model/utils.py:6-125) for the
+models of the hot path.  Anything the B200 path does not implement is a hard ValueError — never a
+silent hand-off to stock PyTorch."""
+
+
+def get_model(args, pretrain=False):
+    if args.dimension == '3d':
+        if args.model in ('unet', 'resunet'):
+            from .unet3d import UNet
+            if pretrain and args.model == 'resunet':
+                raise ValueError('No pretrain model available')   # model/utils.py:77-78
+            return UNet(args.in_chan, args.base_chan, num_classes=args.classes, scale=args.down_scale,
+                        norm=args.norm, kernel_size=args.kernel_size, block=args.block)
+        raise ValueError("model %r (3d) is not implemented by the B200 path yet" % (args.model,))
+    if args.dimension == '2d':
+        raise ValueError("2d models are outside the B200 hot path (SURVEY.md §2); use the reference")
+    raise ValueError("Invalid dimension, should be '2d' or '3d'")

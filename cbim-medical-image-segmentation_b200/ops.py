@@ -1,0 +1,418 @@
+"""Thin launch wrappers over the C ABI (include/b200seg.h) and the torch.autograd.Functions built from
+them.  PyTorch is plumbing here: it owns device memory (caching allocator), the current stream and the
+autograd tape; every FLOP and every byte of activation traffic goes through libb200seg.so.
+
+Internal activation format: NDHWC tensors ``[B, D, H, W, ld]`` (fp16 under autocast, else fp32) plus a
+side tensor of InstanceNorm sums ``stats[B, C, 2]`` (fp64) produced by whichever kernel wrote the
+activation.  Channel slices of a wider tensor are addressed with (coff, C) — never with torch views —
+so fused tensors (conv1+shortcut outputs, concat buffers) are consumed in place.
+"""
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ALGO_AUTO, F16, F32, call
+
+IN_EPS = 1e-4  # nn.InstanceNorm3d(eps=1e-4): reference conv_layers.py:40,42
+
+
+def _dt(t):
+    if t.dtype == torch.float16:
+        return F16
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError("b200seg supports float16/float32 activations, got %s" % t.dtype)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t):
+    if not t.is_cuda:
+        raise _lib.B200SegError("b200seg ops need CUDA tensors on a B200 — there is no CPU fallback")
+
+
+def compute_dtype():
+    """fp16 storage/tensor-core operands under torch.autocast (the reference's --amp path,
+    train_ddp.py:181), fp32 otherwise."""
+    return torch.float16 if torch.is_autocast_enabled() else torch.float32
+
+
+def new_stats(B, C, device):
+    return torch.zeros(B, C, 2, dtype=torch.float64, device=device)
+
+
+# ----------------------------------------------------------------------------- raw launches
+def pack_weight(w, dtype, transpose_flip=False, out=None, co_off=0, co_total=None):
+    """[Cout,Cin,kd,kh,kw] fp32 parameter -> packed [taps][Cout_total][Cin] (or the dgrad operand)."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    taps = w.shape[2] * w.shape[3] * w.shape[4]
+    co_total = Cout if co_total is None else co_total
+    if out is None:
+        out = torch.empty(taps * co_total * Cin, dtype=dtype, device=w.device)
+    wc = w.detach()
+    if wc.dtype != torch.float32 or not wc.is_contiguous():
+        wc = wc.float().contiguous()
+    call("b200seg_pack_weight", wc.data_ptr(), Cout, Cin, taps, out.data_ptr(), _dt(out),
+         1 if transpose_flip else 0, co_off, co_total, _stream())
+    return out
+
+
+def conv3d_fwd(x, x_coff, Cin, x_stats, act, wp, Cout, ksize, bias=None, residual=None, r_coff=0,
+               want_stats=True, dgrad_of=None, algo=ALGO_AUTO, eps=IN_EPS):
+    """y = conv(act(IN(x[..., x_coff:x_coff+Cin]))) (+bias)(+residual); returns (y, y_stats).
+    dgrad_of=(tensor, coff, stats, act): data-gradient mode, see b200seg_conv3d_fwd."""
+    _need_cuda(x)
+    B, D, H, W, x_ld = x.shape
+    y = torch.empty(B, D, H, W, Cout, dtype=x.dtype, device=x.device)
+    y_stats = new_stats(B, Cout, x.device) if want_stats else None
+    gx = gcoff = gstats = None
+    gact = ACT_NONE
+    gld = 0
+    if dgrad_of is not None:
+        gx, gcoff, gstats, gact = dgrad_of
+        gld = gx.shape[-1]
+    call("b200seg_conv3d_fwd", x.data_ptr(), x_ld, x_coff, _p(x_stats), eps, act,
+         wp.data_ptr(), _p(bias), _p(residual), 0 if residual is None else residual.shape[-1], r_coff,
+         y.data_ptr(), Cout, 0, _p(y_stats),
+         _p(gx), gld, gcoff or 0, _p(gstats), eps, gact,
+         B, D, H, W, Cin, Cout, ksize[0], ksize[1], ksize[2], _dt(x), algo, _stream())
+    return y, y_stats
+
+
+def conv3d_wgrad(x, x_coff, Cin, x_stats, act, dy, dy_coff, Cout, ksize, want_bias=False,
+                 algo=ALGO_AUTO, eps=IN_EPS):
+    B, D, H, W, x_ld = x.shape
+    dw = torch.zeros(Cout, Cin, ksize[0], ksize[1], ksize[2], dtype=torch.float32, device=x.device)
+    db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    call("b200seg_conv3d_wgrad", x.data_ptr(), x_ld, x_coff, _p(x_stats), eps, act,
+         dy.data_ptr(), dy.shape[-1], dy_coff, dw.data_ptr(), _p(db),
+         B, D, H, W, Cin, Cout, ksize[0], ksize[1], ksize[2], _dt(x), algo, _stream())
+    return dw, db
+
+
+def in_bwd_apply(g, x, x_coff, C, x_stats, bstats, add=None, add_coff=0, out=None, out_coff=0, eps=IN_EPS):
+    """dx = rstd*(g - S1/n - xhat*S2/n) (+ add); g is [B,D,H,W,C] dense."""
+    B, D, H, W, _ = x.shape
+    V = D * H * W
+    if out is None:
+        out = torch.empty(B, D, H, W, C, dtype=x.dtype, device=x.device)
+    call("b200seg_instnorm_bwd_apply", g.data_ptr(), g.shape[-1], 0, x.data_ptr(), x.shape[-1], x_coff, _dt(x),
+         x_stats.data_ptr(), bstats.data_ptr(), eps,
+         _p(add), 0 if add is None else add.shape[-1], add_coff,
+         out.data_ptr(), out.shape[-1], out_coff, B, V, C, _stream())
+    return out
+
+
+def copy_channels(x, x_coff, y, y_coff, C, accumulate=False):
+    nvox = x.numel() // x.shape[-1]
+    call("b200seg_copy_channels", x.data_ptr(), _dt(x), x.shape[-1], x_coff, y.data_ptr(), _dt(y), y.shape[-1],
+         y_coff, 1 if accumulate else 0, nvox, C, _stream())
+    return y
+
+
+def instnorm_stats(x, x_coff, C):
+    B, D, H, W, ld = x.shape
+    st = new_stats(B, C, x.device)
+    call("b200seg_instnorm_stats", x.data_ptr(), _dt(x), ld, x_coff, B, D * H * W, C, st.data_ptr(), _stream())
+    return st
+
+
+# ----------------------------------------------------------------------------- weight cache
+class PackedWeights:
+    """Per-module cache of packed (fwd and dgrad) weights, keyed on the parameters' version counters so a
+    repack happens once per optimiser step, not once per use (SURVEY.md §8b "Ownership")."""
+
+    def __init__(self):
+        self._key = None
+        self._fwd = None
+        self._bwd = None
+
+    def get(self, weights, dtype):
+        key = (dtype,) + tuple((w.data_ptr(), w._version) for w in weights)
+        if key != self._key:
+            co_total = sum(w.shape[0] for w in weights)
+            Cin = weights[0].shape[1]
+            taps = weights[0][0, 0].numel()
+            dev = weights[0].device
+            fwd = torch.empty(taps * co_total * Cin, dtype=dtype, device=dev)
+            bwd = torch.empty(taps * co_total * Cin, dtype=dtype, device=dev)
+            off = 0
+            for w in weights:
+                pack_weight(w, dtype, False, fwd, off, co_total)
+                pack_weight(w, dtype, True, bwd, off, co_total)
+                off += w.shape[0]
+            self._key, self._fwd, self._bwd = key, fwd, bwd
+        return self._fwd, self._bwd
+
+
+# ----------------------------------------------------------------------------- autograd Functions
+class StemConvFn(torch.autograd.Function):
+    """Raw conv (no norm/act on the input) + IN sums of the output: `inconv.conv1`, unet_utils.py:14,18."""
+
+    @staticmethod
+    def forward(ctx, x, w, wp_fwd, ksize):
+        Cout, Cin = w.shape[0], w.shape[1]
+        y, st = conv3d_fwd(x, 0, Cin, None, ACT_NONE, wp_fwd, Cout, ksize)
+        ctx.save_for_backward(x)
+        ctx.meta = (Cin, Cout, ksize, x.requires_grad)
+        ctx.mark_non_differentiable(st)
+        return y, st
+
+    @staticmethod
+    def backward(ctx, dy, _):
+        (x,) = ctx.saved_tensors
+        Cin, Cout, ksize, _xg = ctx.meta
+        dy = dy.contiguous()
+        dw, _ = conv3d_wgrad(x, 0, Cin, None, ACT_NONE, dy, 0, Cout, ksize)
+        # the network input needs no gradient ("minus dgrad of the stem")
+        return None, dw, None, None
+
+
+class BasicBlockFn(torch.autograd.Function):
+    """Pre-activation residual block, conv_layers.py:71-94:
+         out = conv2(relu(IN(conv1(relu(IN(x)))))) + shortcut(x)
+       shortcut = identity, or conv(relu(IN(x))) sharing conv1's normalised input -> one fused GEMM of
+       width 2*Cout (conv_layers.py:79,84).  Forward = 2 conv launches; IN normalise+ReLU live in the
+       conv loaders, residual add and the next layer's IN sums in the conv epilogues."""
+
+    @staticmethod
+    def forward(ctx, x, x_stats, w1, w2, wsc, packs, ksize, x_coff, Cin):
+        Cout = w1.shape[0]
+        has_sc = wsc is not None
+        (wf_fwd, wf_bwd), (w2_fwd, w2_bwd) = packs
+        Cf = 2 * Cout if has_sc else Cout
+        ts, ts_stats = conv3d_fwd(x, x_coff, Cin, x_stats, ACT_RELU, wf_fwd, Cf, ksize)
+        t1_stats = ts_stats[:, :Cout].contiguous() if has_sc else ts_stats
+        if has_sc:
+            out, out_stats = conv3d_fwd(ts, 0, Cout, t1_stats, ACT_RELU, w2_fwd, Cout, ksize, residual=ts, r_coff=Cout)
+        else:
+            out, out_stats = conv3d_fwd(ts, 0, Cout, t1_stats, ACT_RELU, w2_fwd, Cout, ksize, residual=x, r_coff=x_coff)
+        ctx.save_for_backward(x, x_stats, ts, t1_stats, wf_bwd, w2_bwd)
+        ctx.meta = (Cin, Cout, ksize, x_coff, has_sc)
+        ctx.mark_non_differentiable(out_stats)
+        return out, out_stats
+
+    @staticmethod
+    def backward(ctx, d_out, _):
+        x, x_stats, ts, t1_stats, wf_bwd, w2_bwd = ctx.saved_tensors
+        Cin, Cout, ksize, x_coff, has_sc = ctx.meta
+        d_out = d_out.contiguous()
+        B, D, H, W, _ = d_out.shape
+        # ---- conv2: out = conv(relu(IN(t1))) + shortcut
+        dw2, _ = conv3d_wgrad(ts, 0, Cout, t1_stats, ACT_RELU, d_out, 0, Cout, ksize)
+        g2, b2 = conv3d_fwd(d_out, 0, Cout, None, ACT_NONE, w2_bwd, Cout, ksize,
+                            dgrad_of=(ts, 0, t1_stats, ACT_RELU))
+        if has_sc:
+            d_ts = torch.empty(B, D, H, W, 2 * Cout, dtype=d_out.dtype, device=d_out.device)
+            in_bwd_apply(g2, ts, 0, Cout, t1_stats, b2, out=d_ts, out_coff=0)
+            copy_channels(d_out, 0, d_ts, Cout, Cout)
+            Cf = 2 * Cout
+        else:
+            d_ts = in_bwd_apply(g2, ts, 0, Cout, t1_stats, b2)
+            Cf = Cout
+        del g2
+        # ---- fused conv1 (+shortcut): ts = conv(relu(IN(x)))
+        dwf, _ = conv3d_wgrad(x, x_coff, Cin, x_stats, ACT_RELU, d_ts, 0, Cf, ksize)
+        g1, b1 = conv3d_fwd(d_ts, 0, Cf, None, ACT_NONE, wf_bwd, Cin, ksize,
+                            dgrad_of=(x, x_coff, x_stats, ACT_RELU))
+        if has_sc:
+            dx = in_bwd_apply(g1, x, x_coff, Cin, x_stats, b1)
+            dw1, dwsc = dwf[:Cout], dwf[Cout:]
+        else:
+            dx = in_bwd_apply(g1, x, x_coff, Cin, x_stats, b1, add=d_out, add_coff=0)
+            dw1, dwsc = dwf, None
+        if x.shape[-1] != Cin:
+            # x was a channel slice of a wider tensor: scatter the gradient back into that frame
+            full = torch.zeros_like(x)
+            copy_channels(dx, 0, full, x_coff, Cin)
+            dx = full
+        return dx, None, dw1, dw2, dwsc, None, None, None, None
+
+
+class SingleConvFn(torch.autograd.Function):
+    """SingleConv (post-activation), conv_layers.py:46-53,56-68: y = relu(IN(conv(x))).  The raw conv output
+    and its IN sums are kept; the normalise+ReLU is materialised by one elementwise kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, packs, ksize, x_coff, Cin):
+        Cout = w.shape[0]
+        w_fwd, w_bwd = packs
+        r, r_stats = conv3d_fwd(x, x_coff, Cin, None, ACT_NONE, w_fwd, Cout, ksize)
+        B, D, H, W, _ = r.shape
+        y = torch.empty_like(r)
+        call("b200seg_instnorm_apply", r.data_ptr(), _dt(r), Cout, 0, r_stats.data_ptr(), IN_EPS, ACT_RELU,
+             y.data_ptr(), Cout, 0, B, D * H * W, Cout, _stream())
+        ctx.save_for_backward(x, r, r_stats, w_bwd)
+        ctx.meta = (Cin, Cout, ksize, x_coff, x.requires_grad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, r, r_stats, w_bwd = ctx.saved_tensors
+        Cin, Cout, ksize, x_coff, need_dx = ctx.meta
+        dy = dy.contiguous()
+        B, D, H, W, _ = dy.shape
+        V = D * H * W
+        g = torch.empty_like(r)
+        bst = new_stats(B, Cout, r.device)
+        call("b200seg_instnorm_bwd_reduce", dy.data_ptr(), Cout, 0, r.data_ptr(), Cout, 0, _dt(r),
+             r_stats.data_ptr(), IN_EPS, ACT_RELU, g.data_ptr(), Cout, 0, bst.data_ptr(), B, V, Cout, _stream())
+        dr = in_bwd_apply(g, r, 0, Cout, r_stats, bst)
+        dw, _ = conv3d_wgrad(x, x_coff, Cin, None, ACT_NONE, dr, 0, Cout, ksize)
+        dx = None
+        if need_dx:
+            dx, _ = conv3d_fwd(dr, 0, Cout, None, ACT_NONE, w_bwd, Cin, ksize, want_stats=False)
+            if x.shape[-1] != Cin:
+                full = torch.zeros_like(x)
+                copy_channels(dx, 0, full, x_coff, Cin)
+                dx = full
+        return dx, dw, None, None, None, None
+
+
+class MaxPoolFn(torch.autograd.Function):
+    """nn.MaxPool3d(scale) (kernel == stride), unet_utils.py:36, + IN sums of the pooled tensor."""
+
+    @staticmethod
+    def forward(ctx, x, scale, want_stats):
+        _need_cuda(x)
+        B, D, H, W, C = x.shape
+        sd, sh, sw = scale
+        Do, Ho, Wo = D // sd, H // sh, W // sw
+        y = torch.empty(B, Do, Ho, Wo, C, dtype=x.dtype, device=x.device)
+        idx = torch.empty(B, Do, Ho, Wo, C, dtype=torch.uint8, device=x.device)
+        st = new_stats(B, C, x.device) if want_stats else None
+        call("b200seg_maxpool3d_fwd", x.data_ptr(), C, 0, y.data_ptr(), C, 0, idx.data_ptr(), _p(st),
+             B, D, H, W, C, sd, sh, sw, _dt(x), _stream())
+        ctx.save_for_backward(idx)
+        ctx.meta = (B, D, H, W, C, scale)
+        if st is None:
+            st = torch.empty(0, device=x.device)
+        ctx.mark_non_differentiable(st)
+        return y, st
+
+    @staticmethod
+    def backward(ctx, dy, _):
+        (idx,) = ctx.saved_tensors
+        B, D, H, W, C, (sd, sh, sw) = ctx.meta
+        dy = dy.contiguous()
+        exact = (D % sd == 0) and (H % sh == 0) and (W % sw == 0)
+        dx = (torch.empty if exact else torch.zeros)(B, D, H, W, C, dtype=dy.dtype, device=dy.device)
+        call("b200seg_maxpool3d_bwd", dy.data_ptr(), C, 0, idx.data_ptr(), dx.data_ptr(), C, 0,
+             B, D, H, W, C, sd, sh, sw, _dt(dy), _stream())
+        return dx, None, None
+
+
+class UpCatFn(torch.autograd.Function):
+    """F.interpolate(x1, size=x2.shape, 'trilinear', align_corners=True) + cat([x2, x1]) (unet_utils.py:69-71)
+    written straight into one concat buffer, with the IN sums of the upsampled channels."""
+
+    @staticmethod
+    def forward(ctx, low, skip, skip_stats, skip_first):
+        _need_cuda(low)
+        B, Di, Hi, Wi, Cl = low.shape
+        _, Do, Ho, Wo, Cs = skip.shape
+        cat = torch.empty(B, Do, Ho, Wo, Cs + Cl, dtype=low.dtype, device=low.device)
+        s_off, u_off = (0, Cs) if skip_first else (Cl, 0)
+        copy_channels(skip, 0, cat, s_off, Cs)
+        up_stats = new_stats(B, Cl, low.device)
+        call("b200seg_upsample_trilinear_fwd", low.data_ptr(), Cl, 0, cat.data_ptr(), Cs + Cl, u_off,
+             up_stats.data_ptr(), B, Di, Hi, Wi, Do, Ho, Wo, Cl, _dt(low), _stream())
+        if skip_stats is None or skip_stats.numel() == 0:
+            skip_stats = instnorm_stats(skip, 0, Cs)
+        cat_stats = torch.cat([skip_stats, up_stats] if skip_first else [up_stats, skip_stats], dim=1).contiguous()
+        ctx.meta = (low.shape, skip.shape, s_off, u_off)
+        ctx.mark_non_differentiable(cat_stats)
+        return cat, cat_stats
+
+    @staticmethod
+    def backward(ctx, d_cat, _):
+        (B, Di, Hi, Wi, Cl), (_, Do, Ho, Wo, Cs), s_off, u_off = ctx.meta
+        d_cat = d_cat.contiguous()
+        d_skip = torch.empty(B, Do, Ho, Wo, Cs, dtype=d_cat.dtype, device=d_cat.device)
+        copy_channels(d_cat, s_off, d_skip, 0, Cs)
+        d_low = torch.empty(B, Di, Hi, Wi, Cl, dtype=d_cat.dtype, device=d_cat.device)
+        call("b200seg_upsample_trilinear_bwd", d_cat.data_ptr(), Cs + Cl, u_off, d_low.data_ptr(), Cl, 0, 0,
+             B, Di, Hi, Wi, Do, Ho, Wo, Cl, _dt(d_cat), _stream())
+        return d_low, d_skip, None, None
+
+
+class OutConvFn(torch.autograd.Function):
+    """1x1x1 conv with bias on the raw block output: `outc`, unet.py:47,62."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, packs):
+        w_fwd, w_bwd = packs
+        Cout, Cin = w.shape[0], w.shape[1]
+        y, _ = conv3d_fwd(x, 0, Cin, None, ACT_NONE, w_fwd, Cout, (1, 1, 1), bias=bias, want_stats=False)
+        ctx.save_for_backward(x, w_bwd)
+        ctx.meta = (Cin, Cout)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_bwd = ctx.saved_tensors
+        Cin, Cout = ctx.meta
+        dy = dy.contiguous()
+        dw, db = conv3d_wgrad(x, 0, Cin, None, ACT_NONE, dy, 0, Cout, (1, 1, 1), want_bias=True)
+        dx, _ = conv3d_fwd(dy, 0, Cout, None, ACT_NONE, w_bwd, Cin, (1, 1, 1), want_stats=False)
+        return dx, dw, db, None
+
+
+class DiceCEFn(torch.autograd.Function):
+    """ce_scale*CrossEntropy(weight) + dice_scale*DiceLoss in one pass each way
+    (training/losses.py:18-58, train_ddp.py:93,186-191)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, weight, ce_scale, dice_scale):
+        _need_cuda(logits)
+        if logits.dtype not in (torch.float16, torch.float32):
+            logits = logits.float()
+        B, C = logits.shape[0], logits.shape[1]
+        V = logits[0, 0].numel()
+        # accept both NCDHW-contiguous and channels-last (our model's output view) without copying
+        lg = logits
+        flat = lg.reshape(B, C, V) if lg.is_contiguous() else None
+        if flat is not None:
+            sb, sc, sv = C * V, V, 1
+        else:
+            perm = lg.permute(0, *range(2, lg.dim()), 1)
+            if not perm.is_contiguous():
+                lg = lg.contiguous()
+                sb, sc, sv = C * V, V, 1
+            else:
+                sb, sc, sv = C * V, 1, C
+        if labels.dtype == torch.int64:
+            lb = 8
+        elif labels.dtype == torch.uint8:
+            lb = 1
+        else:
+            labels = labels.long()
+            lb = 8
+        labels = labels.contiguous()
+        if labels.numel() != B * V:
+            raise ValueError("labels must have B*V elements")
+        dev = logits.device
+        partial = torch.empty(3 * C + 2, dtype=torch.float64, device=dev)
+        out = torch.empty(4 + 4 * C, dtype=torch.float32, device=dev)
+        wt = None if weight is None else weight.to(device=dev, dtype=torch.float32).contiguous()
+        call("b200seg_dice_ce_fwd", lg.data_ptr(), _dt(lg), sb, sv, sc, labels.data_ptr(), lb, _p(wt),
+             B, V, C, float(ce_scale), float(dice_scale), partial.data_ptr(), out.data_ptr(), _stream())
+        ctx.save_for_backward(lg, labels, out, wt if wt is not None else torch.empty(0, device=dev))
+        ctx.meta = (B, V, C, sb, sv, sc, lb, float(ce_scale), float(dice_scale), wt is not None, logits.shape)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        lg, labels, out, wt = ctx.saved_tensors
+        B, V, C, sb, sv, sc, lb, ce_scale, dice_scale, has_w, shape = ctx.meta
+        d = torch.empty_like(lg)  # preserves strides (channels-last or contiguous)
+        gg = g.detach().to(torch.float32).contiguous()
+        call("b200seg_dice_ce_bwd", lg.data_ptr(), _dt(lg), sb, sv, sc, labels.data_ptr(), lb,
+             wt.data_ptr() if has_w else None, B, V, C, ce_scale, dice_scale, out.data_ptr(), gg.data_ptr(),
+             d.data_ptr(), _stream())
+        return d.view(shape) if d.shape != shape else d, None, None, None, None

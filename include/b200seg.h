@@ -1,0 +1,212 @@
+/*
+ * b200seg.h — C ABI of libb200seg.so: the B200 (sm_100a) kernels behind the
+ * 3D-segmentation training hot path of yhygao/CBIM-Medical-Image-Segmentation.
+ *
+ * The reference has NO native interface (it is 100% Python): every
+ * entry point below replaces a *library call site* in the reference, cited as
+ * reference file:line.  All pointers are DEVICE pointers owned by the caller
+ * (PyTorch's caching allocator in the drop-in); kernels never allocate, free,
+ * or keep a pointer past return.  Every call takes the CUDA stream to launch on
+ * (as a void* holding a cudaStream_t) and returns 0 on success or a negative
+ * B200SEG_E* code; b200seg_strerror() maps codes to text.  No entry point
+ * synchronises the host.
+ *
+ * Layout conventions
+ *   activations : NDHWC ("channels-last-3d"), element (b,d,h,w,c) of a tensor
+ *                 with leading dimension `ld` (channels physically stored per
+ *                 voxel) and channel offset `coff` lives at
+ *                 base[(((b*D+d)*H+h)*W+w)*ld + coff + c]            (c < C)
+ *   dtype       : B200SEG_F32 (0) or B200SEG_F16 (1) storage; accumulation is
+ *                 always fp32 (tcgen05 kind::f16 or FFMA).
+ *   stats       : per-(batch,channel) InstanceNorm sums, double[B][C][2] =
+ *                 {sum, sum of squares} over D*H*W.  Producers ACCUMULATE into
+ *                 them (caller zeroes first); consumers derive mean / rstd.
+ *   weights     : "packed" conv weights, [taps][Cout][Cin] in the activation
+ *                 dtype, tap = (kd_i*kh + kh_i)*kw + kw_i; produced from the
+ *                 reference's [Cout][Cin][kd][kh][kw] fp32 parameter by
+ *                 b200seg_pack_weight (optionally flipped+transposed for dgrad).
+ */
+#ifndef B200SEG_H
+#define B200SEG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SEG_VERSION 100
+
+enum { B200SEG_F32 = 0, B200SEG_F16 = 1 };
+
+enum {
+  B200SEG_OK = 0,
+  B200SEG_EINVAL = -1,      /* bad argument (null pointer, non-positive dim, bad dtype)      */
+  B200SEG_EUNSUPPORTED = -2,/* shape not supported by the requested algorithm (hard error)   */
+  B200SEG_ECUDA = -3,       /* a CUDA runtime call failed (see b200seg_last_cuda_error)      */
+  B200SEG_ENODEVICE = -4    /* device is not sm_100 (this library has no fallback)           */
+};
+
+/* conv algorithms: AUTO picks TC when the shape qualifies, else DIRECT. */
+enum { B200SEG_ALGO_AUTO = 0, B200SEG_ALGO_DIRECT = 1, B200SEG_ALGO_TC = 2 };
+
+/* activation applied to the (optionally normalised) conv input in the loader */
+enum { B200SEG_ACT_NONE = 0, B200SEG_ACT_RELU = 1 };
+
+int         b200seg_version(void);
+const char* b200seg_strerror(int code);
+const char* b200seg_last_cuda_error(void);
+/* 0 if the current device can run this library (compute capability 10.x). */
+int         b200seg_check_device(void);
+
+/* ---------------------------------------------------------------------------
+ * Fused softmax + adaptive-Tversky Dice + weighted cross-entropy.
+ * Replaces training/losses.py:18-58 (DiceLoss.forward), nn.CrossEntropyLoss at
+ * train_ddp.py:93,189-191 and the sum at train_ddp.py:186-191.
+ *
+ * logits element (b,v,c) is at logits[b*stride_b + v*stride_v + c*stride_c]
+ * (NCDHW: stride_c=V, stride_v=1; NDHWC: stride_c=1, stride_v=C).
+ * labels: int64 (label_bytes=8) or uint8 (label_bytes=1), [B][V].
+ * ce_weight: float[C] or NULL (=ones).  partial: double[3*C+2] scratch, zeroed
+ * by the call itself.  out: float[4+4*C]:
+ *   out[0]=ce_scale*CE + dice_scale*Dice, out[1]=CE, out[2]=Dice, out[3]=sum_w,
+ *   out[4+c]      = dDice/dTP_c (total derivative, alpha kept differentiable)
+ *   out[4+C+c]    = dDice/dSP_c
+ *   out[4+2C+c]   = alpha_c,  out[4+3C+c] = dice_c
+ * ------------------------------------------------------------------------- */
+int b200seg_dice_ce_fwd(const void* logits, int dtype,
+                        int64_t stride_b, int64_t stride_v, int64_t stride_c,
+                        const void* labels, int label_bytes,
+                        const float* ce_weight,
+                        int B, int64_t V, int C,
+                        float ce_scale, float dice_scale,
+                        double* partial, float* out, void* stream);
+
+/* dlogits gets the same strides as logits.  grad_out: device float scalar
+ * (upstream gradient, e.g. GradScaler's scale) or NULL (=1). */
+int b200seg_dice_ce_bwd(const void* logits, int dtype,
+                        int64_t stride_b, int64_t stride_v, int64_t stride_c,
+                        const void* labels, int label_bytes,
+                        const float* ce_weight,
+                        int B, int64_t V, int C,
+                        float ce_scale, float dice_scale,
+                        const float* fwd_out, const float* grad_out,
+                        void* dlogits, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * InstanceNorm statistics (nn.InstanceNorm3d, conv_layers.py:40,42 — the
+ * reduction half).  Accumulates {sum, sumsq} of x[..., coff:coff+C] into
+ * stats[B][C][2].
+ * ------------------------------------------------------------------------- */
+int b200seg_instnorm_stats(const void* x, int dtype, int ld, int coff,
+                           int B, int64_t V, int C, double* stats, void* stream);
+
+/* y = act((x - mean) * rstd), materialised (used where the normalise cannot be
+ * folded into a consumer's loader: SingleConv post-activation, conv_layers.py:46-53). */
+int b200seg_instnorm_apply(const void* x, int dtype, int x_ld, int x_coff,
+                           const double* stats, float eps, int act,
+                           void* y, int y_ld, int y_coff,
+                           int B, int64_t V, int C, void* stream);
+
+/* Backward of y = act(IN(x)), stage 1: g = dy * act'(xhat); accumulates
+ * bstats[B][C][2] += {sum g, sum g*xhat}; writes g.  */
+int b200seg_instnorm_bwd_reduce(const void* dy, int dy_ld, int dy_coff,
+                                const void* x, int x_ld, int x_coff, int dtype,
+                                const double* stats, float eps, int act,
+                                void* g, int g_ld, int g_coff,
+                                double* bstats, int B, int64_t V, int C, void* stream);
+
+/* Stage 2: dx = rstd * (g - S1/n - xhat*S2/n) (+ add).  `add` (nullable, may
+ * alias dx) carries a gradient arriving over another branch, e.g. the identity
+ * residual of a BasicBlock (conv_layers.py:92). */
+int b200seg_instnorm_bwd_apply(const void* g, int g_ld, int g_coff,
+                               const void* x, int x_ld, int x_coff, int dtype,
+                               const double* stats, const double* bstats, float eps,
+                               const void* add, int add_ld, int add_coff,
+                               void* dx, int dx_ld, int dx_coff,
+                               int B, int64_t V, int C, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Conv3d family (nn.Conv3d call sites conv_layers.py:29-38, unet_utils.py:14,
+ * unet.py:47; autograd of same at train_ddp.py:193/208).  Stride 1, padding
+ * k/2, odd k, dilation 1, groups 1.
+ * ------------------------------------------------------------------------- */
+
+/* w_packed[tap][Cout][Cin] <- w[Cout][Cin][kd][kh][kw] (fp32 parameter).
+ * transpose_flip!=0 builds the dgrad operand instead:
+ *   w_packed[T-1-tap][Cin][Cout] (roles of Cin/Cout swapped, taps mirrored).
+ * co_off / co_total place this weight's output channels inside a wider fused
+ * weight (conv1+shortcut of a BasicBlock share one GEMM, conv_layers.py:79,84). */
+int b200seg_pack_weight(const float* w, int Cout, int Cin, int taps,
+                        void* w_packed, int dtype, int transpose_flip,
+                        int co_off, int co_total, void* stream);
+
+/* y[.., y_coff:y_coff+Cout] = conv(act(IN(x))) (+bias) (+residual); optionally
+ * accumulates InstanceNorm sums of the STORED y into y_stats.
+ *   x_stats==NULL  -> no normalisation of the input (raw conv, e.g. the stem)
+ *   residual==NULL -> no residual add (conv_layers.py:92 `out += shortcut`)
+ * When dgrad_x != NULL the call is the data-gradient of a pre-activation conv:
+ * the accumulator `da` is multiplied by act'(xhat(dgrad_x)) before the store
+ * and y_stats receives {sum g, sum g*xhat} instead (stage 1 of IN backward),
+ * with dgrad_stats the forward statistics of dgrad_x. */
+int b200seg_conv3d_fwd(const void* x, int x_ld, int x_coff,
+                       const double* x_stats, float eps, int act,
+                       const void* w_packed, const float* bias,
+                       const void* residual, int r_ld, int r_coff,
+                       void* y, int y_ld, int y_coff, double* y_stats,
+                       const void* dgrad_x, int dx_ld, int dx_coff,
+                       const double* dgrad_stats, float dgrad_eps, int dgrad_act,
+                       int B, int D, int H, int W, int Cin, int Cout,
+                       int kd, int kh, int kw, int dtype, int algo, void* stream);
+
+/* dw[Cout][Cin][kd][kh][kw] (fp32, the reference parameter layout, what DDP
+ * all-reduces) (+)= sum_vox dy[vox][co] * act(IN(x))[vox+tap][ci].
+ * dw must be zeroed by the caller unless accumulating.  dbias (float[Cout] or
+ * NULL) += sum_vox dy.  co_off/co_total select a channel slice of a fused dy. */
+int b200seg_conv3d_wgrad(const void* x, int x_ld, int x_coff,
+                         const double* x_stats, float eps, int act,
+                         const void* dy, int dy_ld, int dy_coff,
+                         float* dw, float* dbias,
+                         int B, int D, int H, int W, int Cin, int Cout,
+                         int kd, int kh, int kw, int dtype, int algo, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * MaxPool3d, kernel == stride (unet_utils.py:36), floor mode, + IN sums of the
+ * pooled tensor.  idx: uint8[B][Do][Ho][Wo][C] argmax offset inside the window.
+ * ------------------------------------------------------------------------- */
+int b200seg_maxpool3d_fwd(const void* x, int x_ld, int x_coff,
+                          void* y, int y_ld, int y_coff, uint8_t* idx, double* y_stats,
+                          int B, int D, int H, int W, int C, int sd, int sh, int sw,
+                          int dtype, void* stream);
+int b200seg_maxpool3d_bwd(const void* dy, int dy_ld, int dy_coff, const uint8_t* idx,
+                          void* dx, int dx_ld, int dx_coff,
+                          int B, int D, int H, int W, int C, int sd, int sh, int sw,
+                          int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Trilinear upsample (align_corners=True) fused with the channel concat
+ * (unet_utils.py:69-71): y[.., y_coff:y_coff+C] = upsample(x) to (Do,Ho,Wo),
+ * + IN sums of the written channels.  bwd is a deterministic gather (no atomics):
+ * dx (+)= sum of the output-voxel gradients whose stencil touches each input voxel.
+ * ------------------------------------------------------------------------- */
+int b200seg_upsample_trilinear_fwd(const void* x, int x_ld, int x_coff,
+                                   void* y, int y_ld, int y_coff, double* y_stats,
+                                   int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
+                                   int C, int dtype, void* stream);
+int b200seg_upsample_trilinear_bwd(const void* dy, int dy_ld, int dy_coff,
+                                   void* dx, int dx_ld, int dx_coff, int accumulate,
+                                   int B, int Di, int Hi, int Wi,
+                                   int Do, int Ho, int Wo, int C, int dtype, void* stream);
+
+/* Strided channel-slice copy / cast / add:  y[..,y_coff+c] (+)= x[..,x_coff+c].
+ * x_dtype and y_dtype may differ (cast).  Used for concat of the skip tensor,
+ * NCDHW<->NDHWC boundary casts and gradient accumulation. */
+int b200seg_copy_channels(const void* x, int x_dtype, int x_ld, int x_coff,
+                          void* y, int y_dtype, int y_ld, int y_coff, int accumulate,
+                          int64_t nvox, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEG_H */

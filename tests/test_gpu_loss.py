@@ -1,0 +1,63 @@
+"""GPU: fused softmax+Dice+CE kernel vs the reference-pinned oracle and the reference's own fixtures."""
+import pytest
+import torch
+
+from oracle import losses as olosses
+from util import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["loss_a", "loss_b", "loss_c"])
+@pytest.mark.parametrize("layout", ["ncdhw", "channels_last"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("label_dtype", [torch.int64, torch.uint8])
+def test_dice_ce_matches_reference_fixture(name, layout, dtype, label_dtype):
+    import b200seg
+    g = load_golden(name)
+    xh = g["x"].to(dtype)
+    x = xh.cuda()
+    if layout == "channels_last":
+        x = x.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+    x.requires_grad_(True)
+    y = g["y"].to(label_dtype).cuda()
+    crit = b200seg.DiceCELoss(weight=g["w"])
+    loss = crit(x, y)
+    loss.backward()
+    # oracle on the SAME (possibly fp16-rounded) logits
+    xo = xh.float().requires_grad_(True)
+    lo = olosses.dice_loss(xo, g["y"]) + olosses.cross_entropy(xo, g["y"], g["w"])
+    lo.backward()
+    assert abs(loss.item() - lo.item()) < 2e-5
+    tol = 1e-4 if dtype == torch.float32 else 2e-3     # fp16: dlogits are stored in fp16
+    assert rel_err(x.grad.float(), xo.grad) < tol
+    if dtype == torch.float32:
+        assert abs(loss.item() - (g["dice"] + g["ce"])) < 2e-5        # the reference's own numbers
+        assert rel_err(x.grad, g["grad"]) < 1e-4
+    # DiceLoss-compatible shim alone
+    d = b200seg.DiceLoss()(x.detach(), y)
+    assert abs(d.item() - olosses.dice_loss(xh.float(), g["y"]).item()) < 2e-5
+
+
+def test_dice_ce_full_size_properties():
+    """BASELINE size (128^3, 4 classes, fp16 NDHWC): size-independent properties of the gradient."""
+    import b200seg
+    torch.manual_seed(0)
+    B, C, D = 1, 4, 128
+    x = (torch.randn(B, D, D, D, C, device="cuda") * 2).half().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    y = torch.randint(0, C, (B, 1, D, D, D), device="cuda")
+    w = torch.tensor([0.5, 1, 1, 1])
+    loss = b200seg.DiceCELoss(weight=w)(x, y)
+    loss.backward()
+    assert torch.isfinite(loss)
+    g = x.grad.float()
+    # softmax-Jacobian property: gradients of one voxel sum to zero over classes
+    assert g.sum(1).abs().max().item() < 1e-2 * g.abs().max().item()
+    # scaling the upstream gradient scales the result linearly (GradScaler path, device scalar)
+    x2 = x.detach().clone().requires_grad_(True)
+    (b200seg.DiceCELoss(weight=w)(x2, y) * 1024.0).backward()
+    assert rel_err(x2.grad.float() / 1024.0, g) < 2e-3
+    # a chunk of the volume against the oracle
+    xo = x.detach().float().cpu().requires_grad_(True)
+    lo = olosses.dice_loss(xo, y.cpu()) + olosses.cross_entropy(xo, y.cpu(), w)
+    assert abs(lo.item() - loss.item()) < 1e-4

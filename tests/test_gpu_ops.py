@@ -1,0 +1,121 @@
+"""GPU: each C-ABI op against a plain PyTorch fp32 CPU evaluation of the same maths (oracle side)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-4   # fp32 storage, fp32 accumulate
+TOL16 = 4e-3   # fp16 storage (one rounding of inputs/outputs), fp32 accumulate
+
+
+def ndhwc(t):   # [B,C,D,H,W] -> [B,D,H,W,C] contiguous
+    return t.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def ncdhw(t):
+    return t.permute(0, 4, 1, 2, 3).contiguous()
+
+
+def stats_of(x):  # x [B,C,...] -> [B,C,2] double
+    xd = x.double().flatten(2)
+    return torch.stack([xd.sum(-1), (xd * xd).sum(-1)], -1)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import b200seg
+    from b200seg import ops as o
+    assert o._lib.load().b200seg_check_device() == 0, "not a B200"
+    return o
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL32), (torch.float16, TOL16)])
+@pytest.mark.parametrize("C", [8, 32, 5])
+def test_instnorm_stats(ops, dtype, tol, C):
+    torch.manual_seed(0)
+    x = (torch.randn(2, C, 6, 10, 12) * 2 + 0.5).to(dtype)
+    st = ops.instnorm_stats(ndhwc(x).cuda(), 0, C)
+    assert rel_err(st, stats_of(x.float())) < 1e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL32), (torch.float16, TOL16)])
+@pytest.mark.parametrize("Cin,Cout,k", [(1, 8, (3, 3, 3)), (8, 16, (3, 3, 3)), (16, 8, (1, 3, 3)), (24, 4, (1, 1, 1)), (5, 7, (3, 3, 3))])
+def test_conv_fwd_preact_residual_stats(ops, dtype, tol, Cin, Cout, k):
+    torch.manual_seed(1)
+    B, D, H, W = 2, 6, 9, 11
+    x = torch.randn(B, Cin, D, H, W).to(dtype)
+    w = torch.randn(Cout, Cin, *k) * 0.2
+    res = torch.randn(B, Cout, D, H, W).to(dtype)
+    xc, rc = ndhwc(x).cuda(), ndhwc(res).cuda()
+    st = ops.instnorm_stats(xc, 0, Cin)
+    wp = ops.pack_weight(w.cuda(), dtype)
+    y, yst = ops.conv3d_fwd(xc, 0, Cin, st, ops.ACT_RELU, wp, Cout, k, residual=rc, algo=ops._lib.ALGO_DIRECT)
+    a = F.relu(F.instance_norm(x.float(), eps=1e-4)).to(dtype).float()
+    ref = F.conv3d(a, w.to(dtype).float(), padding=[i // 2 for i in k]).to(dtype).float() + res.float()
+    assert rel_err(ncdhw(y.float()), ref) < tol
+    assert rel_err(yst, stats_of(ncdhw(y.float().cpu()))) < 1e-5      # sums describe what was STORED
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL32), (torch.float16, TOL16)])
+@pytest.mark.parametrize("Cin,Cout,k", [(1, 8, (3, 3, 3)), (8, 16, (3, 3, 3)), (16, 8, (1, 3, 3)), (24, 4, (1, 1, 1))])
+def test_conv_wgrad_and_dgrad(ops, dtype, tol, Cin, Cout, k):
+    torch.manual_seed(2)
+    B, D, H, W = 2, 6, 8, 10
+    x = torch.randn(B, Cin, D, H, W).to(dtype).float().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, *k) * 0.2).to(dtype).float().requires_grad_(True)
+    dy = torch.randn(B, Cout, D, H, W).to(dtype).float()
+    a = F.relu(F.instance_norm(x, eps=1e-4))
+    y = F.conv3d(a, w, padding=[i // 2 for i in k])
+    y.backward(dy)
+    xc, dyc = ndhwc(x.detach().to(dtype)).cuda(), ndhwc(dy.to(dtype)).cuda()
+    st = ops.instnorm_stats(xc, 0, Cin)
+    dw, _ = ops.conv3d_wgrad(xc, 0, Cin, st, ops.ACT_RELU, dyc, 0, Cout, k, algo=ops._lib.ALGO_DIRECT)
+    assert rel_err(dw, w.grad) < max(tol, 2e-3 if dtype == torch.float16 else tol)
+    # data gradient incl. ReLU mask + both InstanceNorm-backward reductions
+    wpb = ops.pack_weight(w.detach().cuda(), dtype, transpose_flip=True)
+    g, bst = ops.conv3d_fwd(dyc, 0, Cout, None, ops.ACT_NONE, wpb, Cin, k, dgrad_of=(xc, 0, st, ops.ACT_RELU),
+                            algo=ops._lib.ALGO_DIRECT)
+    dx = ops.in_bwd_apply(g, xc, 0, Cin, st, bst)
+    assert rel_err(ncdhw(dx.float()), x.grad) < (2e-2 if dtype == torch.float16 else 1e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("scale", [(2, 2, 2), (1, 2, 2)])
+@pytest.mark.parametrize("C", [16, 3])
+def test_maxpool(ops, dtype, scale, C):
+    torch.manual_seed(3)
+    x = torch.randn(2, C, 8, 12, 10).to(dtype).float().requires_grad_(True)
+    y = F.max_pool3d(x, scale)
+    dy = torch.randn_like(y).to(dtype).float()
+    y.backward(dy)
+    xc = ndhwc(x.detach().to(dtype)).cuda().requires_grad_(True)
+    yo, st = ops.MaxPoolFn.apply(xc, scale, True)
+    assert torch.equal(ncdhw(yo.detach().float().cpu()), y.detach())
+    assert rel_err(st, stats_of(y.detach())) < 1e-5
+    yo.backward(ndhwc(dy.to(dtype)).cuda())
+    assert torch.equal(ncdhw(xc.grad.float().cpu()), x.grad)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("shp", [((4, 5, 6), (8, 10, 12)), ((8, 3, 5), (8, 6, 10)), ((3, 3, 3), (7, 5, 6))])
+def test_upsample_cat(ops, dtype, tol, shp):
+    torch.manual_seed(4)
+    (Di, Hi, Wi), (Do, Ho, Wo) = shp
+    Cl, Cs = 16, 8
+    low = torch.randn(2, Cl, Di, Hi, Wi).to(dtype).float().requires_grad_(True)
+    skip = torch.randn(2, Cs, Do, Ho, Wo).to(dtype).float().requires_grad_(True)
+    up = F.interpolate(low, size=(Do, Ho, Wo), mode="trilinear", align_corners=True)
+    cat = torch.cat([skip, up], 1)
+    dcat = torch.randn_like(cat).to(dtype).float()
+    cat.backward(dcat)
+    lc = ndhwc(low.detach().to(dtype)).cuda().requires_grad_(True)
+    sc = ndhwc(skip.detach().to(dtype)).cuda().requires_grad_(True)
+    co, cst = ops.UpCatFn.apply(lc, sc, None, True)
+    assert rel_err(ncdhw(co.detach().float()), cat.detach()) < tol
+    assert rel_err(cst, stats_of(ncdhw(co.detach().float().cpu()))) < 1e-5
+    co.backward(ndhwc(dcat.to(dtype)).cuda())
+    assert rel_err(ncdhw(lc.grad.float()), low.grad) < max(tol, 1e-5) * 2
+    assert rel_err(ncdhw(sc.grad.float()), skip.grad) < 1e-6

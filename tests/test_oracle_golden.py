@@ -1,0 +1,59 @@
+"""CPU: the oracle restatement reproduces the fixtures generated from the real reference
+(oracle/make_golden.py).  This is what pins the oracle on machines without /root/reference."""
+import pytest
+import torch
+
+from oracle import losses as olosses
+from oracle import unet3d as ounet
+from oracle.synth import make_volume
+from util import load_golden, rel_err
+
+
+@pytest.mark.parametrize("name", ["resunet_iso", "resunet_acdc", "unet_single"])
+def test_unet_oracle_matches_reference_fixture(name):
+    g = load_golden(name)
+    cfg = g["cfg"]
+    shapes = ounet.unet_param_shapes(1, cfg["base"], cfg["classes"], cfg["kernel"], cfg["block"])
+    assert list(shapes) == g["keys"]
+    sd = {k: v.requires_grad_(True) for k, v in ounet.make_state_dict(shapes, seed=cfg["state_seed"]).items()}
+    img, lab = make_volume(*cfg["shape"], cfg["classes"], seed=cfg["data_seed"])
+    torch.set_num_threads(8)
+    logits = ounet.unet_forward(sd, img, cfg["scale"], cfg["kernel"], cfg["block"])
+    w = torch.tensor(cfg["ce_weight"], dtype=torch.float32)
+    loss = olosses.total_loss(logits, lab, w)
+    loss.backward()
+    assert rel_err(logits, g["logits"].float()) < 2e-3          # fixture logits are stored in fp16
+    assert torch.equal(logits.argmax(1).to(torch.uint8), g["argmax"])
+    assert abs(loss.item() - g["loss"]) < 1e-5
+    for k in g["grad_small"]:
+        assert rel_err(sd[k].grad, g["grad_small"][k]) < 1e-4, k
+    for k, d in g["grad_digest"].items():
+        gs = sd[k].grad.double()
+        assert abs(gs.abs().sum().item() - d["abs"]) <= 1e-4 * d["abs"] + 1e-12, k
+
+
+@pytest.mark.parametrize("name", ["loss_a", "loss_b", "loss_c"])
+def test_loss_oracle_matches_reference_fixture(name):
+    g = load_golden(name)
+    x = g["x"].clone().requires_grad_(True)
+    d = olosses.dice_loss(x, g["y"])
+    c = olosses.cross_entropy(x, g["y"], g["w"])
+    (d + c).backward()
+    assert abs(d.item() - g["dice"]) < 1e-6
+    assert abs(c.item() - g["ce"]) < 1e-6
+    assert rel_err(x.grad, g["grad"]) < 1e-5
+
+
+def test_dice_alpha_is_differentiable():
+    """Detaching alpha changes the gradient — the oracle must keep it attached."""
+    g = load_golden("loss_a")
+    x = g["x"].clone().requires_grad_(True)
+    olosses.dice_loss(x, g["y"]).backward()
+    ga = x.grad.clone()
+    # finite-difference check of one logit
+    with torch.no_grad():
+        e = torch.zeros_like(x)
+        e.view(-1)[17] = 1e-3
+        xd = x.detach().double()
+        fd = (olosses.dice_loss(xd + e.double(), g["y"]) - olosses.dice_loss(xd - e.double(), g["y"])) / 2e-3
+    assert abs(fd.item() - ga.view(-1)[17].item()) < 5e-3 * abs(fd.item()) + 1e-9
