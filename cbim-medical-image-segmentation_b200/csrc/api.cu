@@ -38,6 +38,11 @@ extern "C" int b200seg_check_device(void) {
   return major == 10 ? B200SEG_OK : B200SEG_ENODEVICE;
 }
 
+extern "C" int b200seg_conv3d_algo(int Cin, int Cout, int kd, int kh, int kw, int dtype, int B) {
+  if (conv3d_tc_shape_ok(Cin, Cout, kd, kh, kw, dtype) && B * Cin <= 4096 && B * Cout <= 2048) return B200SEG_ALGO_TC;
+  return B200SEG_ALGO_DIRECT;
+}
+
 extern "C" int b200seg_conv3d_fwd(const void* x, int x_ld, int x_coff, const double* x_stats, float eps, int act,
                                   const void* w_packed, const float* bias, const void* residual, int r_ld,
                                   int r_coff, void* y, int y_ld, int y_coff, double* y_stats,
@@ -52,9 +57,9 @@ extern "C" int b200seg_conv3d_fwd(const void* x, int x_ld, int x_coff, const dou
   ConvArgs a{x, x_ld, x_coff, x_stats, eps, act, w_packed, bias, residual, r_ld, r_coff, y, y_ld, y_coff, y_stats,
              dgrad_x, dx_ld, dx_coff, dgrad_stats, dgrad_eps, dgrad_act, B, D, H, W, Cin, Cout, kd, kh, kw};
   cudaStream_t st = as_stream(stream);
+  // the packed-weight layout differs per algorithm, so the caller must name one (b200seg_conv3d_algo)
   if (algo == B200SEG_ALGO_TC) return conv3d_fwd_tc(a, dtype, st);
-  if (algo == B200SEG_ALGO_AUTO && conv3d_fwd_tc_supported(a, dtype)) return conv3d_fwd_tc(a, dtype, st);
-  if (algo != B200SEG_ALGO_AUTO && algo != B200SEG_ALGO_DIRECT) return B200SEG_EINVAL;
+  if (algo != B200SEG_ALGO_DIRECT) return B200SEG_EINVAL;
   return conv3d_fwd_direct(a, dtype, st);
 }
 

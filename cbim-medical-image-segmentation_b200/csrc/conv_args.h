@@ -28,3 +28,21 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st);
 int conv3d_wgrad_tc(const WgradArgs& a, int dtype, cudaStream_t st);
 bool conv3d_fwd_tc_supported(const ConvArgs& a, int dtype);
 bool conv3d_wgrad_tc_supported(const WgradArgs& a, int dtype);
+
+// ---- tcgen05 tiling choices shared by the packer and the kernels
+// N tile (output channels per CTA tile): whole Cout when <=256, else the largest even split.
+__host__ __device__ static inline int tc_pick_nt(int Cout) {
+  if (Cout % 16) return 0;
+  if (Cout <= 256) return Cout;
+  for (int t = (Cout + 255) / 256; t <= 16; ++t)
+    if (Cout % t == 0 && (Cout / t) % 16 == 0 && Cout / t <= 256) return Cout / t;
+  return 0;
+}
+// K chunk (input channels per staged halo tile): largest multiple of 16 dividing Cin, <= 64.
+__host__ __device__ static inline int tc_pick_kc(int Cin) {
+  if (Cin % 16) return 0;
+  for (int kc = 64; kc >= 16; kc -= 16)
+    if (Cin % kc == 0) return kc;
+  return 0;
+}
+bool conv3d_tc_shape_ok(int Cin, int Cout, int kd, int kh, int kw, int dtype);

@@ -231,14 +231,25 @@ conv_wgrad_direct_kernel(WgradArgs a) {
 
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, T* __restrict__ wp,
-                                   int transpose_flip, int co_off, int co_total) {
+                                   int transpose_flip, int co_off, int co_total, int layout_tc) {
   int64_t n = (int64_t)Cout * Cin * taps;
+  // virtual packed tensor [taps][R][Cc]: fwd: R = co_total rows (cout), Cc = Cin cols; dgrad operand: R = Cin, Cc = co_total
+  const int R = transpose_flip ? Cin : co_total, Cc = transpose_flip ? co_total : Cin;
+  const int NT = layout_tc ? tc_pick_nt(R) : 1, KC = layout_tc ? tc_pick_kc(Cc) : 1;
+  const int NKC = layout_tc ? Cc / KC : 1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int tap = (int)(i % taps); int64_t t = i / taps; int ci = (int)(t % Cin); int co = (int)(t / Cin);
     float v = w[i];
+    const int tp = transpose_flip ? taps - 1 - tap : tap;
+    const int row = transpose_flip ? ci : co_off + co;
+    const int col = transpose_flip ? co_off + co : ci;
     int64_t o;
-    if (!transpose_flip) o = ((int64_t)tap * co_total + co_off + co) * Cin + ci;              // [tap][Cout_total][Cin]
-    else o = ((int64_t)(taps - 1 - tap) * Cin + ci) * co_total + co_off + co;                  // [tap'][Cin][Cout_total]
+    if (!layout_tc) {
+      o = ((int64_t)tp * R + row) * Cc + col;
+    } else {
+      const int ntile = row / NT, nn = row % NT, kc = col / KC, kk = col % KC, k8 = kk >> 3, e = kk & 7;
+      o = ((((int64_t)(ntile * taps + tp) * NKC + kc) * (KC / 8) + k8) * NT + nn) * 8 + e;
+    }
     Elem<T>::st(wp + o, v);
   }
 }
@@ -289,13 +300,19 @@ int conv3d_wgrad_direct(const WgradArgs& a_in, int dtype, cudaStream_t st) {
 }
 
 extern "C" int b200seg_pack_weight(const float* w, int Cout, int Cin, int taps, void* w_packed, int dtype,
-                                   int transpose_flip, int co_off, int co_total, void* stream) {
+                                   int transpose_flip, int co_off, int co_total, int layout, void* stream) {
   if (!w || !w_packed || Cout <= 0 || Cin <= 0 || taps <= 0 || co_off < 0 || co_off + Cout > co_total) return B200SEG_EINVAL;
+  if (layout != B200SEG_ALGO_DIRECT && layout != B200SEG_ALGO_TC) return B200SEG_EINVAL;
+  const int tc = layout == B200SEG_ALGO_TC;
+  if (tc) {
+    const int R = transpose_flip ? Cin : co_total, Cc = transpose_flip ? co_total : Cin;
+    if (!tc_pick_nt(R) || !tc_pick_kc(Cc) || dtype != B200SEG_F16) return B200SEG_EUNSUPPORTED;
+  }
   cudaStream_t st = as_stream(stream);
   int64_t n = (int64_t)Cout * Cin * taps;
   int grid = ceil_div(n, 256); if (grid > B200SEG_NUM_SMS * 8) grid = B200SEG_NUM_SMS * 8;
-  if (dtype == B200SEG_F16) pack_weight_kernel<__half><<<grid, 256, 0, st>>>(w, Cout, Cin, taps, (__half*)w_packed, transpose_flip, co_off, co_total);
-  else if (dtype == B200SEG_F32) pack_weight_kernel<float><<<grid, 256, 0, st>>>(w, Cout, Cin, taps, (float*)w_packed, transpose_flip, co_off, co_total);
+  if (dtype == B200SEG_F16) pack_weight_kernel<__half><<<grid, 256, 0, st>>>(w, Cout, Cin, taps, (__half*)w_packed, transpose_flip, co_off, co_total, tc);
+  else if (dtype == B200SEG_F32) pack_weight_kernel<float><<<grid, 256, 0, st>>>(w, Cout, Cin, taps, (float*)w_packed, transpose_flip, co_off, co_total, tc);
   else return B200SEG_EINVAL;
   B200_CHECK_LAUNCH("pack_weight_kernel");
   return B200SEG_OK;

@@ -1,7 +1,532 @@
-// placeholder until the tcgen05 kernels land (next commit)
+// conv_tc.cu — conv3d forward / data-gradient as a tcgen05 implicit GEMM (sm_100a), fp16 operands,
+// fp32 accumulation in TMEM.  Replaces cuDNN fprop/dgrad behind nn.Conv3d (conv_layers.py:29-38) and
+// fuses the surrounding InstanceNorm+ReLU (conv_layers.py:40-43), residual add (:92) and the next
+// layer's InstanceNorm reduction.
+//
+// GEMM view (per CTA tile):  D[128 voxels][NT cout] += A[128 voxels][KC cin] * B[KC cin][NT cout]
+// for every filter tap and every KC-chunk of Cin.
+//   * M tile  = 16(h) x 8(w) output voxels of one depth slice; GEMM row r = hl*8 + wl.
+//   * A operand = a HALO tile (16+kh-1)x(8+kw-1) voxels x KC channels of ONE input depth slice, staged
+//     once in shared memory as [KC/8][halo voxel][8 ch] (UMMA K-major, no-swizzle core matrices:
+//     8 consecutive w-voxels x 16 B).  Every (kh,kw) tap reads the SAME staged tile through a shifted
+//     matrix descriptor (start += (zh*HALO_W + zw)*16 B, SBO = HALO_W*16 B) — im2col is never formed.
+//     The loader warps apply InstanceNorm-normalise + ReLU while staging (the normalised activation
+//     tensor never exists in HBM) and zero-fill padding / ragged-tile voxels.
+//   * B operand = weights pre-packed on device into the exact shared-memory image per (ntile,tap,kchunk)
+//     ([KC/8][NT][8] fp16), streamed by 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) through an mbarrier ring.
+//   * D lives in TMEM (double-buffered when 2*NT <= 512 columns); 4 epilogue warps drain it with
+//     tcgen05.ld while the MMA warp already works on the next tile.
+// Warp roles (448 threads, 1 CTA/SM, persistent over tiles):
+//   warps 0-3  epilogue (TMEM lane quadrant == warp id): bias / residual / dgrad ReLU-mask, fp16 store,
+//              InstanceNorm sums (or IN-backward sums) of what was stored
+//   warp  4    TMEM alloc + single-thread tcgen05.mma issue
+//   warp  5    weight producer (bulk TMA)
+//   warps 6-13 A loaders, two groups of 4 warps working on alternating stages
+// Roofline: tensor pipe (dense fp16) for NT>=128; for NT<128 the MMA is bound by the shared-memory read of
+// A (SS mode), see DESIGN.md.
 #include "common.cuh"
 #include "conv_args.h"
-bool conv3d_fwd_tc_supported(const ConvArgs&, int) { return false; }
+#include <string.h>
+#include <stdio.h>
+
+namespace {
+
+constexpr int TH = 16, TW = 8;            // output tile (h, w); M = 128
+constexpr int kEpiWarps = 4;
+constexpr int kMmaWarp = 4;
+constexpr int kWgtWarp = 5;
+constexpr int kLoadWarp0 = 6;
+constexpr int kLoadGroups = 2;
+constexpr int kLoadGroupThreads = 128;
+constexpr int kThreads = (kLoadWarp0 + kLoadGroups * 4) * 32;   // 448
+constexpr int kMaxChunksPerThread = 12;   // (18*10 voxels * 64/8 chunks) / 128 threads = 11.25
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+struct TcParams {
+  ConvArgs a;
+  const void* wimg;        // weight image [ntile][tap][kchunk][KC/8][NT][8]
+  int KC, NKC, NT, NTILES;
+  int HALO_H, HALO_W, nvox_h, plane_stride;   // plane_stride in bytes (odd multiple of 16)
+  int a_stage_bytes, b_stage_bytes, SA, SB;
+  int tiles_h, tiles_w, n_tiles;
+  int tmem_cols, acc_stages;
+  int smem_a_off, smem_b_off, smem_bar_off, smem_norm_off, smem_gnorm_off, smem_stat_off;
+  int* err_flag;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) {
+      if (err_flag) atomicExch(err_flag, code);
+      printf("b200seg conv_tc: mbarrier timeout code=%d block=%d thread=%d parity=%u\n", code, blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], fp16 x fp16 -> fp32
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, SWIZZLE_NONE (cute::UMMA::SmemDescriptor, version 1 = sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;      // descriptor version (Blackwell)
+  return d;                    // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+
+struct Ring {
+  int idx; uint32_t phase; int n;
+  __device__ __forceinline__ void init(int n_) { idx = 0; phase = 0; n = n_; }
+  __device__ __forceinline__ void advance() { if (++idx == n) { idx = 0; phase ^= 1; } }
+};
+
+struct TileCoord { int b, d, h0, w0, ntile; };
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int t) {
+  TileCoord c;
+  c.ntile = t % p.NTILES; t /= p.NTILES;
+  c.w0 = (t % p.tiles_w) * TW; t /= p.tiles_w;
+  c.h0 = (t % p.tiles_h) * TH; t /= p.tiles_h;
+  c.d = t % p.a.D; c.b = t / p.a.D;
+  return c;
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const ConvArgs& a = p.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps_hw = a.kh * a.kw;
+  const int pd = a.kd / 2, ph = a.kh / 2, pw = a.kw / 2;
+
+  // barrier block layout (uint64 each): a_full[SA] a_empty[SA] b_full[SB] b_empty[SB] t_full[2] t_empty[2]; then tmem ptr
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.smem_bar_off);
+  const uint32_t bar0 = smem_u32(bars);
+  auto A_FULL = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  auto A_EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(p.SA + i); };
+  auto B_FULL = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.SA + i); };
+  auto B_EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.SA + p.SB + i); };
+  auto T_FULL = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.SA + 2 * p.SB + i); };
+  auto T_EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.SA + 2 * p.SB + 2 + i); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(bars + 2 * p.SA + 2 * p.SB + 4);
+
+  float2* s_norm = reinterpret_cast<float2*>(smem + p.smem_norm_off);   // [B][Cin] {mean, rstd}
+  float2* s_gnorm = reinterpret_cast<float2*>(smem + p.smem_gnorm_off); // [B][Cout] {mean, rstd} of dgrad_x
+  float* s_stat = reinterpret_cast<float*>(smem + p.smem_stat_off);     // [4 warps][B][Cout][2]
+  const uint32_t smem_a = smem_u32(smem + p.smem_a_off);
+  const uint32_t smem_b = smem_u32(smem + p.smem_b_off);
+
+  // ---- one-time setup
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.SA; ++i) { mbar_init(A_FULL(i), kLoadGroupThreads); mbar_init(A_EMPTY(i), 1); }
+    for (int i = 0; i < p.SB; ++i) { mbar_init(B_FULL(i), 1); mbar_init(B_EMPTY(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(T_FULL(i), 1); mbar_init(T_EMPTY(i), kEpiWarps * 32); }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), (uint32_t)p.tmem_cols);
+  {
+    const double n = (double)a.D * a.H * a.W;
+    for (int i = threadIdx.x; i < a.B * a.Cin; i += kThreads) {
+      float m = 0.f, r = 1.f;
+      if (a.x_stats) stats_to_mean_rstd(a.x_stats + (int64_t)i * 2, n, a.eps, m, r);
+      s_norm[i] = make_float2(m, r);
+    }
+    if (a.gx) {
+      for (int i = threadIdx.x; i < a.B * a.Cout; i += kThreads) {
+        float m, r;
+        stats_to_mean_rstd(a.g_stats + (int64_t)i * 2, n, a.g_eps, m, r);
+        s_gnorm[i] = make_float2(m, r);
+      }
+    }
+    const int nstat = kEpiWarps * a.B * a.Cout * 2;
+    for (int i = threadIdx.x; i < nstat; i += kThreads) s_stat[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int ksteps = p.KC / 16;
+
+  if (warp >= kLoadWarp0) {
+    // =========================== A LOADERS ===========================
+    const int grp = (warp - kLoadWarp0) >> 2;
+    const int lt = threadIdx.x - (kLoadWarp0 * 32 + grp * kLoadGroupThreads);
+    const int cpv = p.KC / 8;
+    const int nchunks = p.nvox_h * cpv;
+    // per-thread chunk table: chunk i = lt + k*128 -> (hh, ww, c8), fixed for the whole kernel
+    int c_hh[kMaxChunksPerThread], c_ww[kMaxChunksPerThread], c_c8[kMaxChunksPerThread];
+#pragma unroll
+    for (int k = 0; k < kMaxChunksPerThread; ++k) {
+      int i = lt + k * kLoadGroupThreads;
+      int vox = i / cpv;
+      c_c8[k] = i - vox * cpv;
+      c_hh[k] = vox / p.HALO_W;
+      c_ww[k] = vox - c_hh[k] * p.HALO_W;
+      if (i >= nchunks) c_hh[k] = -1000000;       // never valid
+    }
+    const __half* xbase = reinterpret_cast<const __half*>(a.x);
+    Ring ring; ring.init(p.SA);
+    int stage_no = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      const TileCoord tc = tile_coord(p, t);
+      for (int kc = 0; kc < p.NKC; ++kc) {
+        for (int zd = 0; zd < a.kd; ++zd) {
+          const int din = tc.d + zd - pd;
+          if ((unsigned)din >= (unsigned)a.D) continue;
+          if ((stage_no & 1) == grp) {
+            mbar_wait(A_EMPTY(ring.idx), ring.phase ^ 1, p.err_flag, 1);
+            uint8_t* sdst = smem + p.smem_a_off + ring.idx * p.a_stage_bytes;
+            const __half* xs = xbase + ((int64_t)(tc.b * a.D + din) * a.H * a.W) * a.x_ld + a.x_coff + kc * p.KC;
+            const float2* nrm = s_norm + tc.b * a.Cin + kc * p.KC;
+            // issue all global loads first (ILP), then transform + store
+            uint4 raw[kMaxChunksPerThread];
+            bool ok[kMaxChunksPerThread];
+#pragma unroll
+            for (int k = 0; k < kMaxChunksPerThread; ++k) {
+              const int h = tc.h0 - ph + c_hh[k], w = tc.w0 - pw + c_ww[k];
+              ok[k] = (c_hh[k] >= 0) && ((unsigned)h < (unsigned)a.H) && ((unsigned)w < (unsigned)a.W);
+              raw[k] = make_uint4(0, 0, 0, 0);
+              if (ok[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(xs + ((int64_t)h * a.W + w) * a.x_ld + c_c8[k] * 8));
+            }
+#pragma unroll
+            for (int k = 0; k < kMaxChunksPerThread; ++k) {
+              if (c_hh[k] < 0) continue;
+              uint4 o = make_uint4(0, 0, 0, 0);
+              if (ok[k]) {
+                if (a.x_stats || a.act) {
+                  const __half2* hv = reinterpret_cast<const __half2*>(&raw[k]);
+                  __half2* ov = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float2 f = __half22float2(hv[j]);
+                    const float2 n0 = nrm[c_c8[k] * 8 + 2 * j], n1 = nrm[c_c8[k] * 8 + 2 * j + 1];
+                    f.x = (f.x - n0.x) * n0.y; f.y = (f.y - n1.x) * n1.y;
+                    if (a.act == B200SEG_ACT_RELU) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+                    ov[j] = __floats2half2_rn(f.x, f.y);
+                  }
+                } else {
+                  o = raw[k];
+                }
+              }
+              const int vox = c_hh[k] * p.HALO_W + c_ww[k];
+              *reinterpret_cast<uint4*>(sdst + c_c8[k] * p.plane_stride + vox * 16) = o;
+            }
+            fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
+            mbar_arrive(A_FULL(ring.idx));
+          }
+          ring.advance();
+          ++stage_no;
+        }
+      }
+    }
+  } else if (warp == kWgtWarp) {
+    // =========================== WEIGHT PRODUCER (bulk TMA) ===========================
+    if (lane == 0) {
+      Ring ring; ring.init(p.SB);
+      const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.wimg);
+      const int taps = a.kd * taps_hw;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(p, t);
+        for (int kc = 0; kc < p.NKC; ++kc) {
+          for (int zd = 0; zd < a.kd; ++zd) {
+            const int din = tc.d + zd - pd;
+            if ((unsigned)din >= (unsigned)a.D) continue;
+            for (int thw = 0; thw < taps_hw; ++thw) {
+              const int tap = zd * taps_hw + thw;
+              mbar_wait(B_EMPTY(ring.idx), ring.phase ^ 1, p.err_flag, 2);
+              mbar_arrive_expect_tx(B_FULL(ring.idx), (uint32_t)p.b_stage_bytes);
+              const uint8_t* src = wimg + ((int64_t)(tc.ntile * taps + tap) * p.NKC + kc) * p.b_stage_bytes;
+              bulk_g2s(smem_b + ring.idx * p.b_stage_bytes, src, (uint32_t)p.b_stage_bytes, B_FULL(ring.idx));
+              ring.advance();
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // =========================== MMA ISSUER (one thread) ===========================
+    if (lane == 0) {
+      Ring ra, rb; ra.init(p.SA); rb.init(p.SB);
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t a_sbo = (uint32_t)p.HALO_W * 16u, a_lbo = (uint32_t)p.plane_stride;
+      const uint32_t b_sbo = 128u, b_lbo = (uint32_t)p.NT * 16u;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+        const TileCoord tc = tile_coord(p, t);
+        const int acc = (p.acc_stages == 2) ? (it & 1) : 0;
+        const uint32_t acc_phase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(T_EMPTY(acc), acc_phase ^ 1, p.err_flag, 3);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.NT);
+        uint32_t accumulate = 0;
+        for (int kc = 0; kc < p.NKC; ++kc) {
+          for (int zd = 0; zd < a.kd; ++zd) {
+            const int din = tc.d + zd - pd;
+            if ((unsigned)din >= (unsigned)a.D) continue;
+            mbar_wait(A_FULL(ra.idx), ra.phase, p.err_flag, 4);
+            tc_fence_after();
+            const uint32_t a_stage = smem_a + ra.idx * p.a_stage_bytes;
+            for (int zh = 0; zh < a.kh; ++zh) {
+              for (int zw = 0; zw < a.kw; ++zw) {
+                mbar_wait(B_FULL(rb.idx), rb.phase, p.err_flag, 5);
+                tc_fence_after();
+                const uint32_t a_tap = a_stage + (uint32_t)(zh * p.HALO_W + zw) * 16u;
+                const uint32_t b_stage = smem_b + rb.idx * p.b_stage_bytes;
+                for (int j = 0; j < ksteps; ++j) {
+                  const uint64_t da = make_desc(a_tap + (uint32_t)(2 * j) * a_lbo, a_lbo, a_sbo);
+                  const uint64_t db = make_desc(b_stage + (uint32_t)(2 * j) * b_lbo, b_lbo, b_sbo);
+                  umma_f16(tmem_d, da, db, idesc, accumulate);
+                  accumulate = 1;
+                }
+                umma_commit(B_EMPTY(rb.idx));     // weights slot free once these MMAs retire
+                rb.advance();
+              }
+            }
+            umma_commit(A_EMPTY(ra.idx));         // halo tile free
+            ra.advance();
+          }
+        }
+        umma_commit(T_FULL(acc));                 // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // =========================== EPILOGUE (warps 0-3) ===========================
+    const int q = warp;                         // TMEM lane quadrant
+    const int row = q * 32 + lane;              // GEMM row = hl*8 + wl
+    const int hl = row >> 3, wl = row & 7;
+    const bool dgrad = a.gx != nullptr;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+      const TileCoord tc = tile_coord(p, t);
+      const int acc = (p.acc_stages == 2) ? (it & 1) : 0;
+      const uint32_t acc_phase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
+      mbar_wait(T_FULL(acc), acc_phase, p.err_flag, 6);
+      tc_fence_after();
+      const int h = tc.h0 + hl, w = tc.w0 + wl;
+      const bool valid = (h < a.H) && (w < a.W);
+      const int64_t vox = ((int64_t)(tc.b * a.D + tc.d) * a.H + h) * a.W + w;
+      const int co_base = tc.ntile * p.NT;
+      __half* yp = reinterpret_cast<__half*>(a.y) + vox * a.y_ld + a.y_coff + co_base;
+      const __half* rp = a.res ? reinterpret_cast<const __half*>(a.res) + vox * a.r_ld + a.r_coff + co_base : nullptr;
+      const __half* gp = dgrad ? reinterpret_cast<const __half*>(a.gx) + vox * a.gx_ld + a.gx_coff + co_base : nullptr;
+      float* wstat = s_stat + ((q * a.B + tc.b) * a.Cout + co_base) * 2;
+      for (int n0 = 0; n0 < p.NT; n0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT + n0), v);
+        tmem_ld_wait();
+        float r[16], s2[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = __uint_as_float(v[j]);
+        if (valid) {
+          if (a.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] += a.bias[co_base + n0 + j];
+          }
+          if (dgrad) {
+            float xv[16];
+            ld8<__half>(gp + n0, reinterpret_cast<float(&)[8]>(xv[0]));
+            ld8<__half>(gp + n0 + 8, reinterpret_cast<float(&)[8]>(xv[8]));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 mr = s_gnorm[tc.b * a.Cout + co_base + n0 + j];
+              const float hx = (xv[j] - mr.x) * mr.y;
+              float g = (a.g_act == B200SEG_ACT_RELU && !(hx > 0.f)) ? 0.f : r[j];
+              g = __half2float(__float2half_rn(g));
+              r[j] = g; s2[j] = g * hx;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __half2float(__float2half_rn(r[j]));
+            if (rp) {
+              float rv[16];
+              ld8<__half>(rp + n0, reinterpret_cast<float(&)[8]>(rv[0]));
+              ld8<__half>(rp + n0 + 8, reinterpret_cast<float(&)[8]>(rv[8]));
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = __half2float(__float2half_rn(r[j] + rv[j]));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s2[j] = r[j] * r[j];
+          }
+          st8<__half>(yp + n0, reinterpret_cast<const float(&)[8]>(r[0]));
+          st8<__half>(yp + n0 + 8, reinterpret_cast<const float(&)[8]>(r[8]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { r[j] = 0.f; s2[j] = 0.f; }
+        }
+        if (a.y_stats) {
+          // column sums over the warp's 32 rows; lane j (<16) ends up owning channel n0+j
+          float keep1 = 0.f, keep2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float u = warp_sum(r[j]), q2 = warp_sum(s2[j]);
+            if (lane == j) { keep1 = u; keep2 = q2; }
+          }
+          if (lane < 16) {
+            wstat[(n0 + lane) * 2] += keep1;
+            wstat[(n0 + lane) * 2 + 1] += keep2;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(T_EMPTY(acc));
+    }
+  }
+
+  // ---- teardown: flush the per-CTA InstanceNorm partial sums, free TMEM
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (a.y_stats) {
+    const int n = a.B * a.Cout * 2;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < kEpiWarps; ++q) s += (double)s_stat[q * n + i];
+      if (s != 0.0) atomicAdd(&a.y_stats[i], s);
+    }
+  }
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace
+
+bool conv3d_tc_shape_ok(int Cin, int Cout, int kd, int kh, int kw, int dtype) {
+  if (dtype != B200SEG_F16) return false;
+  if (tc_pick_nt(Cout) == 0 || tc_pick_kc(Cin) == 0) return false;
+  if (kh > 3 || kw > 3 || kd > 3 || kd < 1 || kh < 1 || kw < 1) return false;
+  return true;
+}
+
+bool conv3d_fwd_tc_supported(const ConvArgs& a, int dtype) {
+  if (!conv3d_tc_shape_ok(a.Cin, a.Cout, a.kd, a.kh, a.kw, dtype)) return false;
+  if (dtype != B200SEG_F16) return false;
+  if (tc_pick_nt(a.Cout) == 0 || tc_pick_kc(a.Cin) == 0) return false;
+  if (a.kh > 3 || a.kw > 3 || a.kd > 3) return false;
+  if ((a.x_ld % 8) || (a.x_coff % 8) || (a.y_ld % 8) || (a.y_coff % 8)) return false;
+  if (a.res && ((a.r_ld % 8) || (a.r_coff % 8))) return false;
+  if (a.gx && ((a.gx_ld % 8) || (a.gx_coff % 8))) return false;
+  if ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.y) | reinterpret_cast<uintptr_t>(a.w)) & 15) return false;
+  if (a.B * a.Cin > 4096 || a.B * a.Cout > 2048) return false;
+  return true;
+}
+
+// `a.w` must be the TC weight IMAGE ([ntile][tap][kchunk][KC/8][NT][8], b200seg_pack_weight layout=TC).
+int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
+  if (!conv3d_fwd_tc_supported(a, dtype)) return B200SEG_EUNSUPPORTED;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.a = a;
+  p.wimg = a.w;
+  p.KC = tc_pick_kc(a.Cin); p.NKC = a.Cin / p.KC;
+  p.NT = tc_pick_nt(a.Cout); p.NTILES = a.Cout / p.NT;
+  p.HALO_H = TH + a.kh - 1; p.HALO_W = TW + a.kw - 1;
+  p.nvox_h = p.HALO_H * p.HALO_W;
+  int slots = p.nvox_h; if ((slots & 1) == 0) slots += 1;     // odd number of 16-B slots -> conflict-free plane stride
+  p.plane_stride = slots * 16;
+  p.a_stage_bytes = (p.KC / 8) * p.plane_stride;
+  p.a_stage_bytes = (p.a_stage_bytes + 127) / 128 * 128;
+  p.b_stage_bytes = p.KC * p.NT * 2;
+  if (p.nvox_h * (p.KC / 8) > kMaxChunksPerThread * kLoadGroupThreads) return B200SEG_EUNSUPPORTED;
+  p.tiles_h = (a.H + TH - 1) / TH; p.tiles_w = (a.W + TW - 1) / TW;
+  int64_t nt = (int64_t)a.B * a.D * p.tiles_h * p.tiles_w * p.NTILES;
+  if (nt > 0x7fffffff) return B200SEG_EUNSUPPORTED;
+  p.n_tiles = (int)nt;
+  p.acc_stages = (2 * p.NT <= 512) ? 2 : 1;
+  int cols = p.acc_stages * p.NT, pow2 = 32;
+  while (pow2 < cols) pow2 <<= 1;
+  p.tmem_cols = pow2;
+  // shared memory carve-up
+  const int norm_bytes = a.B * a.Cin * 8;
+  const int stat_bytes = kEpiWarps * a.B * a.Cout * 2 * 4;
+  const int budget = 227 * 1024 - 1024 - norm_bytes - stat_bytes - a.B * a.Cout * 8 - 512;
+  p.SB = 4; p.SA = 4;
+  while (p.SA * p.a_stage_bytes + p.SB * p.b_stage_bytes > budget && (p.SA > 2 || p.SB > 2)) {
+    if (p.SB > 2 && (p.SB * p.b_stage_bytes >= p.SA * p.a_stage_bytes || p.SA <= 2)) --p.SB; else --p.SA;
+  }
+  if (p.SA * p.a_stage_bytes + p.SB * p.b_stage_bytes > budget) return B200SEG_EUNSUPPORTED;
+  int off = 0;
+  p.smem_a_off = off; off += p.SA * p.a_stage_bytes;
+  off = (off + 127) / 128 * 128;
+  p.smem_b_off = off; off += p.SB * p.b_stage_bytes;
+  off = (off + 15) / 16 * 16;
+  p.smem_bar_off = off; off += (2 * p.SA + 2 * p.SB + 4) * 8 + 16;
+  off = (off + 15) / 16 * 16;
+  p.smem_norm_off = off; off += norm_bytes;
+  off = (off + 15) / 16 * 16;
+  p.smem_gnorm_off = off; off += a.B * a.Cout * 8;
+  off = (off + 15) / 16 * 16;
+  p.smem_stat_off = off; off += stat_bytes;
+  const int smem_bytes = off + 1024;       // slack for the 1024-B alignment of the dynamic segment
+  p.err_flag = nullptr;
+  int grid = p.n_tiles < B200SEG_NUM_SMS ? p.n_tiles : B200SEG_NUM_SMS;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(p);
+  B200_CHECK_LAUNCH("conv_tc_kernel");
+  return B200SEG_OK;
+}
+
 bool conv3d_wgrad_tc_supported(const WgradArgs&, int) { return false; }
-int conv3d_fwd_tc(const ConvArgs&, int, cudaStream_t) { return B200SEG_EUNSUPPORTED; }
 int conv3d_wgrad_tc(const WgradArgs&, int, cudaStream_t) { return B200SEG_EUNSUPPORTED; }

@@ -10,7 +10,7 @@ so fused tensors (conv1+shortcut outputs, concat buffers) are consumed in place.
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, ALGO_AUTO, F16, F32, call
+from ._lib import ACT_NONE, ACT_RELU, ALGO_AUTO, ALGO_DIRECT, ALGO_TC, F16, F32, call
 
 IN_EPS = 1e-4  # nn.InstanceNorm3d(eps=1e-4): reference conv_layers.py:40,42
 
@@ -47,8 +47,14 @@ def new_stats(B, C, device):
 
 
 # ----------------------------------------------------------------------------- raw launches
-def pack_weight(w, dtype, transpose_flip=False, out=None, co_off=0, co_total=None):
-    """[Cout,Cin,kd,kh,kw] fp32 parameter -> packed [taps][Cout_total][Cin] (or the dgrad operand)."""
+def conv_algo(Cin, Cout, ksize, dtype, B=1):
+    """Algorithm (ALGO_TC / ALGO_DIRECT) the library uses for this conv shape; also names the packed-weight layout."""
+    return _lib.load().b200seg_conv3d_algo(Cin, Cout, ksize[0], ksize[1], ksize[2],
+                                           F16 if dtype == torch.float16 else F32, B)
+
+
+def pack_weight(w, dtype, transpose_flip=False, out=None, co_off=0, co_total=None, layout=ALGO_DIRECT):
+    """[Cout,Cin,kd,kh,kw] fp32 parameter -> packed weights for `layout` (see b200seg_pack_weight)."""
     Cout, Cin = w.shape[0], w.shape[1]
     taps = w.shape[2] * w.shape[3] * w.shape[4]
     co_total = Cout if co_total is None else co_total
@@ -58,15 +64,21 @@ def pack_weight(w, dtype, transpose_flip=False, out=None, co_off=0, co_total=Non
     if wc.dtype != torch.float32 or not wc.is_contiguous():
         wc = wc.float().contiguous()
     call("b200seg_pack_weight", wc.data_ptr(), Cout, Cin, taps, out.data_ptr(), _dt(out),
-         1 if transpose_flip else 0, co_off, co_total, _stream())
+         1 if transpose_flip else 0, co_off, co_total, layout, _stream())
     return out
 
 
 def conv3d_fwd(x, x_coff, Cin, x_stats, act, wp, Cout, ksize, bias=None, residual=None, r_coff=0,
-               want_stats=True, dgrad_of=None, algo=ALGO_AUTO, eps=IN_EPS):
+               want_stats=True, dgrad_of=None, algo=None, eps=IN_EPS):
     """y = conv(act(IN(x[..., x_coff:x_coff+Cin]))) (+bias)(+residual); returns (y, y_stats).
+    wp: packed weights, either a tensor (DIRECT layout) or a (tensor, algo) pair from PackedWeights.
     dgrad_of=(tensor, coff, stats, act): data-gradient mode, see b200seg_conv3d_fwd."""
     _need_cuda(x)
+    if isinstance(wp, tuple):
+        wp, walgo = wp
+        algo = walgo if algo is None else algo
+    if algo is None:
+        algo = ALGO_DIRECT
     B, D, H, W, x_ld = x.shape
     y = torch.empty(B, D, H, W, Cout, dtype=x.dtype, device=x.device)
     y_stats = new_stats(B, Cout, x.device) if want_stats else None
@@ -132,21 +144,24 @@ class PackedWeights:
         self._fwd = None
         self._bwd = None
 
-    def get(self, weights, dtype):
-        key = (dtype,) + tuple((w.data_ptr(), w._version) for w in weights)
+    def get(self, weights, dtype, B=1):
+        key = (dtype, B) + tuple((w.data_ptr(), w._version) for w in weights)
         if key != self._key:
             co_total = sum(w.shape[0] for w in weights)
             Cin = weights[0].shape[1]
+            ks = tuple(weights[0].shape[2:])
             taps = weights[0][0, 0].numel()
             dev = weights[0].device
+            algo_f = conv_algo(Cin, co_total, ks, dtype, B)
+            algo_b = conv_algo(co_total, Cin, ks, dtype, B)      # dgrad: channels swap roles
             fwd = torch.empty(taps * co_total * Cin, dtype=dtype, device=dev)
             bwd = torch.empty(taps * co_total * Cin, dtype=dtype, device=dev)
             off = 0
             for w in weights:
-                pack_weight(w, dtype, False, fwd, off, co_total)
-                pack_weight(w, dtype, True, bwd, off, co_total)
+                pack_weight(w, dtype, False, fwd, off, co_total, algo_f)
+                pack_weight(w, dtype, True, bwd, off, co_total, algo_b)
                 off += w.shape[0]
-            self._key, self._fwd, self._bwd = key, fwd, bwd
+            self._key, self._fwd, self._bwd = key, (fwd, algo_f), (bwd, algo_b)
         return self._fwd, self._bwd
 
 
@@ -192,15 +207,16 @@ class BasicBlockFn(torch.autograd.Function):
             out, out_stats = conv3d_fwd(ts, 0, Cout, t1_stats, ACT_RELU, w2_fwd, Cout, ksize, residual=ts, r_coff=Cout)
         else:
             out, out_stats = conv3d_fwd(ts, 0, Cout, t1_stats, ACT_RELU, w2_fwd, Cout, ksize, residual=x, r_coff=x_coff)
-        ctx.save_for_backward(x, x_stats, ts, t1_stats, wf_bwd, w2_bwd)
-        ctx.meta = (Cin, Cout, ksize, x_coff, has_sc)
+        ctx.save_for_backward(x, x_stats, ts, t1_stats, wf_bwd[0], w2_bwd[0])
+        ctx.meta = (Cin, Cout, ksize, x_coff, has_sc, wf_bwd[1], w2_bwd[1])
         ctx.mark_non_differentiable(out_stats)
         return out, out_stats
 
     @staticmethod
     def backward(ctx, d_out, _):
         x, x_stats, ts, t1_stats, wf_bwd, w2_bwd = ctx.saved_tensors
-        Cin, Cout, ksize, x_coff, has_sc = ctx.meta
+        Cin, Cout, ksize, x_coff, has_sc, algo_f, algo_2 = ctx.meta
+        wf_bwd, w2_bwd = (wf_bwd, algo_f), (w2_bwd, algo_2)
         d_out = d_out.contiguous()
         B, D, H, W, _ = d_out.shape
         # ---- conv2: out = conv(relu(IN(t1))) + shortcut
@@ -247,14 +263,15 @@ class SingleConvFn(torch.autograd.Function):
         y = torch.empty_like(r)
         call("b200seg_instnorm_apply", r.data_ptr(), _dt(r), Cout, 0, r_stats.data_ptr(), IN_EPS, ACT_RELU,
              y.data_ptr(), Cout, 0, B, D * H * W, Cout, _stream())
-        ctx.save_for_backward(x, r, r_stats, w_bwd)
-        ctx.meta = (Cin, Cout, ksize, x_coff, x.requires_grad)
+        ctx.save_for_backward(x, r, r_stats, w_bwd[0])
+        ctx.meta = (Cin, Cout, ksize, x_coff, x.requires_grad, w_bwd[1])
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, r, r_stats, w_bwd = ctx.saved_tensors
-        Cin, Cout, ksize, x_coff, need_dx = ctx.meta
+        Cin, Cout, ksize, x_coff, need_dx, algo_b = ctx.meta
+        w_bwd = (w_bwd, algo_b)
         dy = dy.contiguous()
         B, D, H, W, _ = dy.shape
         V = D * H * W
@@ -349,14 +366,15 @@ class OutConvFn(torch.autograd.Function):
         w_fwd, w_bwd = packs
         Cout, Cin = w.shape[0], w.shape[1]
         y, _ = conv3d_fwd(x, 0, Cin, None, ACT_NONE, w_fwd, Cout, (1, 1, 1), bias=bias, want_stats=False)
-        ctx.save_for_backward(x, w_bwd)
-        ctx.meta = (Cin, Cout)
+        ctx.save_for_backward(x, w_bwd[0])
+        ctx.meta = (Cin, Cout, w_bwd[1])
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w_bwd = ctx.saved_tensors
-        Cin, Cout = ctx.meta
+        Cin, Cout, algo_b = ctx.meta
+        w_bwd = (w_bwd, algo_b)
         dy = dy.contiguous()
         dw, db = conv3d_wgrad(x, 0, Cin, None, ACT_NONE, dy, 0, Cout, (1, 1, 1), want_bias=True)
         dx, _ = conv3d_fwd(dy, 0, Cout, None, ACT_NONE, w_bwd, Cin, (1, 1, 1), want_stats=False)

@@ -50,7 +50,7 @@ class SingleConv(nn.Module):
     def forward(self, a):
         x, _ = a
         w = self.conv.conv.weight
-        y = SingleConvFn.apply(x, w, self._pack.get([w], x.dtype), self.ksize, 0, w.shape[1])
+        y = SingleConvFn.apply(x, w, self._pack.get([w], x.dtype, x.shape[0]), self.ksize, 0, w.shape[1])
         return (y, None)
 
 
@@ -80,7 +80,7 @@ class BasicBlock(nn.Module):
         w1, w2 = self.conv1.conv.weight, self.conv2.conv.weight
         wsc = self.shortcut.conv.weight if isinstance(self.shortcut, ConvNormAct) else None
         fused = [w1] if wsc is None else [w1, wsc]
-        packs = (self._pack_f.get(fused, x.dtype), self._pack_2.get([w2], x.dtype))
+        packs = (self._pack_f.get(fused, x.dtype, x.shape[0]), self._pack_2.get([w2], x.dtype, x.shape[0]))
         out, out_st = BasicBlockFn.apply(x, st, w1, w2, wsc, packs, self.ksize, 0, w1.shape[1])
         return (out, out_st)
 
@@ -109,7 +109,7 @@ class inconv(nn.Module):
 
     def forward(self, x):
         w = self.conv1.weight
-        wf, _ = self._pack.get([w], x.dtype)
+        wf, _ = self._pack.get([w], x.dtype, x.shape[0])
         y, st = StemConvFn.apply(x, w, wf, self.ksize)
         return self.conv2((y, st))
 
@@ -203,6 +203,6 @@ class UNet(nn.Module):
         out = self.up3(out, x2)
         out = self.up4(out, x1)
         w, b = self.outc.weight, self.outc.bias
-        logits = OutConvFn.apply(out[0], w, b, self._pack_out.get([w], dt))
+        logits = OutConvFn.apply(out[0], w, b, self._pack_out.get([w], dt, x.shape[0]))
         # boundary: logical NCDHW shape over the NDHWC buffer (channels_last_3d strides, zero-copy)
         return logits.permute(0, 4, 1, 2, 3)

@@ -48,7 +48,8 @@ enum {
   B200SEG_ENODEVICE = -4    /* device is not sm_100 (this library has no fallback)           */
 };
 
-/* conv algorithms: AUTO picks TC when the shape qualifies, else DIRECT. */
+/* conv algorithms.  conv3d_fwd takes TC or DIRECT (whatever b200seg_conv3d_algo returned when the
+ * weights were packed); wgrad also accepts AUTO since it consumes no packed weights. */
 enum { B200SEG_ALGO_AUTO = 0, B200SEG_ALGO_DIRECT = 1, B200SEG_ALGO_TC = 2 };
 
 /* activation applied to the (optionally normalised) conv input in the loader */
@@ -140,7 +141,14 @@ int b200seg_instnorm_bwd_apply(const void* g, int g_ld, int g_coff,
  * weight (conv1+shortcut of a BasicBlock share one GEMM, conv_layers.py:79,84). */
 int b200seg_pack_weight(const float* w, int Cout, int Cin, int taps,
                         void* w_packed, int dtype, int transpose_flip,
-                        int co_off, int co_total, void* stream);
+                        int co_off, int co_total, int layout, void* stream);
+
+/* Which algorithm (B200SEG_ALGO_TC or _DIRECT) serves a conv of this shape.  The
+ * packed-weight layout is per algorithm (`layout` above = this value):
+ *   DIRECT: [tap][Cout][Cin];
+ *   TC    : the shared-memory image the tcgen05 kernel streams with bulk TMA,
+ *           [ntile][tap][kchunk][KC/8][NT][8]  (NT / KC: csrc/conv_args.h). */
+int b200seg_conv3d_algo(int Cin, int Cout, int kd, int kh, int kw, int dtype, int B);
 
 /* y[.., y_coff:y_coff+Cout] = conv(act(IN(x))) (+bias) (+residual); optionally
  * accumulates InstanceNorm sums of the STORED y into y_stats.
