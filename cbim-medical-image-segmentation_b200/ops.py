@@ -120,6 +120,25 @@ def in_bwd_apply(g, x, x_coff, C, x_stats, bstats, add=None, add_coff=0, out=Non
     return out
 
 
+def in_apply(x, C, stats, act, eps=IN_EPS):
+    """y = act(IN(x)) materialised (SingleConv post-activation)."""
+    B, D, H, W, _ = x.shape
+    y = torch.empty(B, D, H, W, C, dtype=x.dtype, device=x.device)
+    call("b200seg_instnorm_apply", x.data_ptr(), _dt(x), x.shape[-1], 0, stats.data_ptr(), eps, act,
+         y.data_ptr(), C, 0, B, D * H * W, C, _stream())
+    return y
+
+
+def in_bwd_reduce(dy, x, C, stats, act, eps=IN_EPS):
+    """g = dy * act'(xhat) and the two IN-backward sums; returns (g, bstats)."""
+    B, D, H, W, _ = x.shape
+    g = torch.empty(B, D, H, W, C, dtype=x.dtype, device=x.device)
+    bst = new_stats(B, C, x.device)
+    call("b200seg_instnorm_bwd_reduce", dy.data_ptr(), dy.shape[-1], 0, x.data_ptr(), x.shape[-1], 0, _dt(x),
+         stats.data_ptr(), eps, act, g.data_ptr(), C, 0, bst.data_ptr(), B, D * H * W, C, _stream())
+    return g, bst
+
+
 def copy_channels(x, x_coff, y, y_coff, C, accumulate=False):
     nvox = x.numel() // x.shape[-1]
     call("b200seg_copy_channels", x.data_ptr(), _dt(x), x.shape[-1], x_coff, y.data_ptr(), _dt(y), y.shape[-1],
@@ -259,10 +278,7 @@ class SingleConvFn(torch.autograd.Function):
         Cout = w.shape[0]
         w_fwd, w_bwd = packs
         r, r_stats = conv3d_fwd(x, x_coff, Cin, None, ACT_NONE, w_fwd, Cout, ksize)
-        B, D, H, W, _ = r.shape
-        y = torch.empty_like(r)
-        call("b200seg_instnorm_apply", r.data_ptr(), _dt(r), Cout, 0, r_stats.data_ptr(), IN_EPS, ACT_RELU,
-             y.data_ptr(), Cout, 0, B, D * H * W, Cout, _stream())
+        y = in_apply(r, Cout, r_stats, ACT_RELU)
         ctx.save_for_backward(x, r, r_stats, w_bwd[0])
         ctx.meta = (Cin, Cout, ksize, x_coff, x.requires_grad, w_bwd[1])
         return y
@@ -273,12 +289,7 @@ class SingleConvFn(torch.autograd.Function):
         Cin, Cout, ksize, x_coff, need_dx, algo_b = ctx.meta
         w_bwd = (w_bwd, algo_b)
         dy = dy.contiguous()
-        B, D, H, W, _ = dy.shape
-        V = D * H * W
-        g = torch.empty_like(r)
-        bst = new_stats(B, Cout, r.device)
-        call("b200seg_instnorm_bwd_reduce", dy.data_ptr(), Cout, 0, r.data_ptr(), Cout, 0, _dt(r),
-             r_stats.data_ptr(), IN_EPS, ACT_RELU, g.data_ptr(), Cout, 0, bst.data_ptr(), B, V, Cout, _stream())
+        g, bst = in_bwd_reduce(dy, r, Cout, r_stats, ACT_RELU)
         dr = in_bwd_apply(g, r, 0, Cout, r_stats, bst)
         dw, _ = conv3d_wgrad(x, x_coff, Cin, None, ACT_NONE, dr, 0, Cout, ksize)
         dx = None

@@ -26,7 +26,8 @@ def dice_loss(preds, targets):
 
 
 def cross_entropy(preds, targets, weight=None):
-    return F.cross_entropy(preds.float(), targets.squeeze(1), weight=weight)
+    x = preds if preds.dtype == torch.float64 else preds.float()
+    return F.cross_entropy(x, targets.squeeze(1), weight=None if weight is None else weight.to(x.dtype))
 
 
 def total_loss(result, label, weight=None, aux_weight=None):

@@ -63,17 +63,29 @@ def main():
         assert all(tuple(v.shape) == tuple(shapes[k]) for k, v in ref.state_dict().items())
         sd = ounet.make_state_dict(shapes, seed=7)
         ref.load_state_dict(sd)
-        img, lab = make_volume(B, D, H, W, classes, seed=2023)
         weight = torch.tensor(w, dtype=torch.float32)
-        # --- reference
         ref.train()
-        logits = ref(img)
-        ce = torch.nn.CrossEntropyLoss(weight=weight)(logits, lab.squeeze(1))
-        dl = DiceLoss()(logits, lab)
-        loss = ce + dl
-        loss.backward()
-        grads = {k: p.grad.clone() for k, p in ref.named_parameters()}
-        # --- oracle restatement must reproduce it
+        # ReLU'(0) makes the gradient discontinuous: a pre-activation within fp32 rounding of 0 flips its mask
+        # between two equally valid fp32 evaluations, and through InstanceNorm's whole-channel reductions a flip
+        # moves gradients far more than 1e-3.  The reference's own fp32 gradients therefore differ from an fp64
+        # evaluation of the same network by ~1e-3..1e-1 (measured here and stored as `ref_fp32_vs_fp64_grad_err`);
+        # the parity tests use that number as the noise floor of "matches the reference's backward".
+        for data_seed in range(2023, 2024):
+            img, lab = make_volume(B, D, H, W, classes, seed=data_seed)
+            ref.zero_grad(set_to_none=True)
+            logits = ref(img)
+            ce = torch.nn.CrossEntropyLoss(weight=weight)(logits, lab.squeeze(1))
+            dl = DiceLoss()(logits, lab)
+            loss = ce + dl
+            loss.backward()
+            grads = {k: p.grad.clone() for k, p in ref.named_parameters()}
+            sd64 = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+            l64 = ounet.unet_forward(sd64, img.double(), scale, kernel, block)
+            olosses.total_loss(l64, lab, weight.double()).backward()
+            e64 = max(((sd64[k].grad - grads[k].double()).abs().max() / (sd64[k].grad.abs().max() + 1e-300)).item() for k in grads)
+            print("   seed %d: reference fp32 vs fp64 evaluation, worst grad rel err %.2e" % (data_seed, e64))
+            break   # first seed; the discrepancy is recorded in the fixture and used as the noise floor by the tests
+        # --- oracle restatement (fp32, same ops) must reproduce the reference
         sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
         lo = ounet.unet_forward(sdo, img, scale, kernel, block)
         losso = olosses.total_loss(lo, lab, weight)
@@ -86,7 +98,8 @@ def main():
         small = ["inc.conv1.weight", "outc.weight", "outc.bias"]
         torch.save({
             "cfg": {"block": block, "base": base, "classes": classes, "scale": scale, "kernel": kernel,
-                    "shape": shp, "ce_weight": w, "state_seed": 7, "data_seed": 2023},
+                    "shape": shp, "ce_weight": w, "state_seed": 7, "data_seed": data_seed,
+                    "ref_fp32_vs_fp64_grad_err": e64},
             "keys": list(shapes), "logits": logits.detach().half(), "argmax": logits.argmax(1).to(torch.uint8),
             "loss": loss.item(), "ce": ce.item(), "dice": dl.item(),
             "grad_digest": {k: digest(g) for k, g in grads.items()},
