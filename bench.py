@@ -299,7 +299,8 @@ def run_b200(args, wl):
         (ci, co, k, d), _ = max(groups.items(), key=lambda kv: kv[1])
         x = torch.randn(B, d[0], d[1], d[2], ci, device=dev).half()
         st = ops.instnorm_stats(x, 0, ci)
-        wp = torch.randn(k[0] * k[1] * k[2] * co * ci, device=dev).half() * 0.05
+        algo = ops.conv_algo(ci, co, k, torch.float16, B)
+        wp = (ops.pack_weight(torch.randn(co, ci, *k, device=dev) * 0.05, torch.float16, layout=algo), algo)
         for _ in range(3):
             ops.conv3d_fwd(x, 0, ci, st, ops.ACT_RELU, wp, co, k)
         torch.cuda.synchronize()
@@ -321,7 +322,7 @@ def run_b200(args, wl):
         out["roofline"] = {"bound": "tensor", "achieved": kfl / (kms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                            "frac": kfl / (kms / 1e3) / 1e12 / peak, "traffic": None,
                            "peak_source": "measured (MEASURED_PEAKS.json, burst)" if peaks else "fallback 1.59 PF",
-                           "kernel": "conv3d_fwd %d->%d k%s @%s (IN+ReLU loader, IN-sums epilogue)" % (ci, co, list(k), list(d)),
+                           "kernel": "conv3d_fwd[%s] %d->%d k%s @%s (IN+ReLU loader, IN-sums epilogue)" % ("tcgen05" if algo == 2 else "direct", ci, co, list(k), list(d)),
                            "ms": kms, "step_frac_of_sustained_peak": out["achieved_tflops_step"] / peaks.get("bf16_tflops_sustained", 1400.0)}
         del x, wp
         # ---- CPU baseline: oracle port on the host cores, bounded sample

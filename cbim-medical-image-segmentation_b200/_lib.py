@@ -34,14 +34,16 @@ _PROTOS = {
     "b200seg_conv3d_algo": [I, I, I, I, I, I, I],
     "b200seg_conv3d_fwd": [P, I, I, P, F, I, P, P, P, I, I, P, I, I, P, P, I, I, P, F, I,
                            I, I, I, I, I, I, I, I, I, I, I, P],
-    "b200seg_conv3d_wgrad": [P, I, I, P, F, I, P, I, I, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
+    "b200seg_conv3d_wgrad_workspace": [I, I, I, I, I, I, I, I, I, I, I, I, I, I, I, I, I],
+    "b200seg_conv3d_wgrad": [P, I, I, P, F, I, P, I, I, P, P, I, I, I, I, I, I, I, I, I, I, I, P, ctypes.c_size_t, P],
     "b200seg_maxpool3d_fwd": [P, I, I, P, I, I, P, P, I, I, I, I, I, I, I, I, I, P],
     "b200seg_maxpool3d_bwd": [P, I, I, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "b200seg_upsample_trilinear_fwd": [P, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P],
     "b200seg_upsample_trilinear_bwd": [P, I, I, P, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "b200seg_copy_channels": [P, I, I, I, P, I, I, I, I, L, I, P],
 }
-_RESTYPES = {"b200seg_strerror": c_char_p, "b200seg_last_cuda_error": c_char_p}
+_RESTYPES = {"b200seg_strerror": c_char_p, "b200seg_last_cuda_error": c_char_p,
+             "b200seg_conv3d_wgrad_workspace": ctypes.c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 
@@ -79,7 +81,7 @@ def check(rc, what):
 
 
 # kernels launched per entry point (dice fwd = reduce + finalize; its memset is not ours)
-_KERNELS = {"b200seg_dice_ce_fwd": 2}
+_KERNELS = {"b200seg_dice_ce_fwd": 2, "b200seg_conv3d_wgrad": 3}
 launch_count = 0
 
 

@@ -63,17 +63,44 @@ extern "C" int b200seg_conv3d_fwd(const void* x, int x_ld, int x_coff, const dou
   return conv3d_fwd_direct(a, dtype, st);
 }
 
+static int wgrad_args(WgradArgs& a, const void* x, int x_ld, int x_coff, const double* x_stats, float eps, int act,
+                      const void* dy, int dy_ld, int dy_coff, float* dw, float* dbias, int B, int D, int H, int W,
+                      int Cin, int Cout, int kd, int kh, int kw, int dtype) {
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return B200SEG_EINVAL;
+  if (kd <= 0 || kh <= 0 || kw <= 0 || !(kd & 1) || !(kh & 1) || !(kw & 1)) return B200SEG_EUNSUPPORTED;
+  if (dtype != B200SEG_F16 && dtype != B200SEG_F32) return B200SEG_EINVAL;
+  a = WgradArgs{x, x_ld, x_coff, x_stats, eps, act, dy, dy_ld, dy_coff, dw, dbias, B, D, H, W, Cin, Cout, kd, kh, kw, 0};
+  return B200SEG_OK;
+}
+
+extern "C" size_t b200seg_conv3d_wgrad_workspace(int x_ld, int x_coff, int normalised, int dy_ld, int dy_coff,
+                                                 int want_bias, int B, int D, int H, int W, int Cin, int Cout,
+                                                 int kd, int kh, int kw, int dtype, int algo) {
+  WgradArgs a;
+  static const double dummy_stats = 0.0;
+  static float dummy_bias = 0.f;
+  // 16-byte aligned placeholders stand in for the tensors (only shapes/strides decide)
+  if (wgrad_args(a, (const void*)16, x_ld, x_coff, normalised ? &dummy_stats : nullptr, 1e-4f, normalised ? 1 : 0,
+                 (const void*)16, dy_ld, dy_coff, (float*)16, want_bias ? &dummy_bias : nullptr, B, D, H, W, Cin, Cout,
+                 kd, kh, kw, dtype)) return 0;
+  if (algo == B200SEG_ALGO_DIRECT) return 0;
+  if (!conv3d_wgrad_tc_supported(a, dtype)) return 0;
+  return conv3d_wgrad_tc_workspace(a);
+}
+
 extern "C" int b200seg_conv3d_wgrad(const void* x, int x_ld, int x_coff, const double* x_stats, float eps, int act,
                                     const void* dy, int dy_ld, int dy_coff, float* dw, float* dbias, int B, int D,
                                     int H, int W, int Cin, int Cout, int kd, int kh, int kw, int dtype, int algo,
-                                    void* stream) {
-  if (!x || !dy || !dw || B <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return B200SEG_EINVAL;
-  if (kd <= 0 || kh <= 0 || kw <= 0 || !(kd & 1) || !(kh & 1) || !(kw & 1)) return B200SEG_EUNSUPPORTED;
-  if (dtype != B200SEG_F16 && dtype != B200SEG_F32) return B200SEG_EINVAL;
-  WgradArgs a{x, x_ld, x_coff, x_stats, eps, act, dy, dy_ld, dy_coff, dw, dbias, B, D, H, W, Cin, Cout, kd, kh, kw, 0};
+                                    void* workspace, size_t ws_bytes, void* stream) {
+  if (!x || !dy || !dw) return B200SEG_EINVAL;
+  WgradArgs a;
+  int rc = wgrad_args(a, x, x_ld, x_coff, x_stats, eps, act, dy, dy_ld, dy_coff, dw, dbias, B, D, H, W, Cin, Cout, kd, kh, kw, dtype);
+  if (rc) return rc;
   cudaStream_t st = as_stream(stream);
-  if (algo == B200SEG_ALGO_TC) return conv3d_wgrad_tc(a, dtype, st);
-  if (algo == B200SEG_ALGO_AUTO && conv3d_wgrad_tc_supported(a, dtype)) return conv3d_wgrad_tc(a, dtype, st);
+  if (algo == B200SEG_ALGO_TC) return conv3d_wgrad_tc(a, dtype, workspace, ws_bytes, st);
+  if (algo == B200SEG_ALGO_AUTO && conv3d_wgrad_tc_supported(a, dtype) && workspace &&
+      ws_bytes >= conv3d_wgrad_tc_workspace(a))
+    return conv3d_wgrad_tc(a, dtype, workspace, ws_bytes, st);
   if (algo != B200SEG_ALGO_AUTO && algo != B200SEG_ALGO_DIRECT) return B200SEG_EINVAL;
   return conv3d_wgrad_direct(a, dtype, st);
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 
 struct ConvArgs {
   const void* x; int x_ld, x_coff;
@@ -25,7 +26,8 @@ int conv3d_fwd_direct(const ConvArgs& a, int dtype, cudaStream_t st);
 int conv3d_wgrad_direct(const WgradArgs& a, int dtype, cudaStream_t st);
 // tcgen05 paths (conv_tc.cu / wgrad_tc.cu); return B200SEG_EUNSUPPORTED when the shape does not qualify
 int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st);
-int conv3d_wgrad_tc(const WgradArgs& a, int dtype, cudaStream_t st);
+int conv3d_wgrad_tc(const WgradArgs& a, int dtype, void* workspace, size_t ws_bytes, cudaStream_t st);
+size_t conv3d_wgrad_tc_workspace(const WgradArgs& a);
 bool conv3d_fwd_tc_supported(const ConvArgs& a, int dtype);
 bool conv3d_wgrad_tc_supported(const WgradArgs& a, int dtype);
 

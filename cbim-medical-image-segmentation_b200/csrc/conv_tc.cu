@@ -528,5 +528,3 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   return B200SEG_OK;
 }
 
-bool conv3d_wgrad_tc_supported(const WgradArgs&, int) { return false; }
-int conv3d_wgrad_tc(const WgradArgs&, int, cudaStream_t) { return B200SEG_EUNSUPPORTED; }

@@ -101,9 +101,14 @@ def conv3d_wgrad(x, x_coff, Cin, x_stats, act, dy, dy_coff, Cout, ksize, want_bi
     B, D, H, W, x_ld = x.shape
     dw = torch.zeros(Cout, Cin, ksize[0], ksize[1], ksize[2], dtype=torch.float32, device=x.device)
     db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    normalised = 1 if (x_stats is not None or act) else 0
+    ws_bytes = _lib.load().b200seg_conv3d_wgrad_workspace(x_ld, x_coff, normalised, dy.shape[-1], dy_coff,
+                                                          1 if want_bias else 0, B, D, H, W, Cin, Cout,
+                                                          ksize[0], ksize[1], ksize[2], _dt(x), algo)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     call("b200seg_conv3d_wgrad", x.data_ptr(), x_ld, x_coff, _p(x_stats), eps, act,
          dy.data_ptr(), dy.shape[-1], dy_coff, dw.data_ptr(), _p(db),
-         B, D, H, W, Cin, Cout, ksize[0], ksize[1], ksize[2], _dt(x), algo, _stream())
+         B, D, H, W, Cin, Cout, ksize[0], ksize[1], ksize[2], _dt(x), algo, _p(ws), ws_bytes, _stream())
     return dw, db
 
 

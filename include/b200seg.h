@@ -169,15 +169,23 @@ int b200seg_conv3d_fwd(const void* x, int x_ld, int x_coff,
                        int kd, int kh, int kw, int dtype, int algo, void* stream);
 
 /* dw[Cout][Cin][kd][kh][kw] (fp32, the reference parameter layout, what DDP
- * all-reduces) (+)= sum_vox dy[vox][co] * act(IN(x))[vox+tap][ci].
+ * all-reduces) += sum_vox dy[vox][co] * act(IN(x))[vox+tap][ci].
  * dw must be zeroed by the caller unless accumulating.  dbias (float[Cout] or
- * NULL) += sum_vox dy.  co_off/co_total select a channel slice of a fused dy. */
+ * NULL) += sum_vox dy.  The tcgen05 path needs a caller-owned scratch buffer
+ * (split-K partial tiles + the materialised act(IN(x))) of
+ * b200seg_conv3d_wgrad_workspace() bytes; with algo=AUTO and a too-small / NULL
+ * workspace the CUDA-core path runs instead. */
+size_t b200seg_conv3d_wgrad_workspace(int x_ld, int x_coff, int normalised,
+                                      int dy_ld, int dy_coff, int want_bias,
+                                      int B, int D, int H, int W, int Cin, int Cout,
+                                      int kd, int kh, int kw, int dtype, int algo);
 int b200seg_conv3d_wgrad(const void* x, int x_ld, int x_coff,
                          const double* x_stats, float eps, int act,
                          const void* dy, int dy_ld, int dy_coff,
                          float* dw, float* dbias,
                          int B, int D, int H, int W, int Cin, int Cout,
-                         int kd, int kh, int kw, int dtype, int algo, void* stream);
+                         int kd, int kh, int kw, int dtype, int algo,
+                         void* workspace, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------
  * MaxPool3d, kernel == stride (unet_utils.py:36), floor mode, + IN sums of the

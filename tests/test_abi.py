@@ -15,7 +15,7 @@ def _header_protos():
     src = open(os.path.join(ROOT, "include", "b200seg.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     protos = {}
-    for m in re.finditer(r"\b(?:int|const char\*)\s+(b200seg_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(?:int|size_t|const char\*)\s+(b200seg_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = m.group(2).strip()
         n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
         protos[m.group(1)] = n

@@ -54,3 +54,33 @@ def test_tc_conv_matches_direct_and_torch(Cin, Cout, k, shape, mode):
         if res is not None:
             ref = ref.half().float() + res.float().permute(0, 4, 1, 2, 3)
         assert rel_err(yt.float().permute(0, 4, 1, 2, 3), ref) < 4e-3
+
+
+WCASES = [
+    (16, 16, (1, 1, 1), (1, 1, 16, 8), False),
+    (32, 32, (3, 3, 3), (1, 4, 16, 16), True),
+    (32, 64, (3, 3, 3), (2, 3, 20, 12), True),
+    (96, 64, (1, 3, 3), (1, 2, 32, 16), True),
+    (128, 128, (3, 3, 3), (1, 4, 32, 32), True),
+    (192, 256, (3, 3, 3), (1, 2, 16, 16), True),
+    (64, 320, (3, 3, 3), (1, 2, 16, 8), True),
+]
+
+
+@pytest.mark.parametrize("Cin,Cout,k,shape,normed", WCASES)
+def test_tc_wgrad_matches_direct_and_torch(Cin, Cout, k, shape, normed):
+    from b200seg import ops, _lib
+    B, D, H, W = shape
+    torch.manual_seed(9)
+    x = torch.randn(B, D, H, W, Cin, device="cuda").half()
+    dy = torch.randn(B, D, H, W, Cout, device="cuda").half()
+    st = ops.instnorm_stats(x, 0, Cin) if normed else None
+    act = ops.ACT_RELU if normed else ops.ACT_NONE
+    dwd, _ = ops.conv3d_wgrad(x, 0, Cin, st, act, dy, 0, Cout, k, algo=_lib.ALGO_DIRECT)
+    dwt, _ = ops.conv3d_wgrad(x, 0, Cin, st, act, dy, 0, Cout, k, algo=_lib.ALGO_TC)
+    assert rel_err(dwt, dwd) < 2e-3
+    xf = x.float().permute(0, 4, 1, 2, 3)
+    a = (F.relu(F.instance_norm(xf, eps=1e-4)).half().float() if normed else xf)
+    w = torch.zeros(Cout, Cin, *k, device="cuda", requires_grad=True)
+    F.conv3d(a, w, padding=[i // 2 for i in k]).backward(dy.float().permute(0, 4, 1, 2, 3))
+    assert rel_err(dwt, w.grad) < 3e-3

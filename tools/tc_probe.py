@@ -30,6 +30,50 @@ PROBES = [
 ]
 
 
+WPROBES = [
+    # name, Cin, Cout, k, (B,D,H,W), normalised
+    ("wgrad 1x1 16->16", 16, 16, (1, 1, 1), (1, 1, 16, 8), False),
+    ("wgrad 1x1 64->128", 64, 128, (1, 1, 1), (1, 2, 16, 16), False),
+    ("wgrad 1x1x3 32->32", 32, 32, (1, 1, 3), (1, 2, 16, 16), False),
+    ("wgrad 1x3x1 32->32", 32, 32, (1, 3, 1), (1, 2, 32, 8), False),
+    ("wgrad 3x1x1 32->32", 32, 32, (3, 1, 1), (1, 4, 16, 8), False),
+    ("wgrad 3x3x3 32->64 norm ragged", 32, 64, (3, 3, 3), (2, 3, 20, 12), True),
+    ("wgrad 1x3x3 96->64 norm", 96, 64, (1, 3, 3), (1, 2, 32, 16), True),
+    ("wgrad 3x3x3 128->128 norm", 128, 128, (3, 3, 3), (1, 4, 32, 32), True),
+    ("wgrad 3x3x3 192->256", 192, 256, (3, 3, 3), (1, 2, 16, 16), True),
+    ("wgrad 3x3x3 64->320", 64, 320, (3, 3, 3), (1, 2, 16, 8), True),
+]
+
+
+def run_wprobe(i):
+    import torch
+    from b200seg import ops, _lib
+    name, Cin, Cout, k, (B, D, H, W), normed = WPROBES[i]
+    torch.manual_seed(200 + i)
+    x = torch.randn(B, D, H, W, Cin, device="cuda").half()
+    dy = torch.randn(B, D, H, W, Cout, device="cuda").half()
+    st = ops.instnorm_stats(x, 0, Cin) if normed else None
+    act = ops.ACT_RELU if normed else ops.ACT_NONE
+    out = {}
+    for algo in (_lib.ALGO_DIRECT, _lib.ALGO_TC):
+        dw, _ = ops.conv3d_wgrad(x, 0, Cin, st, act, dy, 0, Cout, k, algo=algo)
+        torch.cuda.synchronize()
+        out[algo] = dw.double().cpu()
+    a, b = out[_lib.ALGO_TC], out[_lib.ALGO_DIRECT]
+    err = ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+    ok = err < 2e-3
+    print("wprobe %2d %-32s swap=%s dw_rel_err %.3e %s" % (i, name, os.environ.get("B200SEG_WGRAD_SWAP", "0"), err, "OK" if ok else "FAIL"), flush=True)
+    if not ok:
+        e = (a - b).abs()
+        print("   tc absmax %.4f direct absmax %.4f nonfinite=%d" % (a.abs().max(), b.abs().max(), (~torch.isfinite(a)).sum()))
+        print("   err by tap :", [round(v, 2) for v in e.flatten(2).amax(dim=(0, 1)).tolist()])
+        print("   err by co  :", [round(v, 2) for v in e.amax(dim=(1, 2, 3, 4)).tolist()][:40])
+        print("   err by ci  :", [round(v, 2) for v in e.amax(dim=(0, 2, 3, 4)).tolist()][:40])
+        print("   tc[0,:8,0,0,0]    :", [round(v, 2) for v in a[0, :8].flatten(1)[:, 0].tolist()])
+        print("   direct[0,:8,...]  :", [round(v, 2) for v in b[0, :8].flatten(1)[:, 0].tolist()])
+    return ok
+
+
 def run_probe(i):
     import torch
     from b200seg import ops, _lib
@@ -73,6 +117,23 @@ def run_probe(i):
 
 if __name__ == "__main__":
     arg = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if arg == "wall":
+        bad = 0
+        for i in range(len(WPROBES)):
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "w%d" % i], capture_output=True, text=True, timeout=180)
+                sys.stdout.write(r.stdout)
+                if r.returncode not in (0, 1):
+                    bad += 1
+                    print("wprobe %2d %-32s CRASHED rc=%d: %s" % (i, WPROBES[i][0], r.returncode, (r.stderr or "")[-600:].replace("\n", " | ")), flush=True)
+                elif r.returncode == 1:
+                    bad += 1
+            except subprocess.TimeoutExpired:
+                bad += 1
+                print("wprobe %2d %-32s TIMEOUT" % (i, WPROBES[i][0]), flush=True)
+        sys.exit(1 if bad else 0)
+    if arg.startswith("w"):
+        sys.exit(0 if run_wprobe(int(arg[1:])) else 1)
     if arg == "all":
         bad = 0
         for i in range(len(PROBES)):
