@@ -102,5 +102,9 @@ extern "C" int b200seg_conv3d_wgrad(const void* x, int x_ld, int x_coff, const d
       ws_bytes >= conv3d_wgrad_tc_workspace(a))
     return conv3d_wgrad_tc(a, dtype, workspace, ws_bytes, st);
   if (algo != B200SEG_ALGO_AUTO && algo != B200SEG_ALGO_DIRECT) return B200SEG_EINVAL;
+  if (algo == B200SEG_ALGO_AUTO) {
+    rc = conv3d_wgrad_small(a, dtype, st);
+    if (rc != B200SEG_EUNSUPPORTED) return rc;
+  }
   return conv3d_wgrad_direct(a, dtype, st);
 }

@@ -119,3 +119,25 @@ def test_upsample_cat(ops, dtype, tol, shp):
     co.backward(ndhwc(dcat.to(dtype)).cuda())
     assert rel_err(ncdhw(lc.grad.float()), low.grad) < max(tol, 1e-5) * 2
     assert rel_err(ncdhw(sc.grad.float()), skip.grad) < 1e-6
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("Cin,Cout,k,normed,bias", [(1, 32, (1, 3, 3), False, False), (1, 32, (3, 3, 3), False, False),
+                                                    (1, 48, (3, 3, 3), False, False), (32, 4, (1, 1, 1), False, True),
+                                                    (64, 14, (1, 1, 1), True, True)])
+def test_small_wgrad_special_cases(ops, dtype, tol, Cin, Cout, k, normed, bias):
+    """AUTO routes the Cin=1 stem and the 1x1x1 few-class head to the HBM-bound special kernels (small_conv.cu)."""
+    torch.manual_seed(5)
+    B, D, H, W = 2, 5, 12, 9
+    x = torch.randn(B, Cin, D, H, W).to(dtype).float()
+    w = torch.zeros(Cout, Cin, *k, requires_grad=True)
+    b = torch.zeros(Cout, requires_grad=True)
+    dy = torch.randn(B, Cout, D, H, W).to(dtype).float()
+    a = F.relu(F.instance_norm(x, eps=1e-4)).to(dtype).float() if normed else x
+    F.conv3d(a, w, b, padding=[i // 2 for i in k]).backward(dy)
+    xc, dyc = ndhwc(x.to(dtype)).cuda(), ndhwc(dy.to(dtype)).cuda()
+    st = ops.instnorm_stats(xc, 0, Cin) if normed else None
+    dw, db = ops.conv3d_wgrad(xc, 0, Cin, st, ops.ACT_RELU if normed else ops.ACT_NONE, dyc, 0, Cout, k, want_bias=bias)
+    assert rel_err(dw, w.grad) < tol
+    if bias:
+        assert rel_err(db, b.grad) < tol
