@@ -50,6 +50,7 @@ struct TcParams {
   int a_stage_bytes, b_stage_bytes, SA, SB;
   int tiles_h, tiles_w, n_tiles;
   int tmem_cols, acc_stages;
+  int w_resident;          // all weights of the layer live in shared memory for the CTA's lifetime (no B ring)
   int smem_a_off, smem_b_off, smem_bar_off, smem_norm_off, smem_gnorm_off, smem_stat_off;
   int* err_flag;
 };
@@ -281,22 +282,30 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   } else if (warp == kWgtWarp) {
     // =========================== WEIGHT PRODUCER (bulk TMA) ===========================
     if (lane == 0) {
-      Ring ring; ring.init(p.SB);
       const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.wimg);
       const int taps = a.kd * taps_hw;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(p, t);
-        for (int kc = 0; kc < p.NKC; ++kc) {
-          for (int zd = 0; zd < a.kd; ++zd) {
-            const int din = tc.d + zd - pd;
-            if ((unsigned)din >= (unsigned)a.D) continue;
-            for (int thw = 0; thw < taps_hw; ++thw) {
-              const int tap = zd * taps_hw + thw;
-              mbar_wait(B_EMPTY(ring.idx), ring.phase ^ 1, p.err_flag, 2);
-              mbar_arrive_expect_tx(B_FULL(ring.idx), (uint32_t)p.b_stage_bytes);
-              const uint8_t* src = wimg + ((int64_t)(tc.ntile * taps + tap) * p.NKC + kc) * p.b_stage_bytes;
-              bulk_g2s(smem_b + ring.idx * p.b_stage_bytes, src, (uint32_t)p.b_stage_bytes, B_FULL(ring.idx));
-              ring.advance();
+      if (p.w_resident) {
+        // small layers: the whole weight image is loaded once; the MMA warp indexes it directly
+        const int nblobs = p.NTILES * taps * p.NKC;
+        mbar_arrive_expect_tx(B_FULL(0), (uint32_t)(nblobs * p.b_stage_bytes));
+        for (int i = 0; i < nblobs; ++i)
+          bulk_g2s(smem_b + i * p.b_stage_bytes, wimg + (int64_t)i * p.b_stage_bytes, (uint32_t)p.b_stage_bytes, B_FULL(0));
+      } else {
+        Ring ring; ring.init(p.SB);
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+          const TileCoord tc = tile_coord(p, t);
+          for (int kc = 0; kc < p.NKC; ++kc) {
+            for (int zd = 0; zd < a.kd; ++zd) {
+              const int din = tc.d + zd - pd;
+              if ((unsigned)din >= (unsigned)a.D) continue;
+              for (int thw = 0; thw < taps_hw; ++thw) {
+                const int tap = zd * taps_hw + thw;
+                mbar_wait(B_EMPTY(ring.idx), ring.phase ^ 1, p.err_flag, 2);
+                mbar_arrive_expect_tx(B_FULL(ring.idx), (uint32_t)p.b_stage_bytes);
+                const uint8_t* src = wimg + ((int64_t)(tc.ntile * taps + tap) * p.NKC + kc) * p.b_stage_bytes;
+                bulk_g2s(smem_b + ring.idx * p.b_stage_bytes, src, (uint32_t)p.b_stage_bytes, B_FULL(ring.idx));
+                ring.advance();
+              }
             }
           }
         }
@@ -310,6 +319,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const uint32_t a_sbo = (uint32_t)p.HALO_W * 16u, a_lbo = (uint32_t)p.plane_stride;
       const uint32_t b_sbo = 128u, b_lbo = (uint32_t)p.NT * 16u;
       int it = 0;
+      const int taps_all = a.kd * taps_hw;
+      if (p.w_resident) { mbar_wait(B_FULL(0), 0, p.err_flag, 7); tc_fence_after(); }
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
         const TileCoord tc = tile_coord(p, t);
         const int acc = (p.acc_stages == 2) ? (it & 1) : 0;
@@ -327,18 +338,25 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             const uint32_t a_stage = smem_a + ra.idx * p.a_stage_bytes;
             for (int zh = 0; zh < a.kh; ++zh) {
               for (int zw = 0; zw < a.kw; ++zw) {
-                mbar_wait(B_FULL(rb.idx), rb.phase, p.err_flag, 5);
-                tc_fence_after();
+                uint32_t b_stage;
+                if (p.w_resident) {
+                  b_stage = smem_b + (uint32_t)(((tc.ntile * taps_all + (zd * a.kh + zh) * a.kw + zw) * p.NKC + kc) * p.b_stage_bytes);
+                } else {
+                  mbar_wait(B_FULL(rb.idx), rb.phase, p.err_flag, 5);
+                  tc_fence_after();
+                  b_stage = smem_b + rb.idx * p.b_stage_bytes;
+                }
                 const uint32_t a_tap = a_stage + (uint32_t)(zh * p.HALO_W + zw) * 16u;
-                const uint32_t b_stage = smem_b + rb.idx * p.b_stage_bytes;
                 for (int j = 0; j < ksteps; ++j) {
                   const uint64_t da = make_desc(a_tap + (uint32_t)(2 * j) * a_lbo, a_lbo, a_sbo);
                   const uint64_t db = make_desc(b_stage + (uint32_t)(2 * j) * b_lbo, b_lbo, b_sbo);
                   umma_f16(tmem_d, da, db, idesc, accumulate);
                   accumulate = 1;
                 }
-                umma_commit(B_EMPTY(rb.idx));     // weights slot free once these MMAs retire
-                rb.advance();
+                if (!p.w_resident) {
+                  umma_commit(B_EMPTY(rb.idx));   // weights slot free once these MMAs retire
+                  rb.advance();
+                }
               }
             }
             umma_commit(A_EMPTY(ra.idx));         // halo tile free
@@ -359,8 +377,6 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const TileCoord tc = tile_coord(p, t);
       const int acc = (p.acc_stages == 2) ? (it & 1) : 0;
       const uint32_t acc_phase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
-      mbar_wait(T_FULL(acc), acc_phase, p.err_flag, 6);
-      tc_fence_after();
       const int h = tc.h0 + hl, w = tc.w0 + wl;
       const bool valid = (h < a.H) && (w < a.W);
       const int64_t vox = ((int64_t)(tc.b * a.D + tc.d) * a.H + h) * a.W + w;
@@ -369,9 +385,24 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const __half* rp = a.res ? reinterpret_cast<const __half*>(a.res) + vox * a.r_ld + a.r_coff + co_base : nullptr;
       const __half* gp = dgrad ? reinterpret_cast<const __half*>(a.gx) + vox * a.gx_ld + a.gx_coff + co_base : nullptr;
       float* wstat = s_stat + ((q * a.B + tc.b) * a.Cout + co_base) * 2;
+      // side input of the epilogue (residual, or x for the dgrad ReLU mask): fetched one 16-channel chunk AHEAD so
+      // its global-memory latency overlaps the wait for the accumulator and the previous chunk's work
+      const __half* side = dgrad ? gp : rp;
+      uint4 nx0 = make_uint4(0, 0, 0, 0), nx1 = make_uint4(0, 0, 0, 0);
+      if (side && valid) {
+        nx0 = __ldg(reinterpret_cast<const uint4*>(side));
+        nx1 = __ldg(reinterpret_cast<const uint4*>(side + 8));
+      }
+      mbar_wait(T_FULL(acc), acc_phase, p.err_flag, 6);
+      tc_fence_after();
       for (int n0 = 0; n0 < p.NT; n0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT + n0), v);
+        const uint4 cur0 = nx0, cur1 = nx1;
+        if (side && valid && n0 + 16 < p.NT) {
+          nx0 = __ldg(reinterpret_cast<const uint4*>(side + n0 + 16));
+          nx1 = __ldg(reinterpret_cast<const uint4*>(side + n0 + 24));
+        }
         tmem_ld_wait();
         float r[16], s2[16];
 #pragma unroll
@@ -381,14 +412,21 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) r[j] += a.bias[co_base + n0 + j];
           }
+          float sv[16];
+          if (side) {
+            const __half2* h0 = reinterpret_cast<const __half2*>(&cur0);
+            const __half2* h1 = reinterpret_cast<const __half2*>(&cur1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f0 = __half22float2(h0[j]), f1 = __half22float2(h1[j]);
+              sv[2 * j] = f0.x; sv[2 * j + 1] = f0.y; sv[8 + 2 * j] = f1.x; sv[8 + 2 * j + 1] = f1.y;
+            }
+          }
           if (dgrad) {
-            float xv[16];
-            ld8<__half>(gp + n0, reinterpret_cast<float(&)[8]>(xv[0]));
-            ld8<__half>(gp + n0 + 8, reinterpret_cast<float(&)[8]>(xv[8]));
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 mr = s_gnorm[tc.b * a.Cout + co_base + n0 + j];
-              const float hx = (xv[j] - mr.x) * mr.y;
+              const float hx = (sv[j] - mr.x) * mr.y;
               float g = (a.g_act == B200SEG_ACT_RELU && !(hx > 0.f)) ? 0.f : r[j];
               g = __half2float(__float2half_rn(g));
               r[j] = g; s2[j] = g * hx;
@@ -397,11 +435,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) r[j] = __half2float(__float2half_rn(r[j]));
             if (rp) {
-              float rv[16];
-              ld8<__half>(rp + n0, reinterpret_cast<float(&)[8]>(rv[0]));
-              ld8<__half>(rp + n0 + 8, reinterpret_cast<float(&)[8]>(rv[8]));
 #pragma unroll
-              for (int j = 0; j < 16; ++j) r[j] = __half2float(__float2half_rn(r[j] + rv[j]));
+              for (int j = 0; j < 16; ++j) r[j] = __half2float(__float2half_rn(r[j] + sv[j]));
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) s2[j] = r[j] * r[j];
@@ -498,15 +533,24 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   const int norm_bytes = a.B * a.Cin * 8;
   const int stat_bytes = kEpiWarps * a.B * a.Cout * 2 * 4;
   const int budget = 227 * 1024 - 1024 - norm_bytes - stat_bytes - a.B * a.Cout * 8 - 512;
-  p.SB = 4; p.SA = 4;
-  while (p.SA * p.a_stage_bytes + p.SB * p.b_stage_bytes > budget && (p.SA > 2 || p.SB > 2)) {
-    if (p.SB > 2 && (p.SB * p.b_stage_bytes >= p.SA * p.a_stage_bytes || p.SA <= 2)) --p.SB; else --p.SA;
+  const int64_t w_total = (int64_t)a.kd * a.kh * a.kw * a.Cin * a.Cout * 2;
+  int b_region;
+  if (w_total <= 112 * 1024 && w_total + 2 * p.a_stage_bytes <= budget) {
+    p.w_resident = 1; p.SB = 1;
+    b_region = (int)w_total;
+    p.SA = (budget - b_region) / p.a_stage_bytes; if (p.SA > 4) p.SA = 4;
+  } else {
+    p.w_resident = 0;
+    p.SA = 4;
+    while (p.SA > 2 && p.SA * p.a_stage_bytes + 3 * p.b_stage_bytes > budget) --p.SA;
+    p.SB = (budget - p.SA * p.a_stage_bytes) / p.b_stage_bytes; if (p.SB > 8) p.SB = 8;
+    if (p.SB < 2) return B200SEG_EUNSUPPORTED;
+    b_region = p.SB * p.b_stage_bytes;
   }
-  if (p.SA * p.a_stage_bytes + p.SB * p.b_stage_bytes > budget) return B200SEG_EUNSUPPORTED;
   int off = 0;
   p.smem_a_off = off; off += p.SA * p.a_stage_bytes;
   off = (off + 127) / 128 * 128;
-  p.smem_b_off = off; off += p.SB * p.b_stage_bytes;
+  p.smem_b_off = off; off += b_region;
   off = (off + 15) / 16 * 16;
   p.smem_bar_off = off; off += (2 * p.SA + 2 * p.SB + 4) * 8 + 16;
   off = (off + 15) / 16 * 16;

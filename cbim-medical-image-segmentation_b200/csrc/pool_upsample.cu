@@ -211,11 +211,33 @@ __device__ __forceinline__ int axis_taps(float scale, int i, int in_size, int ou
   return n;
 }
 
+// per-axis tap tables, built once per block in shared memory: for input index i the output indices whose
+// stencil touches i and their (non-zero) weights
+struct AxisTab { int n; int o[kMaxTaps]; float w[kMaxTaps]; };
+__device__ __forceinline__ void build_axis_table(AxisTab* tab, float scale, int in_size, int out_size) {
+  for (int i = threadIdx.x; i < in_size; i += kThreads) {
+    int oo[kMaxTaps]; float ww[kMaxTaps];
+    const int n = axis_taps(scale, i, in_size, out_size, oo, ww);
+    int m = 0;
+    for (int k = 0; k < n; ++k)
+      if (ww[k] != 0.f) { tab[i].o[m] = oo[k]; tab[i].w[m] = ww[k]; ++m; }
+    tab[i].n = m;
+  }
+}
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 upsample_bwd_kernel(const T* __restrict__ dy, int dy_ld, int dy_coff, T* __restrict__ dx, int dx_ld, int dx_coff,
                     int accumulate, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int C,
                     float rd, float rh, float rw, int64_t vpb) {
+  extern __shared__ float smem[];
+  AxisTab* td = reinterpret_cast<AxisTab*>(smem);
+  AxisTab* th = td + Di;
+  AxisTab* tw = th + Hi;
+  build_axis_table(td, rd, Di, Do);
+  build_axis_table(th, rh, Hi, Ho);
+  build_axis_table(tw, rw, Wi, Wo);
+  __syncthreads();
   const int64_t Vi = (int64_t)Di * Hi * Wi;
   const int b = blockIdx.y;
   Map m = make_map<VEC>(C);
@@ -224,21 +246,18 @@ upsample_bwd_kernel(const T* __restrict__ dy, int dy_ld, int dy_coff, T* __restr
   const T* dyb = dy + (int64_t)b * Do * Ho * Wo * dy_ld + dy_coff + m.cchunk * VEC;
   for (int64_t v = v0 + m.vloc; v < v1; v += m.vpp) {
     int wi = (int)(v % Wi); int64_t t = v / Wi; int hi = (int)(t % Hi); int di = (int)(t / Hi);
-    int od[kMaxTaps], oh[kMaxTaps], ow[kMaxTaps]; float wd[kMaxTaps], wh[kMaxTaps], ww[kMaxTaps];
-    int nd = axis_taps(rd, di, Di, Do, od, wd);
-    int nh = axis_taps(rh, hi, Hi, Ho, oh, wh);
-    int nw = axis_taps(rw, wi, Wi, Wo, ow, ww);
+    const AxisTab& ad = td[di]; const AxisTab& ah = th[hi]; const AxisTab& aw = tw[wi];
     float acc[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-    for (int a = 0; a < nd; ++a)
-      for (int bq = 0; bq < nh; ++bq) {
-        float wdh = wd[a] * wh[bq];
-        const T* row = dyb + (((int64_t)od[a] * Ho + oh[bq]) * Wo) * dy_ld;
-        for (int c = 0; c < nw; ++c) {
+    for (int a = 0; a < ad.n; ++a)
+      for (int bq = 0; bq < ah.n; ++bq) {
+        const float wdh = ad.w[a] * ah.w[bq];
+        const T* row = dyb + (((int64_t)ad.o[a] * Ho + ah.o[bq]) * Wo) * dy_ld;
+        for (int c = 0; c < aw.n; ++c) {
           float g[VEC];
-          VecIO<VEC, T>::ld(row + (int64_t)ow[c] * dy_ld, g);
-          float wt = wdh * ww[c];
+          VecIO<VEC, T>::ld(row + (int64_t)aw.o[c] * dy_ld, g);
+          const float wt = wdh * aw.w[c];
 #pragma unroll
           for (int i = 0; i < VEC; ++i) acc[i] += wt * g[i];
         }
@@ -351,8 +370,11 @@ extern "C" int b200seg_upsample_trilinear_bwd(const void* dy, int dy_ld, int dy_
       (Ho > 1 && rh > 0.f && 2.0f / rh + 3.0f > (float)kMaxTaps && Ho > kMaxTaps) ||
       (Wo > 1 && rw > 0.f && 2.0f / rw + 3.0f > (float)kMaxTaps && Wo > kMaxTaps))
     return B200SEG_EUNSUPPORTED;
+  const size_t tab_bytes = sizeof(AxisTab) * (size_t)(Di + Hi + Wi);
+  if (tab_bytes > 96 * 1024) return B200SEG_EUNSUPPORTED;
   DISPATCH_TV(dtype, vok, {
-    upsample_bwd_kernel<T, VEC><<<grid, kThreads, 0, st>>>((const T*)dy, dy_ld, dy_coff, (T*)dx, dx_ld, dx_coff, accumulate,
+    if (tab_bytes > 48 * 1024) cudaFuncSetAttribute(upsample_bwd_kernel<T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes);
+    upsample_bwd_kernel<T, VEC><<<grid, kThreads, tab_bytes, st>>>((const T*)dy, dy_ld, dy_coff, (T*)dx, dx_ld, dx_coff, accumulate,
                                                            Di, Hi, Wi, Do, Ho, Wo, C, rd, rh, rw, vpb);
   })
   B200_CHECK_LAUNCH("upsample_bwd_kernel");

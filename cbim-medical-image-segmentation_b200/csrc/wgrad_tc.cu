@@ -100,6 +100,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // SWIZZLE_NONE matrix descriptor.  MN-major operands: lbo = stride between core matrices along K (voxels),
 // sbo = stride between core matrices along M/N (channel planes)  (cute::UMMA::make_umma_desc<Major::MN>).
@@ -178,7 +183,12 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
     const int vstep_a = kLoadGroupThreads / cpv_a;
     const int c8_a = lt % cpv_a, v0_a = lt / cpv_a;
     const int sh_a = vstep_a / p.HALO_W, sw_a = vstep_a % p.HALO_W;
+    // Both operands are raw fp16, so they are staged with cp.async (LDGSTS): no register round trip, every
+    // 16-B chunk of a stage is in flight at once, out-of-volume voxels are zero-filled by src-size 0.  A stage is
+    // published one stage late (wait_group 1 -> fence.proxy.async -> mbarrier arrive), so the copies of stage
+    // k+1 overlap the completion of stage k.
     int idx = 0; uint32_t phase = 0; int stage_no = 0;
+    int pending_slot = -1;
     for (int vt = job.s; vt < p.nvt; vt += p.S) {
       int t = vt;
       const int w0 = (t % p.tiles_w) * TW; t /= p.tiles_w;
@@ -188,56 +198,44 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
       if ((unsigned)din >= (unsigned)p.D) continue;
       if ((stage_no & 1) == grp) {
         mbar_wait(EMPTY(idx), phase ^ 1, 1);
-        uint8_t* sdy = smem + idx * p.stage_bytes;
-        uint8_t* sa = sdy + p.dy_bytes;
-        // ---- dy tile
+        const uint32_t sdy = smem_u32(smem + idx * p.stage_bytes);
+        const uint32_t sa = sdy + (uint32_t)p.dy_bytes;
         if (lt < act_d) {
           const __half* src = p.dy + ((int64_t)(b * p.D + d) * p.H * p.W) * p.dy_ld + p.dy_coff + co0 + c8_d * 8;
-          uint8_t* dst = sdy + c8_d * p.dy_plane;
-          for (int v = v0_d; v < TH * TW; v += 4 * vstep_d) {
-            uint4 r[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int vv = v + u * vstep_d;
-              const int h = h0 + (vv >> 3), w = w0 + (vv & 7);
-              r[u] = make_uint4(0, 0, 0, 0);
-              if (vv < TH * TW && h < p.H && w < p.W)
-                r[u] = __ldg(reinterpret_cast<const uint4*>(src + ((int64_t)h * p.W + w) * p.dy_ld));
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int vv = v + u * vstep_d;
-              if (vv < TH * TW) *reinterpret_cast<uint4*>(dst + vv * 16) = r[u];
-            }
+          const uint32_t dst = sdy + (uint32_t)(c8_d * p.dy_plane);
+          for (int v = v0_d; v < TH * TW; v += vstep_d) {
+            const int h = h0 + (v >> 3), w = w0 + (v & 7);
+            const bool ok = h < p.H && w < p.W;
+            cp_async16(dst + (uint32_t)v * 16u, ok ? src + ((int64_t)h * p.W + w) * p.dy_ld : src, ok ? 16u : 0u);
           }
         }
-        // ---- a halo tile
         if (lt < act_a) {
           const __half* src = p.a + ((int64_t)(b * p.D + din) * p.H * p.W) * p.a_ld + p.a_coff + ci0 + c8_a * 8;
-          uint8_t* dst = sa + c8_a * p.a_plane;
+          const uint32_t dst = sa + (uint32_t)(c8_a * p.a_plane);
           int hh = v0_a / p.HALO_W, ww = v0_a % p.HALO_W;
-          for (int v = v0_a; v < p.nvox_h; v += 4 * vstep_a) {
-            uint4 r[4]; int vv[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              vv[u] = hh * p.HALO_W + ww;
-              const int h = h0 - ph + hh, w = w0 - pw + ww;
-              r[u] = make_uint4(0, 0, 0, 0);
-              if (vv[u] < p.nvox_h && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W)
-                r[u] = __ldg(reinterpret_cast<const uint4*>(src + ((int64_t)h * p.W + w) * p.a_ld));
-              hh += sh_a; ww += sw_a;
-              if (ww >= p.HALO_W) { ww -= p.HALO_W; ++hh; }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (vv[u] < p.nvox_h) *reinterpret_cast<uint4*>(dst + vv[u] * 16) = r[u];
+          for (int v = v0_a; v < p.nvox_h; v += vstep_a) {
+            const int h = h0 - ph + hh, w = w0 - pw + ww;
+            const bool ok = (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
+            cp_async16(dst + (uint32_t)v * 16u, ok ? src + ((int64_t)h * p.W + w) * p.a_ld : src, ok ? 16u : 0u);
+            hh += sh_a; ww += sw_a;
+            if (ww >= p.HALO_W) { ww -= p.HALO_W; ++hh; }
           }
         }
-        fence_proxy_async();
-        mbar_arrive(FULL(idx));
+        cp_async_commit();
+        if (pending_slot >= 0) {
+          cp_async_wait<1>();
+          fence_proxy_async();
+          mbar_arrive(FULL(pending_slot));
+        }
+        pending_slot = idx;
       }
       if (++idx == p.NS) { idx = 0; phase ^= 1; }
       ++stage_no;
+    }
+    if (pending_slot >= 0) {
+      cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(FULL(pending_slot));
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
