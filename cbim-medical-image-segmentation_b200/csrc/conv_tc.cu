@@ -76,15 +76,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU
+// bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.  The diagnostics
+// live out of line so the polling loop stays a handful of instructions (the single MMA-issuing thread runs it
+// once per weight tile).
+__device__ __noinline__ void mbar_timeout(int* err_flag, int code, uint32_t parity) {
+  if (err_flag) atomicExch(err_flag, code);
+  printf("b200seg conv_tc: mbarrier timeout code=%d block=%d thread=%d parity=%u\n", code, blockIdx.x, threadIdx.x, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > kSpinLimit) {
-      if (err_flag) atomicExch(err_flag, code);
-      printf("b200seg conv_tc: mbarrier timeout code=%d block=%d thread=%d parity=%u\n", code, blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
+    if (++spins > kSpinLimit) mbar_timeout(err_flag, code, parity);
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -313,13 +317,19 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER (one thread) ===========================
-    if (lane == 0) {
+    {   // the whole warp runs the (warp-uniform) control flow; lane 0 alone issues tcgen05 instructions
+      // The issue loop is the critical path of the whole CTA (one thread feeds the tensor core), so it is kept to
+      // a few instructions per MMA: descriptors are 64-bit templates plus a 16-byte-unit start address that is
+      // advanced by constant adds (tap to the right: +1, tap row down: +HALO_W, K step: +2*LBO).
       Ring ra, rb; ra.init(p.SA); rb.init(p.SB);
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t a_sbo = (uint32_t)p.HALO_W * 16u, a_lbo = (uint32_t)p.plane_stride;
-      const uint32_t b_sbo = 128u, b_lbo = (uint32_t)p.NT * 16u;
-      int it = 0;
+      const uint64_t a_tmpl = make_desc(0, (uint32_t)p.plane_stride, (uint32_t)p.HALO_W * 16u);
+      const uint64_t b_tmpl = make_desc(0, (uint32_t)p.NT * 16u, 128u);
+      const uint32_t a_kstep = (2u * (uint32_t)p.plane_stride) >> 4, b_kstep = (2u * (uint32_t)p.NT * 16u) >> 4;
+      const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
+      const uint32_t smem_a16 = smem_a >> 4, smem_b16 = smem_b >> 4;
       const int taps_all = a.kd * taps_hw;
+      int it = 0;
       if (p.w_resident) { mbar_wait(B_FULL(0), 0, p.err_flag, 7); tc_fence_after(); }
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
         const TileCoord tc = tile_coord(p, t);
@@ -335,35 +345,44 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             if ((unsigned)din >= (unsigned)a.D) continue;
             mbar_wait(A_FULL(ra.idx), ra.phase, p.err_flag, 4);
             tc_fence_after();
-            const uint32_t a_stage = smem_a + ra.idx * p.a_stage_bytes;
+            uint64_t da_row = a_tmpl + (uint64_t)(smem_a16 + (uint32_t)ra.idx * a_stage16);
+            // resident image: blob (ntile, tap, kc); consecutive in-plane taps are NKC blobs apart
+            uint64_t db_res = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)((tc.ntile * taps_all + zd * taps_hw) * p.NKC + kc) * b_stage16);
             for (int zh = 0; zh < a.kh; ++zh) {
+              uint64_t da_tap = da_row;
               for (int zw = 0; zw < a.kw; ++zw) {
-                uint32_t b_stage;
+                uint64_t db;
                 if (p.w_resident) {
-                  b_stage = smem_b + (uint32_t)(((tc.ntile * taps_all + (zd * a.kh + zh) * a.kw + zw) * p.NKC + kc) * p.b_stage_bytes);
+                  db = db_res;
+                  db_res += (uint64_t)((uint32_t)p.NKC * b_stage16);
                 } else {
                   mbar_wait(B_FULL(rb.idx), rb.phase, p.err_flag, 5);
                   tc_fence_after();
-                  b_stage = smem_b + rb.idx * p.b_stage_bytes;
+                  db = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)rb.idx * b_stage16);
                 }
-                const uint32_t a_tap = a_stage + (uint32_t)(zh * p.HALO_W + zw) * 16u;
+                uint64_t da = da_tap;
+#pragma unroll 4
                 for (int j = 0; j < ksteps; ++j) {
-                  const uint64_t da = make_desc(a_tap + (uint32_t)(2 * j) * a_lbo, a_lbo, a_sbo);
-                  const uint64_t db = make_desc(b_stage + (uint32_t)(2 * j) * b_lbo, b_lbo, b_sbo);
-                  umma_f16(tmem_d, da, db, idesc, accumulate);
+                  if (lane == 0) umma_f16(tmem_d, da, db, idesc, accumulate);
                   accumulate = 1;
+                  da += a_kstep; db += b_kstep;
                 }
                 if (!p.w_resident) {
-                  umma_commit(B_EMPTY(rb.idx));   // weights slot free once these MMAs retire
+                  if (lane == 0) umma_commit(B_EMPTY(rb.idx));   // weights slot free once these MMAs retire
+                  __syncwarp();
                   rb.advance();
                 }
+                da_tap += 1;                      // next tap to the right: 16 B
               }
+              da_row += (uint64_t)p.HALO_W;       // next tap row: HALO_W voxels
             }
-            umma_commit(A_EMPTY(ra.idx));         // halo tile free
+            if (lane == 0) umma_commit(A_EMPTY(ra.idx));         // halo tile free
+            __syncwarp();
             ra.advance();
           }
         }
-        umma_commit(T_FULL(acc));                 // accumulator complete -> epilogue
+        if (lane == 0) umma_commit(T_FULL(acc));                 // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else {

@@ -61,7 +61,9 @@ wgrad_cin1_kernel(WgradArgs a, int64_t vox_per_warp) {
 template <typename T, int MAXCO>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 wgrad_head_kernel(WgradArgs a, int64_t vox_per_warp) {
-  __shared__ float s_mean[128], s_rstd[128];
+  __shared__ float s_mean_all[kWarpsPerBlock][128], s_rstd_all[kWarpsPerBlock][128];   // per warp: runs may sit in different samples
+  float* s_mean = s_mean_all[threadIdx.x >> 5];
+  float* s_rstd = s_rstd_all[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int64_t warp_id = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t V = (int64_t)a.D * a.H * a.W, total = (int64_t)a.B * V;

@@ -63,13 +63,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+__device__ __noinline__ void mbar_timeout(int code, uint32_t parity) {
+  printf("b200seg wgrad_tc: mbarrier timeout code=%d block=%d thread=%d parity=%u\n", code, blockIdx.x, threadIdx.x, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > kSpinLimit) {
-      printf("b200seg wgrad_tc: mbarrier timeout code=%d block=%d thread=%d parity=%u\n", code, blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
+    if (++spins > kSpinLimit) mbar_timeout(code, parity);
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -239,38 +241,47 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
-    if (lane == 0) {
+    {   // warp-uniform control flow; lane 0 alone issues tcgen05 instructions
       const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NTC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       uint32_t dy_lbo = 128u, dy_sbo = (uint32_t)p.dy_plane;
       uint32_t a_lbo = (uint32_t)p.HALO_W * 16u, a_sbo = (uint32_t)p.a_plane;
       if (p.swap_lbo_sbo) { uint32_t t1 = dy_lbo; dy_lbo = dy_sbo; dy_sbo = t1; t1 = a_lbo; a_lbo = a_sbo; a_sbo = t1; }
+      // lean issue loop (this one thread feeds the tensor core): descriptor templates + constant adds
+      const uint64_t dy_tmpl = make_desc(0, dy_lbo, dy_sbo), a_tmpl = make_desc(0, a_lbo, a_sbo);
+      const uint32_t a_kstep = (2u * (uint32_t)p.HALO_W * 16u) >> 4;    // two voxel rows per K=16 step
+      const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, dy16 = (uint32_t)p.dy_bytes >> 4;
+      const uint32_t smem16 = smem_u32(smem) >> 4;
+      const int zh0 = job.tap0 / p.kw, zw0 = job.tap0 % p.kw;
+      const int dslab = p.tiles_w * p.tiles_h;
       int idx = 0; uint32_t phase = 0; uint32_t accumulate = 0;
       for (int vt = job.s; vt < p.nvt; vt += p.S) {
-        const int d = (vt / (p.tiles_w * p.tiles_h)) % p.D;
+        const int d = (vt / dslab) % p.D;
         const int din = d + job.zd - pd;
         if ((unsigned)din >= (unsigned)p.D) continue;
         mbar_wait(FULL(idx), phase, 2);
         tc_fence_after();
-        const uint32_t sdy = smem_u32(smem + idx * p.stage_bytes);
-        const uint32_t sa = sdy + (uint32_t)p.dy_bytes;
+        const uint64_t da0 = dy_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16);
+        uint64_t db_tap = a_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16 + dy16 + (uint32_t)(zh0 * p.HALO_W + zw0));
+        int zw = zw0;
+        uint32_t tmem_d = tmem_base;
         for (int tl = 0; tl < job.ntaps; ++tl) {
-          const int thw = job.tap0 + tl;
-          const int zh = thw / p.kw, zw = thw % p.kw;
-          const uint32_t a_tap = sa + (uint32_t)(zh * p.HALO_W + zw) * 16u;
-          const uint32_t tmem_d = tmem_base + (uint32_t)(tl * p.NTC);
-#pragma unroll 1
+          uint64_t da = da0, db = db_tap;
+#pragma unroll
           for (int j = 0; j < (TH * TW) / 16; ++j) {
-            // K step j = voxel rows 2j, 2j+1 of the tile
-            const uint64_t da = make_desc(sdy + (uint32_t)j * 256u, dy_lbo, dy_sbo);
-            const uint64_t db = make_desc(a_tap + (uint32_t)j * 2u * (uint32_t)p.HALO_W * 16u, a_lbo, a_sbo);
-            umma_f16(tmem_d, da, db, idesc, (accumulate | (uint32_t)(j > 0)));
+            if (lane == 0) umma_f16(tmem_d, da, db, idesc, (accumulate | (uint32_t)(j > 0)));
+            da += 16;            // 2 voxel rows of the dy tile = 256 B
+            db += a_kstep;
           }
+          tmem_d += (uint32_t)p.NTC;
+          // next in-plane tap: one voxel to the right, or wrap to the next halo row
+          if (++zw == p.kw) { zw = 0; db_tap += (uint64_t)(p.HALO_W - (p.kw - 1)); } else db_tap += 1;
         }
         accumulate = 1;
-        umma_commit(EMPTY(idx));
+        if (lane == 0) umma_commit(EMPTY(idx));
+        __syncwarp();
         if (++idx == p.NS) { idx = 0; phase ^= 1; }
       }
-      umma_commit(DONE);
+      if (lane == 0) umma_commit(DONE);
     }
   } else if (warp < kEpiWarps) {
     // =========================== EPILOGUE (once) ===========================
