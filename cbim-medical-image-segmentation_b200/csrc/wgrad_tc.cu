@@ -15,7 +15,7 @@
 //   * split-K over voxel tiles fills the machine: grid = jobs x S; partial D tiles go to a workspace with
 //     plain coalesced stores and a small second kernel reduces them into dW (+=) — no atomics.
 // Warp roles (448 threads, 1 CTA/SM): warps 0-3 epilogue, warp 4 MMA issue + TMEM alloc, warp 5 idle,
-// warps 6-13 loaders (two groups alternating stages).
+// warps 6-13 loaders (cp.async, all 256 threads per stage, stage k published while stage k+1 is in flight).
 #include "common.cuh"
 #include "conv_args.h"
 #include <string.h>
@@ -28,9 +28,9 @@ constexpr int TH = 16, TW = 8;
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kLoadWarp0 = 6;
-constexpr int kLoadGroups = 2;
-constexpr int kLoadGroupThreads = 128;
-constexpr int kThreads = (kLoadWarp0 + kLoadGroups * 4) * 32;   // 448
+constexpr int kLoadGroups = 1;             // all loader warps cooperate on every stage (deferred publication needs
+constexpr int kLoadGroupThreads = 256;     // consecutive stages from the same threads; works for a 2-slot ring)
+constexpr int kThreads = kLoadWarp0 * 32 + kLoadGroups * kLoadGroupThreads;   // 448
 constexpr uint32_t kSpinLimit = 1u << 24;
 constexpr int MT = 128;                    // output-channel tile (GEMM M)
 
@@ -173,8 +173,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
 
   if (warp >= kLoadWarp0) {
     // =========================== LOADERS ===========================
-    const int grp = (warp - kLoadWarp0) >> 2;
-    const int lt = threadIdx.x - (kLoadWarp0 * 32 + grp * kLoadGroupThreads);
+    const int lt = threadIdx.x - kLoadWarp0 * 32;
     // dy tile: cpv planes, thread owns plane (lt % cpv) and walks voxels v0, v0+vstep, ...
     const int cpv_d = co_real / 8;
     const int act_d = (kLoadGroupThreads / cpv_d) * cpv_d;
@@ -198,7 +197,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
       const int d = t % p.D; const int b = t / p.D;
       const int din = d + job.zd - pd;
       if ((unsigned)din >= (unsigned)p.D) continue;
-      if ((stage_no & 1) == grp) {
+      {
         mbar_wait(EMPTY(idx), phase ^ 1, 1);
         const uint32_t sdy = smem_u32(smem + idx * p.stage_bytes);
         const uint32_t sa = sdy + (uint32_t)p.dy_bytes;

@@ -21,6 +21,8 @@ CASES = [
     (128, 256, (3, 3, 3), (1, 2, 16, 8), "norm"),
     (64, 32, (3, 3, 3), (2, 3, 16, 16), "dgrad"),
     (32, 32, (1, 3, 3), (1, 8, 64, 64), "normres"),
+    (128, 128, (3, 3, 3), (1, 16, 64, 64), "normres"),   # many tiles per CTA, streamed weights
+    (64, 64, (1, 3, 3), (1, 16, 128, 128), "normres"),   # resident weights, many tiles
 ]
 
 
@@ -62,6 +64,8 @@ WCASES = [
     (32, 64, (3, 3, 3), (2, 3, 20, 12), True),
     (96, 64, (1, 3, 3), (1, 2, 32, 16), True),
     (128, 128, (3, 3, 3), (1, 4, 32, 32), True),
+    (128, 128, (3, 3, 3), (1, 16, 64, 64), True),     # many voxel tiles per CTA on the 2-slot ring
+    (32, 32, (1, 3, 3), (1, 16, 128, 128), True),     # 148-way split-K, long accumulation
     (192, 256, (3, 3, 3), (1, 2, 16, 16), True),
     (64, 320, (3, 3, 3), (1, 2, 16, 8), True),
 ]
