@@ -28,6 +28,7 @@
 #include "conv_args.h"
 #include <string.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -53,6 +54,7 @@ struct TcParams {
   int w_resident;          // all weights of the layer live in shared memory for the CTA's lifetime (no B ring)
   int smem_a_off, smem_b_off, smem_bar_off, smem_norm_off, smem_gnorm_off, smem_stat_off;
   int* err_flag;
+  int debug;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -137,6 +139,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;                    // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
 }
 
+// optional cycle accounting of block 0 (B200SEG_TC_DEBUG=1): where each warp role spends its time
+__device__ long long g_tc_dbg[32];
+#define DBG_ADD(slot, val) do { if (dbg) atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_dbg[slot]), (unsigned long long)(val)); } while (0)
+
 struct Ring {
   int idx; uint32_t phase; int n;
   __device__ __forceinline__ void init(int n_) { idx = 0; phase = 0; n = n_; }
@@ -210,6 +216,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int ksteps = p.KC / 16;
+  const bool dbg = p.debug && blockIdx.x == 0;
 
   if (warp >= kLoadWarp0) {
     // =========================== A LOADERS ===========================
@@ -238,7 +245,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           const int din = tc.d + zd - pd;
           if ((unsigned)din >= (unsigned)a.D) continue;
           if ((stage_no & 1) == grp) {
+            const bool dl = dbg && grp == 0 && lt == 0;
+            long long q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+            if (dl) q0 = clock64();
             mbar_wait(A_EMPTY(ring.idx), ring.phase ^ 1, p.err_flag, 1);
+            if (dl) q1 = clock64();
             uint8_t* sdst = smem + p.smem_a_off + ring.idx * p.a_stage_bytes;
             const __half* xs = xbase + ((int64_t)(tc.b * a.D + din) * a.H * a.W) * a.x_ld + a.x_coff + kc * p.KC;
             const float2* nrm = s_norm + tc.b * a.Cin + kc * p.KC;
@@ -252,6 +263,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               raw[k] = make_uint4(0, 0, 0, 0);
               if (ok[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(xs + ((int64_t)h * a.W + w) * a.x_ld + c_c8[k] * 8));
             }
+            if (dl) q2 = clock64();
 #pragma unroll
             for (int k = 0; k < kMaxChunksPerThread; ++k) {
               if (c_hh[k] < 0) continue;
@@ -275,8 +287,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               const int vox = c_hh[k] * p.HALO_W + c_ww[k];
               *reinterpret_cast<uint4*>(sdst + c_c8[k] * p.plane_stride + vox * 16) = o;
             }
+            if (dl) q3 = clock64();
             fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(A_FULL(ring.idx));
+            if (dl) { DBG_ADD(0, q1 - q0); DBG_ADD(1, q2 - q1); DBG_ADD(2, q3 - q2); DBG_ADD(3, clock64() - q3); DBG_ADD(4, 1); }
           }
           ring.advance();
           ++stage_no;
@@ -335,7 +349,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         const TileCoord tc = tile_coord(p, t);
         const int acc = (p.acc_stages == 2) ? (it & 1) : 0;
         const uint32_t acc_phase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
+        long long m0 = 0;
+        if (dbg && lane == 0) m0 = clock64();
         mbar_wait(T_EMPTY(acc), acc_phase ^ 1, p.err_flag, 3);
+        if (dbg && lane == 0) DBG_ADD(8, clock64() - m0);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.NT);
         uint32_t accumulate = 0;
@@ -343,7 +360,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           for (int zd = 0; zd < a.kd; ++zd) {
             const int din = tc.d + zd - pd;
             if ((unsigned)din >= (unsigned)a.D) continue;
+            if (dbg && lane == 0) m0 = clock64();
             mbar_wait(A_FULL(ra.idx), ra.phase, p.err_flag, 4);
+            if (dbg && lane == 0) { DBG_ADD(9, clock64() - m0); DBG_ADD(12, 1); m0 = clock64(); }
             tc_fence_after();
             uint64_t da_row = a_tmpl + (uint64_t)(smem_a16 + (uint32_t)ra.idx * a_stage16);
             // resident image: blob (ntile, tap, kc); consecutive in-plane taps are NKC blobs apart
@@ -356,7 +375,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                   db = db_res;
                   db_res += (uint64_t)((uint32_t)p.NKC * b_stage16);
                 } else {
+                  long long b0 = 0;
+                  if (dbg && lane == 0) b0 = clock64();
                   mbar_wait(B_FULL(rb.idx), rb.phase, p.err_flag, 5);
+                  if (dbg && lane == 0) DBG_ADD(10, clock64() - b0);
                   tc_fence_after();
                   db = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)rb.idx * b_stage16);
                 }
@@ -378,6 +400,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             }
             if (lane == 0) umma_commit(A_EMPTY(ra.idx));         // halo tile free
             __syncwarp();
+            if (dbg && lane == 0) DBG_ADD(11, clock64() - m0);      // issue time of one stage (incl. weight waits)
             ra.advance();
           }
         }
@@ -412,7 +435,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         nx0 = __ldg(reinterpret_cast<const uint4*>(side));
         nx1 = __ldg(reinterpret_cast<const uint4*>(side + 8));
       }
+      long long e0 = 0;
+      const bool de = dbg && threadIdx.x == 0;
+      if (de) e0 = clock64();
       mbar_wait(T_FULL(acc), acc_phase, p.err_flag, 6);
+      if (de) { DBG_ADD(16, clock64() - e0); e0 = clock64(); }
       tc_fence_after();
       for (int n0 = 0; n0 < p.NT; n0 += 16) {
         uint32_t v[16];
@@ -482,6 +509,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       }
       tc_fence_before();
       mbar_arrive(T_EMPTY(acc));
+      if (de) { DBG_ADD(17, clock64() - e0); DBG_ADD(18, 1); }
     }
   }
 
@@ -580,6 +608,7 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   p.smem_stat_off = off; off += stat_bytes;
   const int smem_bytes = off + 1024;       // slack for the 1024-B alignment of the dynamic segment
   p.err_flag = nullptr;
+  { const char* dv = getenv("B200SEG_TC_DEBUG"); p.debug = (dv && dv[0] == '1') ? 1 : 0; }
   int grid = p.n_tiles < B200SEG_NUM_SMS ? p.n_tiles : B200SEG_NUM_SMS;
   static thread_local bool attr_set = false;
   if (!attr_set) {
@@ -591,3 +620,15 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   return B200SEG_OK;
 }
 
+
+// debug: read-and-clear the cycle counters written by block 0 when B200SEG_TC_DEBUG=1
+extern "C" int b200seg_debug_tc_timers(long long* out32) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return b200seg_record_cuda(e, "sync");
+  e = cudaMemcpyFromSymbol(out32, g_tc_dbg, sizeof(long long) * 32);
+  if (e != cudaSuccess) return b200seg_record_cuda(e, "memcpyFromSymbol");
+  long long z[32] = {0};
+  e = cudaMemcpyToSymbol(g_tc_dbg, z, sizeof(z));
+  if (e != cudaSuccess) return b200seg_record_cuda(e, "memcpyToSymbol");
+  return B200SEG_OK;
+}
