@@ -14,8 +14,8 @@
 //     B descriptor, exactly like the forward kernel.
 //   * split-K over voxel tiles fills the machine: grid = jobs x S; partial D tiles go to a workspace with
 //     plain coalesced stores and a small second kernel reduces them into dW (+=) — no atomics.
-// Warp roles (448 threads, 1 CTA/SM): warps 0-3 epilogue, warp 4 MMA issue + TMEM alloc, warp 5 idle,
-// warps 6-13 loaders (cp.async, all 256 threads per stage, stage k published while stage k+1 is in flight).
+// Warp roles (416 threads, 1 CTA/SM): warps 0-3 epilogue, warps 4-11 loaders, warp 12 MMA issue + TMEM alloc
+// (was: loaders (cp.async, all 256 threads per stage, stage k published while stage k+1 is in flight).
 #include "common.cuh"
 #include "conv_args.h"
 #include <string.h>
@@ -26,11 +26,11 @@ namespace {
 
 constexpr int TH = 16, TW = 8;
 constexpr int kEpiWarps = 4;
-constexpr int kMmaWarp = 4;
-constexpr int kLoadWarp0 = 6;
+constexpr int kLoadWarp0 = 4;
+constexpr int kMmaWarp = 12;                // highest warp id = highest issue priority in its SM sub-partition
 constexpr int kLoadGroups = 1;             // all loader warps cooperate on every stage (deferred publication needs
 constexpr int kLoadGroupThreads = 256;     // consecutive stages from the same threads; works for a 2-slot ring)
-constexpr int kThreads = kLoadWarp0 * 32 + kLoadGroups * kLoadGroupThreads;   // 448
+constexpr int kThreads = 13 * 32;   // 416
 constexpr uint32_t kSpinLimit = 1u << 24;
 constexpr int MT = 128;                    // output-channel tile (GEMM M)
 
@@ -171,7 +171,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp >= kLoadWarp0) {
+  if (warp >= kLoadWarp0 && warp < kMmaWarp) {
     // =========================== LOADERS ===========================
     const int lt = threadIdx.x - kLoadWarp0 * 32;
     // dy tile: cpv planes, thread owns plane (lt % cpv) and walks voxels v0, v0+vstep, ...
