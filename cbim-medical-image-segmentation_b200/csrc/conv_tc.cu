@@ -358,7 +358,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER (one thread) ===========================
-    {   // the whole warp runs the (warp-uniform) control flow; lane 0 alone issues tcgen05 instructions
+    if (lane == 0) {   // ONE active lane: with several active lanes the compiler wraps every tcgen05.mma in an
+      // elect/broadcast loop that iterates once per lane (measured ~300 cycles per MMA instead of ~50)
       // The issue loop is the critical path of the whole CTA (one thread feeds the tensor core), so it is kept to
       // a few instructions per MMA: descriptors are 64-bit templates plus a 16-byte-unit start address that is
       // advanced by constant adds (tap to the right: +1, tap row down: +HALO_W, K step: +2*LBO).
@@ -412,27 +413,24 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                 uint64_t da = da_tap;
 #pragma unroll 4
                 for (int j = 0; j < ksteps; ++j) {
-                  if (lane == 0) umma_f16(tmem_d, da, db, idesc, accumulate);
+                  umma_f16(tmem_d, da, db, idesc, accumulate);
                   accumulate = 1;
                   da += a_kstep; db += b_kstep;
                 }
                 if (!p.w_resident) {
-                  if (lane == 0) umma_commit(B_EMPTY(rb.idx));   // weights slot free once these MMAs retire
-                  __syncwarp();
+                  umma_commit(B_EMPTY(rb.idx));   // weights slot free once these MMAs retire
                   rb.advance();
                 }
                 da_tap += 1;                      // next tap to the right: 16 B
               }
               da_row += (uint64_t)p.HALO_W;       // next tap row: HALO_W voxels
             }
-            if (lane == 0) umma_commit(A_EMPTY(ra.idx));         // halo tile free
-            __syncwarp();
+            umma_commit(A_EMPTY(ra.idx));         // halo tile free
             if (dbg && lane == 0) DBG_ADD(11, clock64() - m0);      // issue time of one stage (incl. weight waits)
             ra.advance();
           }
         }
-        if (lane == 0) umma_commit(T_FULL(acc));                 // accumulator complete -> epilogue
-        __syncwarp();
+        umma_commit(T_FULL(acc));                 // accumulator complete -> epilogue
       }
     }
   } else {

@@ -240,7 +240,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
-    {   // warp-uniform control flow; lane 0 alone issues tcgen05 instructions
+    if (lane == 0) {   // one active lane (see conv_tc.cu: multi-lane regions make every tcgen05.mma a 32-iteration loop)
       const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NTC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       uint32_t dy_lbo = 128u, dy_sbo = (uint32_t)p.dy_plane;
       uint32_t a_lbo = (uint32_t)p.HALO_W * 16u, a_sbo = (uint32_t)p.a_plane;
@@ -267,7 +267,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
           uint64_t da = da0, db = db_tap;
 #pragma unroll
           for (int j = 0; j < (TH * TW) / 16; ++j) {
-            if (lane == 0) umma_f16(tmem_d, da, db, idesc, (accumulate | (uint32_t)(j > 0)));
+            umma_f16(tmem_d, da, db, idesc, (accumulate | (uint32_t)(j > 0)));
             da += 16;            // 2 voxel rows of the dy tile = 256 B
             db += a_kstep;
           }
@@ -276,11 +276,10 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
           if (++zw == p.kw) { zw = 0; db_tap += (uint64_t)(p.HALO_W - (p.kw - 1)); } else db_tap += 1;
         }
         accumulate = 1;
-        if (lane == 0) umma_commit(EMPTY(idx));
-        __syncwarp();
+        umma_commit(EMPTY(idx));
         if (++idx == p.NS) { idx = 0; phase ^= 1; }
       }
-      if (lane == 0) umma_commit(DONE);
+      umma_commit(DONE);
     }
   } else if (warp < kEpiWarps) {
     // =========================== EPILOGUE (once) ===========================
