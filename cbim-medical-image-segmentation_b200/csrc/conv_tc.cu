@@ -42,7 +42,6 @@ constexpr int kMmaWarp = 13;
 constexpr int kLoadGroups = 2;
 constexpr int kLoadGroupThreads = 128;
 constexpr int kThreads = 14 * 32;   // 448
-constexpr int kMaxChunksPerThread = 12;   // (18*10 voxels * 64/8 chunks) / 128 threads = 11.25
 constexpr uint32_t kSpinLimit = 1u << 24;
 
 struct TcParams {
@@ -247,21 +246,18 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 
   if (warp >= kLoadWarp0 && warp < kWgtWarp) {
     // =========================== A LOADERS ===========================
+    // Compact code on purpose: 14 warps run 4 different programs on this SM, and a loader body unrolled over its
+    // 12 chunks (~25 KB of SASS) evicted the MMA warp's tiny issue loop from the instruction cache on every
+    // iteration (measured ~300 cycles per tcgen05.mma instead of ~50).  Each thread owns ONE 8-channel plane
+    // (its InstanceNorm scale/shift live in registers for the whole stage) and walks the halo voxels in steps.
     const int grp = (warp - kLoadWarp0) >> 2;
     const int lt = threadIdx.x - (kLoadWarp0 * 32 + grp * kLoadGroupThreads);
     const int cpv = p.KC / 8;
-    const int nchunks = p.nvox_h * cpv;
-    // per-thread chunk table: chunk i = lt + k*128 -> (hh, ww, c8), fixed for the whole kernel
-    int c_hh[kMaxChunksPerThread], c_ww[kMaxChunksPerThread], c_c8[kMaxChunksPerThread];
-#pragma unroll
-    for (int k = 0; k < kMaxChunksPerThread; ++k) {
-      int i = lt + k * kLoadGroupThreads;
-      int vox = i / cpv;
-      c_c8[k] = i - vox * cpv;
-      c_hh[k] = vox / p.HALO_W;
-      c_ww[k] = vox - c_hh[k] * p.HALO_W;
-      if (i >= nchunks) c_hh[k] = -1000000;       // never valid
-    }
+    const int act_thr = (kLoadGroupThreads / cpv) * cpv;
+    const int vstep = kLoadGroupThreads / cpv;
+    const int c8 = lt % cpv, v0 = lt / cpv;
+    const int sh = vstep / p.HALO_W, sw = vstep % p.HALO_W;
+    const bool xform = (a.x_stats != nullptr) || (a.act != 0);
     const __half* xbase = reinterpret_cast<const __half*>(a.x);
     Ring ring; ring.init(p.SA);
     int stage_no = 0;
@@ -273,51 +269,57 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           if ((unsigned)din >= (unsigned)a.D) continue;
           if ((stage_no & 1) == grp) {
             const bool dl = dbg && grp == 0 && lt == 0;
-            long long q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+            long long q0 = 0, q1 = 0;
             if (dl) q0 = clock64();
             mbar_wait(A_EMPTY(ring.idx), ring.phase ^ 1, p.err_flag, 1);
             if (dl) q1 = clock64();
-            uint8_t* sdst = smem + p.smem_a_off + ring.idx * p.a_stage_bytes;
-            const __half* xs = xbase + ((int64_t)(tc.b * a.D + din) * a.H * a.W) * a.x_ld + a.x_coff + kc * p.KC;
-            const float2* nrm = s_norm + tc.b * a.Cin + kc * p.KC;
-            // issue all global loads first (ILP), then transform + store
-            uint4 raw[kMaxChunksPerThread];
-            bool ok[kMaxChunksPerThread];
+            if (lt < act_thr) {
+              uint8_t* sdst = smem + p.smem_a_off + ring.idx * p.a_stage_bytes + c8 * p.plane_stride;
+              const __half* xs = xbase + ((int64_t)(tc.b * a.D + din) * a.H * a.W) * a.x_ld + a.x_coff + kc * p.KC + c8 * 8;
+              float sc[8], sf[8];          // x*sc + sf == (x - mean) * rstd
 #pragma unroll
-            for (int k = 0; k < kMaxChunksPerThread; ++k) {
-              const int h = tc.h0 - ph + c_hh[k], w = tc.w0 - pw + c_ww[k];
-              ok[k] = (c_hh[k] >= 0) && ((unsigned)h < (unsigned)a.H) && ((unsigned)w < (unsigned)a.W);
-              raw[k] = make_uint4(0, 0, 0, 0);
-              if (ok[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(xs + ((int64_t)h * a.W + w) * a.x_ld + c_c8[k] * 8));
-            }
-            if (dl) q2 = clock64();
+              for (int j = 0; j < 8; ++j) {
+                const float2 mr = s_norm[tc.b * a.Cin + kc * p.KC + c8 * 8 + j];
+                sc[j] = mr.y; sf[j] = -mr.x * mr.y;
+              }
+              int hh = v0 / p.HALO_W, ww = v0 % p.HALO_W;
+#pragma unroll 1
+              for (int v = v0; v < p.nvox_h; v += 4 * vstep) {
+                uint4 raw[4]; int vv[4]; bool ok[4];
 #pragma unroll
-            for (int k = 0; k < kMaxChunksPerThread; ++k) {
-              if (c_hh[k] < 0) continue;
-              uint4 o = make_uint4(0, 0, 0, 0);
-              if (ok[k]) {
-                if (a.x_stats || a.act) {
-                  const __half2* hv = reinterpret_cast<const __half2*>(&raw[k]);
-                  __half2* ov = reinterpret_cast<__half2*>(&o);
+                for (int u = 0; u < 4; ++u) {
+                  vv[u] = hh * p.HALO_W + ww;
+                  const int h = tc.h0 - ph + hh, w = tc.w0 - pw + ww;
+                  ok[u] = (vv[u] < p.nvox_h) && ((unsigned)h < (unsigned)a.H) && ((unsigned)w < (unsigned)a.W);
+                  raw[u] = make_uint4(0, 0, 0, 0);
+                  if (ok[u]) raw[u] = __ldg(reinterpret_cast<const uint4*>(xs + ((int64_t)h * a.W + w) * a.x_ld));
+                  hh += sh; ww += sw;
+                  if (ww >= p.HALO_W) { ww -= p.HALO_W; ++hh; }
+                }
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    float2 f = __half22float2(hv[j]);
-                    const float2 n0 = nrm[c_c8[k] * 8 + 2 * j], n1 = nrm[c_c8[k] * 8 + 2 * j + 1];
-                    f.x = (f.x - n0.x) * n0.y; f.y = (f.y - n1.x) * n1.y;
-                    if (a.act == B200SEG_ACT_RELU) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
-                    ov[j] = __floats2half2_rn(f.x, f.y);
+                for (int u = 0; u < 4; ++u) {
+                  if (vv[u] >= p.nvox_h) continue;
+                  uint4 o = raw[u];
+                  if (ok[u] && xform) {
+                    const __half2* hv = reinterpret_cast<const __half2*>(&raw[u]);
+                    __half2* ov = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      float2 f = __half22float2(hv[j]);
+                      f.x = fmaf(f.x, sc[2 * j], sf[2 * j]); f.y = fmaf(f.y, sc[2 * j + 1], sf[2 * j + 1]);
+                      if (a.act == B200SEG_ACT_RELU) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+                      ov[j] = __floats2half2_rn(f.x, f.y);
+                    }
                   }
-                } else {
-                  o = raw[k];
+                  *reinterpret_cast<uint4*>(sdst + vv[u] * 16) = o;
                 }
               }
-              const int vox = c_hh[k] * p.HALO_W + c_ww[k];
-              *reinterpret_cast<uint4*>(sdst + c_c8[k] * p.plane_stride + vox * 16) = o;
             }
+            long long q3 = 0;
             if (dl) q3 = clock64();
             fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(A_FULL(ring.idx));
-            if (dl) { DBG_ADD(0, q1 - q0); DBG_ADD(1, q2 - q1); DBG_ADD(2, q3 - q2); DBG_ADD(3, clock64() - q3); DBG_ADD(4, 1); }
+            if (dl) { DBG_ADD(0, q1 - q0); DBG_ADD(2, q3 - q1); DBG_ADD(3, clock64() - q3); DBG_ADD(4, 1); }
           }
           ring.advance();
           ++stage_no;
@@ -589,7 +591,6 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   p.a_stage_bytes = (p.KC / 8) * p.plane_stride;
   p.a_stage_bytes = (p.a_stage_bytes + 127) / 128 * 128;
   p.b_stage_bytes = p.KC * p.NT * 2;
-  if (p.nvox_h * (p.KC / 8) > kMaxChunksPerThread * kLoadGroupThreads) return B200SEG_EUNSUPPORTED;
   p.tiles_h = (a.H + TH - 1) / TH; p.tiles_w = (a.W + TW - 1) / TW;
   int64_t nt = (int64_t)a.B * a.D * p.tiles_h * p.tiles_w * p.NTILES;
   if (nt > 0x7fffffff) return B200SEG_EUNSUPPORTED;
