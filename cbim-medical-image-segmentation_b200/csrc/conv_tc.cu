@@ -144,6 +144,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ long long g_tc_dbg[32];
 #define DBG_ADD(slot, val) do { if (dbg) atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_dbg[slot]), (unsigned long long)(val)); } while (0)
 
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+
 struct Ring {
   int idx; uint32_t phase; int n;
   __device__ __forceinline__ void init(int n_) { idx = 0; phase = 0; n = n_; }
@@ -273,7 +279,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             if (dl) q0 = clock64();
             mbar_wait(A_EMPTY(ring.idx), ring.phase ^ 1, p.err_flag, 1);
             if (dl) q1 = clock64();
-            if (lt < act_thr) {
+            if (lt < act_thr && !(p.debug & 2)) {
               uint8_t* sdst = smem + p.smem_a_off + ring.idx * p.a_stage_bytes + c8 * p.plane_stride;
               const __half* xs = xbase + ((int64_t)(tc.b * a.D + din) * a.H * a.W) * a.x_ld + a.x_coff + kc * p.KC + c8 * 8;
               float sc[8], sf[8];          // x*sc + sf == (x - mean) * rstd
@@ -359,12 +365,15 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       }
     }
   } else if (warp == kMmaWarp) {
-    // =========================== MMA ISSUER (one thread) ===========================
-    if (lane == 0) {   // ONE active lane: with several active lanes the compiler wraps every tcgen05.mma in an
-      // elect/broadcast loop that iterates once per lane (measured ~300 cycles per MMA instead of ~50)
-      // The issue loop is the critical path of the whole CTA (one thread feeds the tensor core), so it is kept to
-      // a few instructions per MMA: descriptors are 64-bit templates plus a 16-byte-unit start address that is
-      // advanced by constant adds (tap to the right: +1, tap row down: +HALO_W, K step: +2*LBO).
+    // =========================== MMA ISSUER ===========================
+    // Production pattern: the WHOLE warp runs this loop with warp-uniform values (everything is derived from
+    // kernel parameters, blockIdx and shuffled broadcasts), and one elected lane issues the tcgen05 instructions.
+    // Uniform values live in uniform registers, so a tcgen05.mma costs a couple of UIADDs instead of an
+    // elect / R2UR.BROADCAST sequence per operand (measured: 134 -> see profiles/ cycles per MMA), and the loop
+    // bounds are copied to locals so no constant-bank load sits on the issue path.
+    {
+      const uint32_t elected = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       Ring ra, rb; ra.init(p.SA); rb.init(p.SB);
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t a_tmpl = make_desc(0, (uint32_t)p.plane_stride, (uint32_t)p.HALO_W * 16u);
@@ -372,67 +381,66 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const uint32_t a_kstep = (2u * (uint32_t)p.plane_stride) >> 4, b_kstep = (2u * (uint32_t)p.NT * 16u) >> 4;
       const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
       const uint32_t smem_a16 = smem_a >> 4, smem_b16 = smem_b >> 4;
-      const int taps_all = a.kd * taps_hw;
+      const int kd = a.kd, kh = a.kh, kw = a.kw, NKC = p.NKC, D = a.D, NT = p.NT, HALO_W = p.HALO_W;
+      const int resident = p.w_resident, n_tiles = p.n_tiles, acc_stages = p.acc_stages, gstride = gridDim.x;
+      const int taps_all = kd * taps_hw;
+      const uint32_t res_step = (uint32_t)NKC * b_stage16;
       int it = 0;
-      if (p.w_resident) { mbar_wait(B_FULL(0), 0, p.err_flag, 7); tc_fence_after(); }
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+      if (resident) { mbar_wait(B_FULL(0), 0, p.err_flag, 7); tc_fence_after(); }
+      for (int t = blockIdx.x; t < n_tiles; t += gstride, ++it) {
         const TileCoord tc = tile_coord(p, t);
-        const int acc = (p.acc_stages == 2) ? (it & 1) : 0;
-        const uint32_t acc_phase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
+        const int acc = (acc_stages == 2) ? (it & 1) : 0;
+        const uint32_t acc_phase = (acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
         long long m0 = 0;
         if (dbg && lane == 0) m0 = clock64();
         mbar_wait(T_EMPTY(acc), acc_phase ^ 1, p.err_flag, 3);
         if (dbg && lane == 0) DBG_ADD(8, clock64() - m0);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.NT);
+        const uint32_t tmem_d = tmem_u + (uint32_t)(acc * NT);
         uint32_t accumulate = 0;
-        for (int kc = 0; kc < p.NKC; ++kc) {
-          for (int zd = 0; zd < a.kd; ++zd) {
+        for (int kc = 0; kc < NKC; ++kc) {
+          for (int zd = 0; zd < kd; ++zd) {
             const int din = tc.d + zd - pd;
-            if ((unsigned)din >= (unsigned)a.D) continue;
+            if ((unsigned)din >= (unsigned)D) continue;
             if (dbg && lane == 0) m0 = clock64();
             mbar_wait(A_FULL(ra.idx), ra.phase, p.err_flag, 4);
             if (dbg && lane == 0) { DBG_ADD(9, clock64() - m0); DBG_ADD(12, 1); m0 = clock64(); }
             tc_fence_after();
             uint64_t da_row = a_tmpl + (uint64_t)(smem_a16 + (uint32_t)ra.idx * a_stage16);
-            // resident image: blob (ntile, tap, kc); consecutive in-plane taps are NKC blobs apart
-            uint64_t db_res = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)((tc.ntile * taps_all + zd * taps_hw) * p.NKC + kc) * b_stage16);
-            for (int zh = 0; zh < a.kh; ++zh) {
+            uint64_t db_res = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)((tc.ntile * taps_all + zd * taps_hw) * NKC + kc) * b_stage16);
+            for (int zh = 0; zh < kh; ++zh) {
               uint64_t da_tap = da_row;
-              for (int zw = 0; zw < a.kw; ++zw) {
+              for (int zw = 0; zw < kw; ++zw) {
                 uint64_t db;
-                if (p.w_resident) {
+                if (resident) {
                   db = db_res;
-                  db_res += (uint64_t)((uint32_t)p.NKC * b_stage16);
+                  db_res += (uint64_t)res_step;
                 } else {
-                  long long b0 = 0;
-                  if (dbg && lane == 0) b0 = clock64();
                   mbar_wait(B_FULL(rb.idx), rb.phase, p.err_flag, 5);
-                  if (dbg && lane == 0) DBG_ADD(10, clock64() - b0);
                   tc_fence_after();
                   db = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)rb.idx * b_stage16);
                 }
                 uint64_t da = da_tap;
 #pragma unroll 4
                 for (int j = 0; j < ksteps; ++j) {
-                  umma_f16(tmem_d, da, db, idesc, accumulate);
+                  if (elected) umma_f16(tmem_d, da, db, idesc, accumulate);
                   accumulate = 1;
                   da += a_kstep; db += b_kstep;
                 }
-                if (!p.w_resident) {
-                  umma_commit(B_EMPTY(rb.idx));   // weights slot free once these MMAs retire
+                if (!resident) {
+                  if (elected) umma_commit(B_EMPTY(rb.idx));   // weights slot free once these MMAs retire
                   rb.advance();
                 }
                 da_tap += 1;                      // next tap to the right: 16 B
               }
-              da_row += (uint64_t)p.HALO_W;       // next tap row: HALO_W voxels
+              da_row += (uint64_t)HALO_W;         // next tap row: HALO_W voxels
             }
-            umma_commit(A_EMPTY(ra.idx));         // halo tile free
-            if (dbg && lane == 0) DBG_ADD(11, clock64() - m0);      // issue time of one stage (incl. weight waits)
+            if (elected) umma_commit(A_EMPTY(ra.idx));         // halo tile free
             ra.advance();
+            if (dbg && lane == 0) DBG_ADD(11, clock64() - m0);      // issue time of one stage (incl. weight waits)
           }
         }
-        umma_commit(T_FULL(acc));                 // accumulator complete -> epilogue
+        if (elected) umma_commit(T_FULL(acc));                 // accumulator complete -> epilogue
       }
     }
   } else {
@@ -468,7 +476,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       mbar_wait(T_FULL(acc), acc_phase, p.err_flag, 6);
       if (de) { DBG_ADD(16, clock64() - e0); e0 = clock64(); }
       tc_fence_after();
-      for (int n0 = 0; n0 < p.NT; n0 += 16) {
+      for (int n0 = 0; n0 < ((p.debug & 4) ? 0 : p.NT); n0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT + n0), v);
         const uint4 cur0 = nx0, cur1 = nx1;
@@ -631,7 +639,7 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   p.smem_stat_off = off; off += stat_bytes;
   const int smem_bytes = off + 1024;       // slack for the 1024-B alignment of the dynamic segment
   p.err_flag = nullptr;
-  { const char* dv = getenv("B200SEG_TC_DEBUG"); p.debug = (dv && dv[0] == '1') ? 1 : 0; }
+  { const char* dv = getenv("B200SEG_TC_DEBUG"); p.debug = dv ? atoi(dv) : 0; }
   int grid = p.n_tiles < B200SEG_NUM_SMS ? p.n_tiles : B200SEG_NUM_SMS;
   static thread_local bool attr_set = false;
   if (!attr_set) {

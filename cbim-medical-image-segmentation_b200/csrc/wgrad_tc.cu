@@ -119,6 +119,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+
 struct Job { int co_tile, ci_tile, zd, grp, tap0, ntaps, s; };
 __device__ __forceinline__ Job decode_job(const WgParams& p, int bid) {
   Job j;
@@ -240,7 +246,9 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
     }
   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
-    if (lane == 0) {   // one active lane (see conv_tc.cu: multi-lane regions make every tcgen05.mma a 32-iteration loop)
+    {   // whole warp, warp-uniform values, one elected lane issues (see conv_tc.cu)
+      const uint32_t elected = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NTC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       uint32_t dy_lbo = 128u, dy_sbo = (uint32_t)p.dy_plane;
       uint32_t a_lbo = (uint32_t)p.HALO_W * 16u, a_sbo = (uint32_t)p.a_plane;
@@ -262,12 +270,12 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
         const uint64_t da0 = dy_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16);
         uint64_t db_tap = a_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16 + dy16 + (uint32_t)(zh0 * p.HALO_W + zw0));
         int zw = zw0;
-        uint32_t tmem_d = tmem_base;
+        uint32_t tmem_d = tmem_u;
         for (int tl = 0; tl < job.ntaps; ++tl) {
           uint64_t da = da0, db = db_tap;
 #pragma unroll
           for (int j = 0; j < (TH * TW) / 16; ++j) {
-            umma_f16(tmem_d, da, db, idesc, (accumulate | (uint32_t)(j > 0)));
+            if (elected) umma_f16(tmem_d, da, db, idesc, (accumulate | (uint32_t)(j > 0)));
             da += 16;            // 2 voxel rows of the dy tile = 256 B
             db += a_kstep;
           }
@@ -276,10 +284,10 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
           if (++zw == p.kw) { zw = 0; db_tap += (uint64_t)(p.HALO_W - (p.kw - 1)); } else db_tap += 1;
         }
         accumulate = 1;
-        umma_commit(EMPTY(idx));
+        if (elected) umma_commit(EMPTY(idx));
         if (++idx == p.NS) { idx = 0; phase ^= 1; }
       }
-      umma_commit(DONE);
+      if (elected) umma_commit(DONE);
     }
   } else if (warp < kEpiWarps) {
     // =========================== EPILOGUE (once) ===========================

@@ -5,7 +5,7 @@ import os
 import sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["B200SEG_TC_DEBUG"] = "1"
+os.environ.setdefault("B200SEG_TC_DEBUG", "1")
 from b200seg import ops, _lib  # noqa
 
 LAYERS = [(32, 32, (1, 3, 3), (128, 128, 128)), (64, 64, (1, 3, 3), (128, 64, 64)), (128, 128, (3, 3, 3), (128, 32, 32)),
