@@ -41,6 +41,7 @@ _PROTOS = {
     "b200seg_upsample_trilinear_fwd": [P, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P],
     "b200seg_upsample_trilinear_bwd": [P, I, I, P, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "b200seg_debug_tc_timers": [P],
+    "b200seg_debug_tc_trace": [P],
     "b200seg_copy_channels": [P, I, I, I, P, I, I, I, I, L, I, P],
 }
 _RESTYPES = {"b200seg_strerror": c_char_p, "b200seg_last_cuda_error": c_char_p,

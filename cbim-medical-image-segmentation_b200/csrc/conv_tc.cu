@@ -94,6 +94,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     if (++spins > kSpinLimit) mbar_timeout(err_flag, code, parity);
   }
 }
+// The MMA warp's variant: NO function call on the slow path.  A call inside the issue loop makes the compiler keep
+// the loop-carried descriptors in vector registers, and every tcgen05.mma then needs five R2UR.BROADCASTs
+// (~250 cycles per MMA measured); with the inline trap the whole loop runs on the uniform datapath.
+__device__ __forceinline__ void mbar_wait_nocall(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) __trap();
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -142,6 +152,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 // optional cycle accounting of block 0 (B200SEG_TC_DEBUG=1): where each warp role spends its time
 __device__ long long g_tc_dbg[32];
+__device__ long long g_tc_trace[4][256];   // [role][event] raw clock64 stamps of block 0 (roles: 0 mma, 1 loader g0, 2 loader g1, 3 epilogue)
+#define TRACE(role, idx) do { const int _i = (idx); if (dbg && _i < 256) g_tc_trace[role][_i] = clock64(); } while (0)
 #define DBG_ADD(slot, val) do { if (dbg) atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_dbg[slot]), (unsigned long long)(val)); } while (0)
 
 __device__ __forceinline__ uint32_t elect_one() {
@@ -196,7 +208,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const ConvArgs& a = p.a;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // canonical warp index: the shuffle makes it provably warp-uniform, so the role branches below are uniform
+  // branches and the MMA warp's loop compiles to the uniform datapath (UIADD3 + UTCHMMA, no R2UR per operand)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int taps_hw = a.kh * a.kw;
   const int pd = a.kd / 2, ph = a.kh / 2, pw = a.kw / 2;
 
@@ -266,7 +280,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     const bool xform = (a.x_stats != nullptr) || (a.act != 0);
     const __half* xbase = reinterpret_cast<const __half*>(a.x);
     Ring ring; ring.init(p.SA);
-    int stage_no = 0;
+    int stage_no = 0, tr_l = 0;
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
       const TileCoord tc = tile_coord(p, t);
       for (int kc = 0; kc < p.NKC; ++kc) {
@@ -277,7 +291,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             const bool dl = dbg && grp == 0 && lt == 0;
             long long q0 = 0, q1 = 0;
             if (dl) q0 = clock64();
+            if (lt == 0) TRACE(1 + grp, tr_l++);                   // stage start (before A_EMPTY wait)
             mbar_wait(A_EMPTY(ring.idx), ring.phase ^ 1, p.err_flag, 1);
+            if (lt == 0) TRACE(1 + grp, tr_l++);                   // slot free
             if (dl) q1 = clock64();
             if (lt < act_thr && !(p.debug & 2)) {
               uint8_t* sdst = smem + p.smem_a_off + ring.idx * p.a_stage_bytes + c8 * p.plane_stride;
@@ -323,8 +339,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             }
             long long q3 = 0;
             if (dl) q3 = clock64();
+            if (lt == 0) TRACE(1 + grp, tr_l++);                   // stored
             fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(A_FULL(ring.idx));
+            if (lt == 0) TRACE(1 + grp, tr_l++);                   // published
             if (dl) { DBG_ADD(0, q1 - q0); DBG_ADD(2, q3 - q1); DBG_ADD(3, clock64() - q3); DBG_ADD(4, 1); }
           }
           ring.advance();
@@ -385,15 +403,15 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const int resident = p.w_resident, n_tiles = p.n_tiles, acc_stages = p.acc_stages, gstride = gridDim.x;
       const int taps_all = kd * taps_hw;
       const uint32_t res_step = (uint32_t)NKC * b_stage16;
-      int it = 0;
-      if (resident) { mbar_wait(B_FULL(0), 0, p.err_flag, 7); tc_fence_after(); }
+      int it = 0, tr_m = 0;
+      if (resident) { mbar_wait_nocall(B_FULL(0), 0); tc_fence_after(); }
       for (int t = blockIdx.x; t < n_tiles; t += gstride, ++it) {
         const TileCoord tc = tile_coord(p, t);
         const int acc = (acc_stages == 2) ? (it & 1) : 0;
         const uint32_t acc_phase = (acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
         long long m0 = 0;
         if (dbg && lane == 0) m0 = clock64();
-        mbar_wait(T_EMPTY(acc), acc_phase ^ 1, p.err_flag, 3);
+        mbar_wait_nocall(T_EMPTY(acc), acc_phase ^ 1);
         if (dbg && lane == 0) DBG_ADD(8, clock64() - m0);
         tc_fence_after();
         const uint32_t tmem_d = tmem_u + (uint32_t)(acc * NT);
@@ -403,7 +421,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             const int din = tc.d + zd - pd;
             if ((unsigned)din >= (unsigned)D) continue;
             if (dbg && lane == 0) m0 = clock64();
-            mbar_wait(A_FULL(ra.idx), ra.phase, p.err_flag, 4);
+            if (lane == 0) TRACE(0, tr_m++);                       // stage start (before A_FULL wait)
+            mbar_wait_nocall(A_FULL(ra.idx), ra.phase);
+            if (lane == 0) TRACE(0, tr_m++);                       // A ready
             if (dbg && lane == 0) { DBG_ADD(9, clock64() - m0); DBG_ADD(12, 1); m0 = clock64(); }
             tc_fence_after();
             uint64_t da_row = a_tmpl + (uint64_t)(smem_a16 + (uint32_t)ra.idx * a_stage16);
@@ -416,7 +436,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                   db = db_res;
                   db_res += (uint64_t)res_step;
                 } else {
-                  mbar_wait(B_FULL(rb.idx), rb.phase, p.err_flag, 5);
+                  mbar_wait_nocall(B_FULL(rb.idx), rb.phase);
                   tc_fence_after();
                   db = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)rb.idx * b_stage16);
                 }
@@ -435,8 +455,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               }
               da_row += (uint64_t)HALO_W;         // next tap row: HALO_W voxels
             }
+            if (lane == 0) TRACE(0, tr_m++);                       // MMAs issued
             if (elected) umma_commit(A_EMPTY(ra.idx));         // halo tile free
             ra.advance();
+            if (lane == 0) TRACE(0, tr_m++);                       // committed
             if (dbg && lane == 0) DBG_ADD(11, clock64() - m0);      // issue time of one stage (incl. weight waits)
           }
         }
@@ -473,7 +495,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       long long e0 = 0;
       const bool de = dbg && threadIdx.x == 0;
       if (de) e0 = clock64();
+      if (threadIdx.x == 0) TRACE(3, 3 * it);                      // tile start (before T_FULL wait)
       mbar_wait(T_FULL(acc), acc_phase, p.err_flag, 6);
+      if (threadIdx.x == 0) TRACE(3, 3 * it + 1);                  // accumulator ready
       if (de) { DBG_ADD(16, clock64() - e0); e0 = clock64(); }
       tc_fence_after();
       for (int n0 = 0; n0 < ((p.debug & 4) ? 0 : p.NT); n0 += 16) {
@@ -541,6 +565,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       }
       tc_fence_before();
       mbar_arrive(T_EMPTY(acc));
+      if (threadIdx.x == 0) TRACE(3, 3 * it + 2);                  // drained
       if (de) { DBG_ADD(17, clock64() - e0); DBG_ADD(18, 1); }
     }
   }
@@ -661,5 +686,13 @@ extern "C" int b200seg_debug_tc_timers(long long* out32) {
   long long z[32] = {0};
   e = cudaMemcpyToSymbol(g_tc_dbg, z, sizeof(z));
   if (e != cudaSuccess) return b200seg_record_cuda(e, "memcpyToSymbol");
+  return B200SEG_OK;
+}
+
+extern "C" int b200seg_debug_tc_trace(long long* out1024) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return b200seg_record_cuda(e, "sync");
+  e = cudaMemcpyFromSymbol(out1024, g_tc_trace, sizeof(long long) * 1024);
+  if (e != cudaSuccess) return b200seg_record_cuda(e, "memcpyFromSymbol");
   return B200SEG_OK;
 }

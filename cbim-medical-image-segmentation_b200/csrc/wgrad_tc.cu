@@ -74,6 +74,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int cod
     if (++spins > kSpinLimit) mbar_timeout(code, parity);
   }
 }
+__device__ __forceinline__ void mbar_wait_nocall(uint32_t bar, uint32_t parity) {   // see conv_tc.cu
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) __trap();
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -140,7 +147,9 @@ __device__ __forceinline__ Job decode_job(const WgParams& p, int bid) {
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // canonical warp index: the shuffle makes it provably warp-uniform, so the role branches below are uniform
+  // branches and the MMA warp's loop compiles to the uniform datapath (UIADD3 + UTCHMMA, no R2UR per operand)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const Job job = decode_job(p, blockIdx.x);
   const int pd = p.kd / 2, ph = p.kh / 2, pw = p.kw / 2;
   const int co0 = job.co_tile * MT;
@@ -265,7 +274,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
         const int d = (vt / dslab) % p.D;
         const int din = d + job.zd - pd;
         if ((unsigned)din >= (unsigned)p.D) continue;
-        mbar_wait(FULL(idx), phase, 2);
+        mbar_wait_nocall(FULL(idx), phase);
         tc_fence_after();
         const uint64_t da0 = dy_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16);
         uint64_t db_tap = a_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16 + dy16 + (uint32_t)(zh0 * p.HALO_W + zw0));
