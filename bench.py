@@ -114,6 +114,19 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cores():
+    """Host threads this process can really use: CPU affinity capped by the cgroup CPU quota (a container that
+    sees 128 logical CPUs but owns a 16-CPU quota thrashes with 128 threads)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def host_info():
     model = "unknown"
     try:
@@ -123,7 +136,7 @@ def host_info():
                 break
     except Exception:
         pass
-    return model, os.cpu_count()
+    return model, usable_cores()
 
 
 # --------------------------------------------------------------------------- CPU (reference) arm
@@ -154,10 +167,10 @@ def cpu_sample_shape(scale, budget_s, steps_total, step, classes):
     for s in scale:
         dmin *= s[0]
     dmin = max(dmin * 2, 8)
-    img, lab = make_volume(1, dmin, 64, 64, classes, seed=1)
+    img, lab = make_volume(1, dmin, 128, 128, classes, seed=1)
     step(img, lab)
     t0 = time.time(); step(img, lab); t = time.time() - t0
-    rate = dmin * 64 * 64 / t
+    rate = dmin * 128 * 128 / t
     return dmin, rate
 
 
@@ -168,7 +181,7 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
+    cores = usable_cores()
     torch.set_num_threads(cores)
     step = oracle_step_fn(scale, kernel, classes, weight)
     dmin, rate = cpu_sample_shape(scale, 0, 0, step, classes)
@@ -334,7 +347,7 @@ def run_b200(args, wl):
         del x, wp
         # ---- CPU baseline: oracle port on the host cores, bounded sample
         if world == 1 and not args.no_cpu:
-            cores = os.cpu_count()
+            cores = usable_cores()
             torch.set_num_threads(cores)
             step = oracle_step_fn(scale, kernel, classes, weight)
             dmin, rate = cpu_sample_shape(scale, 0, 0, step, classes)
