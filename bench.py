@@ -339,8 +339,11 @@ def run_b200(args, wl):
         except Exception:
             pass
         peak = peaks.get("bf16_tflops", 1590.0)
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        # (profiles/r1_ncu_full_conv_wgrad_128.txt: 68.09 MB read + 5.81 MB written per launch, incl. a residual read)
+        traffic = 73.9e6 if (ci, co, tuple(k), tuple(d)) == (128, 128, (3, 3, 3), (128, 32, 32)) else None
         out["roofline"] = {"bound": "tensor", "achieved": kfl / (kms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                           "frac": kfl / (kms / 1e3) / 1e12 / peak, "traffic": None,
+                           "frac": kfl / (kms / 1e3) / 1e12 / peak, "traffic": traffic,
                            "peak_source": "measured (MEASURED_PEAKS.json, burst)" if peaks else "fallback 1.59 PF",
                            "kernel": "conv3d_fwd[%s] %d->%d k%s @%s (IN+ReLU loader, IN-sums epilogue)" % ("tcgen05" if algo == 2 else "direct", ci, co, list(k), list(d)),
                            "ms": kms, "step_frac_of_sustained_peak": out["achieved_tflops_step"] / peaks.get("bf16_tflops_sustained", 1400.0)}
