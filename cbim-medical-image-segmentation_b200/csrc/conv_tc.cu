@@ -162,6 +162,30 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
+// Straight-line issue of one staged halo tile against RESIDENT weights: every tap and K step unrolled, descriptor low
+// words are `base + compile-time-shaped offsets`, high words constant.  ~5 uniform instructions per tcgen05.mma
+// and no loop / constant-bank traffic between them (the 32-channel layers are issue-bound otherwise).
+template <int KS, int KH, int KW>
+__device__ __forceinline__ void issue_stage_resident(uint32_t tmem_d, uint64_t da_stage, uint64_t db_stage, uint32_t idesc,
+                                                     uint32_t& accumulate, uint32_t a_kstep, uint32_t b_kstep,
+                                                     uint32_t halo_w, uint32_t b_tap_step, uint32_t elected) {
+  const uint32_t a_lo = (uint32_t)da_stage, a_hi = (uint32_t)(da_stage >> 32);
+  const uint32_t b_lo = (uint32_t)db_stage, b_hi = (uint32_t)(db_stage >> 32);
+#pragma unroll
+  for (int zh = 0; zh < KH; ++zh) {
+#pragma unroll
+    for (int zw = 0; zw < KW; ++zw) {
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)zh * halo_w + (uint32_t)zw + (uint32_t)j * a_kstep);
+        const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(zh * KW + zw) * b_tap_step + (uint32_t)j * b_kstep);
+        if (elected) umma_f16(tmem_d, da, db, idesc, accumulate);
+        accumulate = 1;
+      }
+    }
+  }
+}
+
 struct Ring {
   int idx; uint32_t phase; int n;
   __device__ __forceinline__ void init(int n_) { idx = 0; phase = 0; n = n_; }
@@ -326,10 +350,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               }
               int hh = v0 / p.HALO_W, ww = v0 % p.HALO_W;
 #pragma unroll 1
-              for (int v = v0; v < p.nvox_h; v += 4 * vstep) {
-                uint4 raw[4]; int vv[4]; bool ok[4];
+              for (int v = v0; v < p.nvox_h; v += 6 * vstep) {
+                uint4 raw[6]; int vv[6]; bool ok[6];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 6; ++u) {
                   vv[u] = hh * p.HALO_W + ww;
                   const int h = tc.h0 - ph + hh, w = tc.w0 - pw + ww;
                   ok[u] = (vv[u] < p.nvox_h) && ((unsigned)h < (unsigned)a.H) && ((unsigned)w < (unsigned)a.W);
@@ -339,7 +363,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                   if (ww >= p.HALO_W) { ww -= p.HALO_W; ++hh; }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 6; ++u) {
                   if (vv[u] >= p.nvox_h) continue;
                   uint4 o = raw[u];
                   if (ok[u] && xform) {
@@ -450,6 +474,18 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             tc_fence_after();
             uint64_t da_row = a_tmpl + (uint64_t)(smem_a16 + (uint32_t)ra.idx * a_stage16);
             uint64_t db_res = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)((tc.ntile * taps_all + zd * taps_hw) * NKC + kc) * b_stage16);
+            bool done = false;
+            if (resident && kh == 3 && kw == 3) {
+              done = true;
+              switch (ksteps) {
+                case 1: issue_stage_resident<1, 3, 3>(tmem_d, da_row, db_res, idesc, accumulate, a_kstep, b_kstep, (uint32_t)HALO_W, res_step, elected); break;
+                case 2: issue_stage_resident<2, 3, 3>(tmem_d, da_row, db_res, idesc, accumulate, a_kstep, b_kstep, (uint32_t)HALO_W, res_step, elected); break;
+                case 3: issue_stage_resident<3, 3, 3>(tmem_d, da_row, db_res, idesc, accumulate, a_kstep, b_kstep, (uint32_t)HALO_W, res_step, elected); break;
+                case 4: issue_stage_resident<4, 3, 3>(tmem_d, da_row, db_res, idesc, accumulate, a_kstep, b_kstep, (uint32_t)HALO_W, res_step, elected); break;
+                default: done = false;
+              }
+            }
+            if (!done) {
             for (int zh = 0; zh < kh; ++zh) {
               uint64_t da_tap = da_row;
               for (int zw = 0; zw < kw; ++zw) {
@@ -476,6 +512,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                 da_tap += 1;                      // next tap to the right: 16 B
               }
               da_row += (uint64_t)HALO_W;         // next tap row: HALO_W voxels
+            }
             }
             if (lane == 0) TRACE(0, tr_m++);                       // MMAs issued
             if (elected) umma_commit(A_EMPTY(ra.idx));         // halo tile free
