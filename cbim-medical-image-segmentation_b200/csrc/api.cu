@@ -60,6 +60,10 @@ extern "C" int b200seg_conv3d_fwd(const void* x, int x_ld, int x_coff, const dou
   // the packed-weight layout differs per algorithm, so the caller must name one (b200seg_conv3d_algo)
   if (algo == B200SEG_ALGO_TC) return conv3d_fwd_tc(a, dtype, st);
   if (algo != B200SEG_ALGO_DIRECT) return B200SEG_EINVAL;
+  {
+    const int rc = conv3d_fwd_small(a, dtype, st);      // HBM-bound special cases (stem, classifier head)
+    if (rc != B200SEG_EUNSUPPORTED) return rc;
+  }
   return conv3d_fwd_direct(a, dtype, st);
 }
 

@@ -26,6 +26,7 @@ int conv3d_fwd_direct(const ConvArgs& a, int dtype, cudaStream_t st);
 int conv3d_wgrad_direct(const WgradArgs& a, int dtype, cudaStream_t st);
 // HBM-bound special cases (Cin=1 stem, 1x1x1 head); EUNSUPPORTED when the shape is not one of them
 int conv3d_wgrad_small(const WgradArgs& a, int dtype, cudaStream_t st);
+int conv3d_fwd_small(const ConvArgs& a, int dtype, cudaStream_t st);
 // tcgen05 paths (conv_tc.cu / wgrad_tc.cu); return B200SEG_EUNSUPPORTED when the shape does not qualify
 int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st);
 int conv3d_wgrad_tc(const WgradArgs& a, int dtype, void* workspace, size_t ws_bytes, cudaStream_t st);

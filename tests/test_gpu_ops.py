@@ -141,3 +141,23 @@ def test_small_wgrad_special_cases(ops, dtype, tol, Cin, Cout, k, normed, bias):
     assert rel_err(dw, w.grad) < tol
     if bias:
         assert rel_err(db, b.grad) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.float16, 3e-3)])
+@pytest.mark.parametrize("Cin,Cout,k,bias", [(1, 32, (1, 3, 3), False), (1, 32, (3, 3, 3), False), (32, 4, (1, 1, 1), True),
+                                             (4, 32, (1, 1, 1), False), (16, 12, (1, 1, 1), True)])
+def test_small_fwd_special_cases(ops, dtype, tol, Cin, Cout, k, bias):
+    """The stem (Cin=1 -> 32) and few-channel 1x1x1 convs (classifier head fwd / dgrad) run HBM-bound special kernels."""
+    torch.manual_seed(6)
+    B, D, H, W = 2, 5, 13, 9
+    x = torch.randn(B, Cin, D, H, W).to(dtype)
+    w = torch.randn(Cout, Cin, *k) * 0.3
+    b = torch.randn(Cout) if bias else None
+    xc = ndhwc(x).cuda()
+    wp = ops.pack_weight(w.cuda(), dtype)
+    y, yst = ops.conv3d_fwd(xc, 0, Cin, None, ops.ACT_NONE, wp, Cout, k, bias=None if b is None else b.cuda(),
+                            want_stats=(Cin == 1), algo=ops._lib.ALGO_DIRECT)
+    ref = F.conv3d(x.float(), w.to(dtype).float(), b, padding=[i // 2 for i in k])
+    assert rel_err(ncdhw(y.float()), ref) < tol
+    if yst is not None:
+        assert rel_err(yst, stats_of(ncdhw(y.float().cpu()))) < 1e-5
