@@ -281,7 +281,7 @@ inline int64_t pick_vpb(int64_t V, int B) {
   int64_t want = (int64_t)B200SEG_NUM_SMS * 8 / (B > 0 ? B : 1);
   if (want < 1) want = 1;
   int64_t vpb = (V + want - 1) / want;
-  if (vpb < 256) vpb = 256;
+  if (vpb < 16) vpb = 16;          // small, channel-heavy levels still need >= one block per SM
   return vpb;
 }
 

@@ -50,10 +50,23 @@ wgrad_cin1_kernel(WgradArgs a, int64_t vox_per_warp) {
       }
     }
   }
+  // block-level reduction first: thousands of warps hammering the same few hundred addresses with atomics
+  // serialise in L2 (measured ~1 ms); one atomic per (block, output) instead
+  __shared__ float s_acc[kWarpsPerBlock][32][MAXT];
+  const int wid = threadIdx.x >> 5;
+  for (int half = 0; half < (two ? 2 : 1); ++half) {
+    __syncthreads();
 #pragma unroll
-  for (int q = 0; q < MAXT; ++q) {
-    if (lane < a.Cout) atomicAdd(&a.dw[(int64_t)lane * MAXT + q], acc0[q]);
-    if (two && lane + 32 < a.Cout) atomicAdd(&a.dw[(int64_t)(lane + 32) * MAXT + q], acc1[q]);
+    for (int q = 0; q < MAXT; ++q) s_acc[wid][lane][q] = half ? acc1[q] : acc0[q];
+    __syncthreads();
+    const int nco = min(32, a.Cout - 32 * half);
+    for (int o = threadIdx.x; o < nco * MAXT; o += kWarpsPerBlock * 32) {
+      const int co = o / MAXT, q = o % MAXT;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarpsPerBlock; ++w) sum += s_acc[w][co][q];
+      atomicAdd(&a.dw[(int64_t)(co + 32 * half) * MAXT + q], sum);
+    }
   }
 }
 
@@ -132,17 +145,35 @@ wgrad_head_kernel(WgradArgs a, int64_t vox_per_warp) {
       }
     }
   }
+  __shared__ float s_acc[kWarpsPerBlock][32][MAXCO];
+  __shared__ float s_bacc[kWarpsPerBlock][MAXCO];
+  const int wid = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < MAXCO; ++c) s_bacc[wid][c] = bacc[c];
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int ci = lane + 32 * k;
-    if (k < nci && ci < a.Cin) {
+    if (k >= nci) break;
+    __syncthreads();
 #pragma unroll
-      for (int c = 0; c < MAXCO; ++c) if (c < a.Cout) atomicAdd(&a.dw[(int64_t)c * a.Cin + ci], acc[k][c]);
+    for (int c = 0; c < MAXCO; ++c) s_acc[wid][lane][c] = acc[k][c];
+    __syncthreads();
+    const int nch = min(32, a.Cin - 32 * k);
+    for (int o = threadIdx.x; o < nch * a.Cout; o += kWarpsPerBlock * 32) {
+      const int c = o / nch, cl = o % nch;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarpsPerBlock; ++w) sum += s_acc[w][cl][c];
+      atomicAdd(&a.dw[(int64_t)c * a.Cin + 32 * k + cl], sum);
     }
   }
-  if (a.dbias && lane == 0) {
+  __syncthreads();
+  if (a.dbias && threadIdx.x < a.Cout) {
+    float sum = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAXCO; ++c) if (c < a.Cout) atomicAdd(&a.dbias[c], bacc[c]);
+    for (int w = 0; w < kWarpsPerBlock; ++w) sum += s_bacc[w][threadIdx.x];
+    atomicAdd(&a.dbias[threadIdx.x], sum);
   }
 }
 
@@ -152,7 +183,7 @@ wgrad_head_kernel(WgradArgs a, int64_t vox_per_warp) {
 int conv3d_wgrad_small(const WgradArgs& a, int dtype, cudaStream_t st) {
   const int taps = a.kd * a.kh * a.kw;
   const int64_t total = (int64_t)a.B * a.D * a.H * a.W;
-  const int nwarps_target = B200SEG_NUM_SMS * kWarpsPerBlock * 8;   // 64 resident warps/SM hide the per-voxel load latency
+  const int nwarps_target = B200SEG_NUM_SMS * kWarpsPerBlock * 4;
   int64_t vpw = (total + nwarps_target - 1) / nwarps_target; if (vpw < 64) vpw = 64;
   const int64_t nwarps = (total + vpw - 1) / vpw;
   const int grid = (int)((nwarps + kWarpsPerBlock - 1) / kWarpsPerBlock);
@@ -261,7 +292,7 @@ stem_fwd_kernel(ConvArgs a) {
 
 // ---- 1x1x1 conv with few channels on one side (the classifier head forward 32->4 and its data-gradient 4->32):
 // one thread per voxel, weights + bias in shared memory, vector loads/stores.  Cin, Cout multiples of 4, <= 64.
-template <typename T>
+template <typename T, int CIN>
 __global__ void __launch_bounds__(256)
 pointwise_small_kernel(ConvArgs a) {
   extern __shared__ float s_wb[];                 // [Cout][Cin] then [Cout] bias
@@ -274,10 +305,10 @@ pointwise_small_kernel(ConvArgs a) {
   if (v >= total) return;
   const T* xp = (const T*)a.x + v * a.x_ld + a.x_coff;
   T* yp = (T*)a.y + v * a.y_ld + a.y_coff;
-  float xin[64];
+  float xin[CIN];
 #pragma unroll
-  for (int c = 0; c < 64; c += 4) {
-    if (c < a.Cin) {
+  for (int c = 0; c < CIN; c += 4) {
+    {
       if constexpr (sizeof(T) == 2) {
         const uint2 u = *reinterpret_cast<const uint2*>(xp + c);
         const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
@@ -293,9 +324,12 @@ pointwise_small_kernel(ConvArgs a) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float s = s_wb[n + co + q];
-      const float* wr = s_wb + (co + q) * a.Cin;
+      const float4* wr = reinterpret_cast<const float4*>(s_wb + (co + q) * CIN);
 #pragma unroll
-      for (int c = 0; c < 64; ++c) if (c < a.Cin) s = fmaf(xin[c], wr[c], s);
+      for (int c = 0; c < CIN / 4; ++c) {
+        const float4 w4 = wr[c];
+        s = fmaf(xin[4 * c], w4.x, s); s = fmaf(xin[4 * c + 1], w4.y, s); s = fmaf(xin[4 * c + 2], w4.z, s); s = fmaf(xin[4 * c + 3], w4.w, s);
+      }
       o[q] = s;
     }
     if constexpr (sizeof(T) == 2) {
@@ -323,12 +357,16 @@ int conv3d_fwd_small(const ConvArgs& a, int dtype, cudaStream_t st) {
     return B200SEG_OK;
   }
   const bool k111 = (a.kd == 1 && a.kh == 1 && a.kw == 1);
-  if (plain && !a.y_stats && k111 && a.Cin % 4 == 0 && a.Cout % 4 == 0 && a.Cin <= 64 && a.Cout <= 64 &&
-      a.x_ld % 4 == 0 && a.x_coff % 4 == 0 && a.y_ld % 4 == 0 && a.y_coff % 4 == 0) {
+  if (plain && !a.y_stats && k111 && (a.Cin == 4 || a.Cin == 8 || a.Cin == 16 || a.Cin == 32 || a.Cin == 64) &&
+      a.Cout % 4 == 0 && a.Cout <= 64 && a.x_ld % 4 == 0 && a.x_coff % 4 == 0 && a.y_ld % 4 == 0 && a.y_coff % 4 == 0) {
     const int64_t total = (int64_t)a.B * V;
     const size_t sm = sizeof(float) * ((size_t)a.Cout * a.Cin + a.Cout);
-    if (dtype == B200SEG_F16) pointwise_small_kernel<__half><<<ceil_div(total, 256), 256, sm, st>>>(a);
-    else pointwise_small_kernel<float><<<ceil_div(total, 256), 256, sm, st>>>(a);
+    const int grid = ceil_div(total, 256);
+#define PW(TT, CI) pointwise_small_kernel<TT, CI><<<grid, 256, sm, st>>>(a)
+#define PWT(TT) switch (a.Cin) { case 4: PW(TT, 4); break; case 8: PW(TT, 8); break; case 16: PW(TT, 16); break; case 32: PW(TT, 32); break; default: PW(TT, 64); }
+    if (dtype == B200SEG_F16) { PWT(__half) } else { PWT(float) }
+#undef PWT
+#undef PW
     B200_CHECK_LAUNCH("pointwise_small_kernel");
     return B200SEG_OK;
   }
