@@ -1,0 +1,358 @@
+// biattn.cu — MedFormer's bidirectional multi-head attention core (B-MHA), fused, forward and backward.
+// Reference: BidirectionAttention.forward, model/dim3/medformer_utils.py:63-97 — the part between the q/v
+// projections and the output projections:
+//     S  = scale * einsum('bhid,bhjd->bhij', feat_q, map_q)            (:77-78)    i in N voxels, j in M map tokens
+//     A1 = softmax(S, dim=-1) ; A2 = softmax(S, dim=-2)                (:80,82)
+//     feat_out = A1 @ map_v ; map_out = A2^T @ feat_v                  (:84,89)
+// The reference materialises S, A1, A2 as [B,h,N,M] fp32 tensors plus six relayout copies; here every voxel is
+// visited ONCE per direction: the M<=32 map tokens live in shared memory, the row softmax is thread-local, the
+// column softmax (over up to 55k voxels) is an online max/sum with per-block partials merged by a tiny kernel,
+// and in the backward the column term  c_j = sum_i A2_ij dA2_ij  collapses to  <dmap_out_j, map_out_j>, so the
+// backward is a single pass over N as well.  HBM-bound: fwd reads q_f, v_f and writes out_f (3*B*N*inner*s bytes).
+// Channel convention (rearrange1, :43-51): channel c of the `inner` block = d * heads + h.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kT = 128;           // voxels per block (one per thread)
+constexpr int MAXM = 32;          // map tokens (27 in the BASELINE config)
+constexpr int DH = 32;            // head dimension (all BASELINE MedFormer levels use 32)
+
+struct BiArgs {
+  const void* fq; int fq_ld, fq_coff;
+  const void* fv; int fv_ld, fv_coff;
+  const void* mq; const void* mv; int m_ld;        // [B][M][m_ld], q at +0.., channel = d*heads + h
+  int mq_coff, mv_coff;
+  void* fo; int fo_ld, fo_coff;
+  void* mo; int mo_ld, mo_coff;
+  float* colstat;                                  // [B][heads][M][2] = {max, sum} of the column softmax
+  float* partial;                                  // fwd: [B][heads][nblk][M][2+DH]; bwd: [B][heads][nblk][M][2*DH]
+  // backward only
+  const void* dfo; int dfo_ld, dfo_coff;
+  const void* dmo; int dmo_ld, dmo_coff;
+  void* dfq; int dfq_ld, dfq_coff;
+  void* dfv; int dfv_ld, dfv_coff;
+  void* dmq; void* dmv; int dm_ld, dmq_coff, dmv_coff;
+  int B, M, heads; int64_t N; float scale;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kT)
+biattn_fwd_kernel(BiArgs a) {
+  extern __shared__ float sm[];
+  float* s_qm = sm;                       // [M][DH] (pre-scaled)
+  float* s_vm = s_qm + MAXM * DH;         // [M][DH]
+  float* s_e = s_vm + MAXM * DH;          // [kT][MAXM+1]
+  float* s_vf = s_e + kT * (MAXM + 1);    // [kT][DH+1]
+  float* s_cmax = s_vf + kT * (DH + 1);   // [4 warps][MAXM] then [MAXM]
+  const int h = blockIdx.y, b = blockIdx.z, M = a.M, heads = a.heads;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int o = tid; o < M * DH; o += kT) {
+    const int j = o / DH, d = o % DH;
+    const int64_t off = ((int64_t)b * M + j) * a.m_ld + d * heads + h;
+    s_qm[o] = Elem<T>::ld((const T*)a.mq + off + a.mq_coff) * a.scale;
+    s_vm[o] = Elem<T>::ld((const T*)a.mv + off + a.mv_coff);
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * kT + tid;
+  const bool valid = i < a.N;
+  float S[MAXM];
+#pragma unroll
+  for (int j = 0; j < MAXM; ++j) S[j] = 0.f;
+  float v[DH];
+  if (valid) {
+    const T* qp = (const T*)a.fq + ((int64_t)b * a.N + i) * a.fq_ld + a.fq_coff + h;
+    const T* vp = (const T*)a.fv + ((int64_t)b * a.N + i) * a.fv_ld + a.fv_coff + h;
+#pragma unroll 4
+    for (int d = 0; d < DH; ++d) {
+      const float qd = Elem<T>::ld(qp + d * heads);
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j) if (j < M) S[j] = fmaf(qd, s_qm[j * DH + d], S[j]);
+    }
+#pragma unroll
+    for (int d = 0; d < DH; ++d) v[d] = Elem<T>::ld(vp + d * heads);
+    // ---- row softmax over the map tokens + feat_out
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j) if (j < M) m = fmaxf(m, S[j]);
+    float p[MAXM], sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j) { p[j] = (j < M) ? __expf(S[j] - m) : 0.f; sum += p[j]; }
+    const float inv = 1.f / sum;
+    T* op = (T*)a.fo + ((int64_t)b * a.N + i) * a.fo_ld + a.fo_coff + h;
+#pragma unroll 4
+    for (int d = 0; d < DH; ++d) {
+      float o = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j) if (j < M) o = fmaf(p[j], s_vm[j * DH + d], o);
+      Elem<T>::st(op + d * heads, o * inv);
+    }
+  }
+  // ---- column softmax partials of this block: max_j, sum_j exp(S - max_j), sum_i exp(S_ij - max_j) v_f[i][:]
+#pragma unroll
+  for (int j = 0; j < MAXM; ++j) {
+    float mj = (valid && j < M) ? S[j] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mj = fmaxf(mj, __shfl_xor_sync(0xffffffffu, mj, o));
+    if (lane == 0) s_cmax[wid * MAXM + j] = mj;
+  }
+  __syncthreads();
+  if (tid < MAXM) {
+    float mj = s_cmax[tid];
+    for (int w = 1; w < kT / 32; ++w) mj = fmaxf(mj, s_cmax[w * MAXM + tid]);
+    s_cmax[4 * MAXM + tid] = mj;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < MAXM; ++j) s_e[tid * (MAXM + 1) + j] = (valid && j < M) ? __expf(S[j] - s_cmax[4 * MAXM + j]) : 0.f;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) s_vf[tid * (DH + 1) + d] = valid ? v[d] : 0.f;
+  __syncthreads();
+  const int nblk = gridDim.x;
+  float* pb = a.partial + ((((int64_t)b * heads + h) * nblk + blockIdx.x) * M) * (2 + DH);
+  for (int o = tid; o < M * (DH + 1); o += kT) {
+    const int j = o / (DH + 1), d = o % (DH + 1);     // d == DH -> the column sum
+    float acc = 0.f;
+    if (d < DH) { for (int r = 0; r < kT; ++r) acc = fmaf(s_e[r * (MAXM + 1) + j], s_vf[r * (DH + 1) + d], acc); pb[j * (2 + DH) + 2 + d] = acc; }
+    else { for (int r = 0; r < kT; ++r) acc += s_e[r * (MAXM + 1) + j]; pb[j * (2 + DH) + 1] = acc; pb[j * (2 + DH)] = s_cmax[4 * MAXM + j]; }
+  }
+}
+
+// merge the per-block column partials: map_out[j][:] and the {max, sum} the backward needs
+template <typename T>
+__global__ void biattn_fwd_merge_kernel(BiArgs a, int nblk) {
+  const int h = blockIdx.x, b = blockIdx.y, M = a.M, heads = a.heads;
+  const float* pb = a.partial + (((int64_t)b * heads + h) * nblk) * M * (2 + DH);
+  for (int o = threadIdx.x; o < M * DH; o += blockDim.x) {
+    const int j = o / DH, d = o % DH;
+    float gmax = -INFINITY;
+    for (int k = 0; k < nblk; ++k) gmax = fmaxf(gmax, pb[((int64_t)k * M + j) * (2 + DH)]);
+    float sum = 0.f, acc = 0.f;
+    for (int k = 0; k < nblk; ++k) {
+      const float* q = pb + ((int64_t)k * M + j) * (2 + DH);
+      const float sc = __expf(q[0] - gmax);
+      sum = fmaf(q[1], sc, sum);
+      acc = fmaf(q[2 + d], sc, acc);
+    }
+    Elem<T>::st((T*)a.mo + ((int64_t)b * M + j) * a.mo_ld + a.mo_coff + d * heads + h, acc / sum);
+    if (d == 0) { float* cs = a.colstat + (((int64_t)b * heads + h) * M + j) * 2; cs[0] = gmax; cs[1] = sum; }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kT)
+biattn_bwd_kernel(BiArgs a) {
+  extern __shared__ float sm[];
+  float* s_qm = sm;                        // [M][DH]  (unscaled)
+  float* s_vm = s_qm + MAXM * DH;
+  float* s_dmo = s_vm + MAXM * DH;         // [M][DH]
+  float* s_col = s_dmo + MAXM * DH;        // [M][3] = {gmax, 1/gsum, c_j}
+  float* s_p1 = s_col + MAXM * 4;          // [kT][MAXM+1]
+  float* s_ds = s_p1 + kT * (MAXM + 1);    // [kT][MAXM+1]
+  float* s_do = s_ds + kT * (MAXM + 1);    // [kT][DH+1]
+  float* s_q = s_do + kT * (DH + 1);       // [kT][DH+1]
+  const int h = blockIdx.y, b = blockIdx.z, M = a.M, heads = a.heads;
+  const int tid = threadIdx.x;
+  for (int o = tid; o < M * DH; o += kT) {
+    const int j = o / DH, d = o % DH;
+    const int64_t off = ((int64_t)b * M + j) * a.m_ld + d * heads + h;
+    s_qm[o] = Elem<T>::ld((const T*)a.mq + off + a.mq_coff);
+    s_vm[o] = Elem<T>::ld((const T*)a.mv + off + a.mv_coff);
+    s_dmo[o] = Elem<T>::ld((const T*)a.dmo + ((int64_t)b * M + j) * a.dmo_ld + a.dmo_coff + d * heads + h);
+  }
+  __syncthreads();
+  if (tid < M) {
+    const float* cs = a.colstat + (((int64_t)b * heads + h) * M + tid) * 2;
+    float c = 0.f;
+    for (int d = 0; d < DH; ++d)
+      c = fmaf(s_dmo[tid * DH + d], Elem<T>::ld((const T*)a.mo + ((int64_t)b * M + tid) * a.mo_ld + a.mo_coff + d * heads + h), c);
+    s_col[tid * 4] = cs[0]; s_col[tid * 4 + 1] = 1.f / cs[1]; s_col[tid * 4 + 2] = c;
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * kT + tid;
+  const bool valid = i < a.N;
+  float S[MAXM], v[DH];
+  float* my_q = s_q + tid * (DH + 1);      // own rows double as register relief; re-read below without a barrier
+  float* my_do = s_do + tid * (DH + 1);
+#pragma unroll
+  for (int j = 0; j < MAXM; ++j) S[j] = 0.f;
+  if (valid) {
+    const int64_t row = (int64_t)b * a.N + i;
+    const T* qp = (const T*)a.fq + row * a.fq_ld + a.fq_coff + h;
+    const T* vp = (const T*)a.fv + row * a.fv_ld + a.fv_coff + h;
+    const T* gp = (const T*)a.dfo + row * a.dfo_ld + a.dfo_coff + h;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+      const float qd = Elem<T>::ld(qp + d * heads);
+      v[d] = Elem<T>::ld(vp + d * heads);
+      my_q[d] = qd; my_do[d] = Elem<T>::ld(gp + d * heads);
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j) if (j < M) S[j] = fmaf(qd, s_qm[j * DH + d], S[j]);
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < DH; ++d) { v[d] = 0.f; my_q[d] = 0.f; my_do[d] = 0.f; }
+  }
+  float p1[MAXM], dS[MAXM];
+  {
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j) { S[j] *= a.scale; if (j < M) m = fmaxf(m, S[j]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j) { p1[j] = (j < M && valid) ? __expf(S[j] - m) : 0.f; sum += p1[j]; }
+    const float inv = valid ? 1.f / sum : 0.f;
+    float t1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j) {
+      p1[j] *= inv;
+      float dA1 = 0.f;
+      if (j < M) {
+#pragma unroll
+        for (int d = 0; d < DH; ++d) dA1 = fmaf(my_do[d], s_vm[j * DH + d], dA1);
+      }
+      dS[j] = dA1;
+      t1 = fmaf(p1[j], dA1, t1);
+    }
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j) dS[j] = p1[j] * (dS[j] - t1);
+  }
+  // column direction: p2_ij = exp(S_ij - gmax_j) / gsum_j ; dS += p2 (dA2 - c_j) ; dVf = sum_j p2 dmo_j
+  float dv[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) dv[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXM; ++j) {
+    if (j < M) {
+      const float p2 = valid ? __expf(S[j] - s_col[j * 4]) * s_col[j * 4 + 1] : 0.f;
+      float dA2 = 0.f;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) { dA2 = fmaf(s_dmo[j * DH + d], v[d], dA2); dv[d] = fmaf(p2, s_dmo[j * DH + d], dv[d]); }
+      dS[j] += p2 * (dA2 - s_col[j * 4 + 2]);
+    }
+  }
+  if (valid) {
+    const int64_t row = (int64_t)b * a.N + i;
+    T* dqp = (T*)a.dfq + row * a.dfq_ld + a.dfq_coff + h;
+    T* dvp = (T*)a.dfv + row * a.dfv_ld + a.dfv_coff + h;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+      float dq = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j) if (j < M) dq = fmaf(dS[j], s_qm[j * DH + d], dq);
+      Elem<T>::st(dqp + d * heads, dq * a.scale);
+      Elem<T>::st(dvp + d * heads, dv[d]);
+    }
+  }
+  // block partials of the map-side gradients: dVm[j][d] = sum_i p1_ij dO_i[d] ; dQm[j][d] = scale sum_i dS_ij q_i[d]
+#pragma unroll
+  for (int j = 0; j < MAXM; ++j) { s_p1[tid * (MAXM + 1) + j] = p1[j]; s_ds[tid * (MAXM + 1) + j] = (j < M) ? dS[j] : 0.f; }
+  __syncthreads();
+  const int nblk = gridDim.x;
+  float* pb = a.partial + ((((int64_t)b * heads + h) * nblk + blockIdx.x) * M) * (2 * DH);
+  for (int o = tid; o < M * DH; o += kT) {
+    const int j = o / DH, d = o % DH;
+    float av = 0.f, aq = 0.f;
+    for (int r = 0; r < kT; ++r) {
+      av = fmaf(s_p1[r * (MAXM + 1) + j], s_do[r * (DH + 1) + d], av);
+      aq = fmaf(s_ds[r * (MAXM + 1) + j], s_q[r * (DH + 1) + d], aq);
+    }
+    pb[j * 2 * DH + d] = aq * a.scale;
+    pb[j * 2 * DH + DH + d] = av;
+  }
+}
+
+template <typename T>
+__global__ void biattn_bwd_merge_kernel(BiArgs a, int nblk) {
+  const int h = blockIdx.x, b = blockIdx.y, M = a.M, heads = a.heads;
+  const float* pb = a.partial + (((int64_t)b * heads + h) * nblk) * M * (2 * DH);
+  for (int o = threadIdx.x; o < M * DH; o += blockDim.x) {
+    const int j = o / DH, d = o % DH;
+    float sq = 0.f, sv = 0.f;
+    for (int k = 0; k < nblk; ++k) { const float* q = pb + ((int64_t)k * M + j) * (2 * DH); sq += q[d]; sv += q[DH + d]; }
+    const int64_t off = ((int64_t)b * M + j) * a.dm_ld + d * heads + h;
+    Elem<T>::st((T*)a.dmq + off + a.dmq_coff, sq);
+    Elem<T>::st((T*)a.dmv + off + a.dmv_coff, sv);
+  }
+}
+
+}  // namespace
+
+extern "C" size_t b200seg_biattn_workspace(int B, int64_t N, int M, int heads) {
+  const int64_t nblk = (N + kT - 1) / kT;
+  return (size_t)B * heads * nblk * M * (2 * DH) * sizeof(float);
+}
+
+static int check_args(int B, int64_t N, int M, int heads, int dim_head, int dtype) {
+  if (B <= 0 || N <= 0 || M <= 0 || heads <= 0) return B200SEG_EINVAL;
+  if (dim_head != DH || M > MAXM) return B200SEG_EUNSUPPORTED;
+  if (dtype != B200SEG_F16 && dtype != B200SEG_F32) return B200SEG_EINVAL;
+  if ((N + kT - 1) / kT > 65535 * 1024) return B200SEG_EUNSUPPORTED;
+  return B200SEG_OK;
+}
+
+extern "C" int b200seg_biattn_fwd(const void* fq, int fq_ld, int fq_coff, const void* fv, int fv_ld, int fv_coff,
+                                  const void* mq, int mq_coff, const void* mv, int mv_coff, int m_ld,
+                                  void* fo, int fo_ld, int fo_coff, void* mo, int mo_ld, int mo_coff,
+                                  float* colstat, float* workspace, int B, int64_t N, int M, int heads, int dim_head,
+                                  float scale, int dtype, void* stream) {
+  int rc = check_args(B, N, M, heads, dim_head, dtype);
+  if (rc) return rc;
+  if (!fq || !fv || !mq || !mv || !fo || !mo || !colstat || !workspace) return B200SEG_EINVAL;
+  BiArgs a; memset(&a, 0, sizeof(a));
+  a.fq = fq; a.fq_ld = fq_ld; a.fq_coff = fq_coff; a.fv = fv; a.fv_ld = fv_ld; a.fv_coff = fv_coff;
+  a.mq = mq; a.mv = mv; a.m_ld = m_ld; a.mq_coff = mq_coff; a.mv_coff = mv_coff;
+  a.fo = fo; a.fo_ld = fo_ld; a.fo_coff = fo_coff; a.mo = mo; a.mo_ld = mo_ld; a.mo_coff = mo_coff;
+  a.colstat = colstat; a.partial = workspace; a.B = B; a.N = N; a.M = M; a.heads = heads; a.scale = scale;
+  cudaStream_t st = as_stream(stream);
+  const int nblk = (int)((N + kT - 1) / kT);
+  dim3 grid(nblk, heads, B);
+  const size_t sm = sizeof(float) * (2 * MAXM * DH + kT * (MAXM + 1) + kT * (DH + 1) + 5 * MAXM);
+  if (dtype == B200SEG_F16) {
+    cudaFuncSetAttribute(biattn_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    biattn_fwd_kernel<__half><<<grid, kT, sm, st>>>(a);
+    biattn_fwd_merge_kernel<__half><<<dim3(heads, B), 256, 0, st>>>(a, nblk);
+  } else {
+    cudaFuncSetAttribute(biattn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    biattn_fwd_kernel<float><<<grid, kT, sm, st>>>(a);
+    biattn_fwd_merge_kernel<float><<<dim3(heads, B), 256, 0, st>>>(a, nblk);
+  }
+  B200_CHECK_LAUNCH("biattn_fwd");
+  return B200SEG_OK;
+}
+
+extern "C" int b200seg_biattn_bwd(const void* fq, int fq_ld, int fq_coff, const void* fv, int fv_ld, int fv_coff,
+                                  const void* mq, int mq_coff, const void* mv, int mv_coff, int m_ld,
+                                  const void* mo, int mo_ld, int mo_coff, const float* colstat,
+                                  const void* dfo, int dfo_ld, int dfo_coff, const void* dmo, int dmo_ld, int dmo_coff,
+                                  void* dfq, int dfq_ld, int dfq_coff, void* dfv, int dfv_ld, int dfv_coff,
+                                  void* dmq, int dmq_coff, void* dmv, int dmv_coff, int dm_ld,
+                                  float* workspace, int B, int64_t N, int M, int heads, int dim_head, float scale,
+                                  int dtype, void* stream) {
+  int rc = check_args(B, N, M, heads, dim_head, dtype);
+  if (rc) return rc;
+  if (!fq || !fv || !mq || !mv || !mo || !colstat || !dfo || !dmo || !dfq || !dfv || !dmq || !dmv || !workspace) return B200SEG_EINVAL;
+  BiArgs a; memset(&a, 0, sizeof(a));
+  a.fq = fq; a.fq_ld = fq_ld; a.fq_coff = fq_coff; a.fv = fv; a.fv_ld = fv_ld; a.fv_coff = fv_coff;
+  a.mq = mq; a.mv = mv; a.m_ld = m_ld; a.mq_coff = mq_coff; a.mv_coff = mv_coff;
+  a.mo = const_cast<void*>(mo); a.mo_ld = mo_ld; a.mo_coff = mo_coff; a.colstat = const_cast<float*>(colstat);
+  a.dfo = dfo; a.dfo_ld = dfo_ld; a.dfo_coff = dfo_coff; a.dmo = dmo; a.dmo_ld = dmo_ld; a.dmo_coff = dmo_coff;
+  a.dfq = dfq; a.dfq_ld = dfq_ld; a.dfq_coff = dfq_coff; a.dfv = dfv; a.dfv_ld = dfv_ld; a.dfv_coff = dfv_coff;
+  a.dmq = dmq; a.dmv = dmv; a.dm_ld = dm_ld; a.dmq_coff = dmq_coff; a.dmv_coff = dmv_coff;
+  a.partial = workspace; a.B = B; a.N = N; a.M = M; a.heads = heads; a.scale = scale;
+  cudaStream_t st = as_stream(stream);
+  const int nblk = (int)((N + kT - 1) / kT);
+  dim3 grid(nblk, heads, B);
+  const size_t sm = sizeof(float) * (3 * MAXM * DH + 4 * MAXM + 2 * kT * (MAXM + 1) + 2 * kT * (DH + 1));
+  if (dtype == B200SEG_F16) {
+    cudaFuncSetAttribute(biattn_bwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    biattn_bwd_kernel<__half><<<grid, kT, sm, st>>>(a);
+    biattn_bwd_merge_kernel<__half><<<dim3(heads, B), 256, 0, st>>>(a, nblk);
+  } else {
+    cudaFuncSetAttribute(biattn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    biattn_bwd_kernel<float><<<grid, kT, sm, st>>>(a);
+    biattn_bwd_merge_kernel<float><<<dim3(heads, B), 256, 0, st>>>(a, nblk);
+  }
+  B200_CHECK_LAUNCH("biattn_bwd");
+  return B200SEG_OK;
+}

@@ -1,0 +1,267 @@
+// dwconv.cu — depthwise 3-D convolution (groups == channels), forward / data-gradient / weight-gradient.
+// Reference: DepthwiseSeparableConv.depthwise, model/dim3/conv_layers.py:135-143 (stride 1, "same" padding,
+// bias=False), used by MedFormer's attention projections (medformer_utils.py:30-31) and MBConv
+// (conv_layers.py MBConv.conv2).  One FMA per loaded byte pair -> HBM/L2 bound; no tensor-core shape here
+// (the contraction is over the 27 taps only), so this is the coalesced 128-bit direct path of the north star.
+// Layout: channels-last [B][D][H][W][ld]; a thread owns 8 consecutive channels (one 16 B vector for fp16) and a
+// run of 4 voxels along W, sliding the 3-wide window so each input vector is loaded once per (kd,kh) row.
+// Optional fused prologue: a = act(IN(x)) from the producer's {sum,sumsq}; optional epilogue: IN sums of y.
+#include "common.cuh"
+
+namespace {
+
+constexpr int RUN = 4;       // output voxels per thread along W
+constexpr int MAXK = 3;      // kernel extent per axis (1 or 3 in every reference config)
+
+struct DwArgs {
+  const void* x; int x_ld, x_coff; const double* x_stats; float eps; int act;
+  const float* w; int flip;
+  void* y; int y_ld, y_coff; double* y_stats;
+  const void* dy; int dy_ld, dy_coff; float* dw;
+  int B, D, H, W, C, kd, kh, kw;
+};
+
+template <typename T>
+__global__ void dwconv_fwd_kernel(DwArgs a) {
+  extern __shared__ float sm[];
+  const int C = a.C, taps = a.kd * a.kh * a.kw;
+  float* s_w = sm;                         // [taps][C]
+  float* s_scale = s_w + taps * C;         // [C]
+  float* s_shift = s_scale + C;            // [C]
+  float* s_sum = s_shift + C;              // [C]
+  float* s_sq = s_sum + C;                 // [C]
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const double nvox = (double)a.D * a.H * a.W;
+  for (int o = tid; o < taps * C; o += blockDim.x) {
+    const int t = o / C, c = o % C;
+    s_w[o] = a.w[(a.flip ? taps - 1 - t : t) * C + c];
+  }
+  for (int c = tid; c < C; c += blockDim.x) {
+    float mean = 0.f, rstd = 1.f;
+    if (a.x_stats) stats_to_mean_rstd(a.x_stats + ((int64_t)b * C + c) * 2, nvox, a.eps, mean, rstd);
+    s_scale[c] = rstd; s_shift[c] = -mean * rstd; s_sum[c] = 0.f; s_sq[c] = 0.f;
+  }
+  __syncthreads();
+  const int ncg = C >> 3, WR = (a.W + RUN - 1) / RUN;
+  const int cg = tid % ncg;                // blockDim.x and the grid stride are multiples of ncg
+  const int pd = a.kd >> 1, ph = a.kh >> 1, pw = a.kw >> 1;
+  const bool norm = a.x_stats != nullptr, relu = a.act == 1;
+  float sc[8], sh[8], tsum[8], tsq[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { sc[c] = s_scale[cg * 8 + c]; sh[c] = s_shift[cg * 8 + c]; tsum[c] = 0.f; tsq[c] = 0.f; }
+  const int64_t items = (int64_t)a.D * a.H * WR * ncg;
+  const T* xb = (const T*)a.x + (int64_t)b * a.D * a.H * a.W * a.x_ld + a.x_coff + cg * 8;
+  T* yb = (T*)a.y + (int64_t)b * a.D * a.H * a.W * a.y_ld + a.y_coff + cg * 8;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + tid; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = it / ncg;
+    const int wr = (int)(r % WR); r /= WR;
+    const int h = (int)(r % a.H), d = (int)(r / a.H);
+    const int w0 = wr * RUN;
+    float acc[RUN][8];
+#pragma unroll
+    for (int o = 0; o < RUN; ++o)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[o][c] = 0.f;
+    for (int zd = 0; zd < a.kd; ++zd) {
+      const int id = d + zd - pd;
+      if (id < 0 || id >= a.D) continue;
+      for (int zh = 0; zh < a.kh; ++zh) {
+        const int ih = h + zh - ph;
+        if (ih < 0 || ih >= a.H) continue;
+        const T* row = xb + ((int64_t)id * a.H + ih) * a.W * a.x_ld;
+        const float* wrow = s_w + (zd * a.kh + zh) * a.kw * C + cg * 8;
+        float wt[MAXK][8];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) wt[k][c] = (k < a.kw) ? wrow[k * C + c] : 0.f;
+#pragma unroll
+        for (int j = 0; j < RUN + MAXK - 1; ++j) {            // input column w0 - pw + j
+          const int iw = w0 - pw + j;
+          if (j >= RUN + a.kw - 1 || iw < 0 || iw >= a.W) continue;
+          float v[8];
+          ld8<T>(row + (int64_t)iw * a.x_ld, v);
+          if (norm) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { v[c] = fmaf(v[c], sc[c], sh[c]); if (relu) v[c] = fmaxf(v[c], 0.f); v[c] = Elem<T>::round(v[c]); }
+          } else if (relu) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
+          }
+#pragma unroll
+          for (int o = 0; o < RUN; ++o) {
+            const int k = j - o;                               // tap index along W
+            if (k >= 0 && k < MAXK) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) acc[o][c] = fmaf(v[c], wt[k][c], acc[o][c]);
+            }
+          }
+        }
+      }
+    }
+    T* yrow = yb + (((int64_t)d * a.H + h) * a.W + w0) * a.y_ld;
+#pragma unroll
+    for (int o = 0; o < RUN; ++o) {
+      if (w0 + o < a.W) {
+        st8<T>(yrow + (int64_t)o * a.y_ld, acc[o]);
+        if (a.y_stats) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { const float r2 = Elem<T>::round(acc[o][c]); tsum[c] += r2; tsq[c] = fmaf(r2, r2, tsq[c]); }
+        }
+      }
+    }
+  }
+  if (a.y_stats) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { atomicAdd(&s_sum[cg * 8 + c], tsum[c]); atomicAdd(&s_sq[cg * 8 + c], tsq[c]); }
+    __syncthreads();
+    for (int c = tid; c < C; c += blockDim.x) {
+      double* st = a.y_stats + ((int64_t)b * C + c) * 2;
+      atomicAdd(st, (double)s_sum[c]); atomicAdd(st + 1, (double)s_sq[c]);
+    }
+  }
+}
+
+// dw[tap][c] += sum_{b,voxel} dy[voxel][c] * a[voxel + tap][c];  grid.y = B * kd (one depth tap per block row)
+template <typename T>
+__global__ void dwconv_wgrad_kernel(DwArgs a) {
+  extern __shared__ float sm[];
+  const int C = a.C;
+  float* s_scale = sm;                     // [C]
+  float* s_shift = s_scale + C;
+  float* s_acc = s_shift + C;              // [kh*kw][C]
+  const int b = blockIdx.y / a.kd, zd = blockIdx.y % a.kd, tid = threadIdx.x;
+  const int thw = a.kh * a.kw;
+  const double nvox = (double)a.D * a.H * a.W;
+  for (int c = tid; c < C; c += blockDim.x) {
+    float mean = 0.f, rstd = 1.f;
+    if (a.x_stats) stats_to_mean_rstd(a.x_stats + ((int64_t)b * C + c) * 2, nvox, a.eps, mean, rstd);
+    s_scale[c] = rstd; s_shift[c] = -mean * rstd;
+  }
+  for (int o = tid; o < thw * C; o += blockDim.x) s_acc[o] = 0.f;
+  __syncthreads();
+  const int ncg = C >> 3, cg = tid % ncg;
+  const int pd = a.kd >> 1, ph = a.kh >> 1, pw = a.kw >> 1;
+  const bool norm = a.x_stats != nullptr, relu = a.act == 1;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { sc[c] = s_scale[cg * 8 + c]; sh[c] = s_shift[cg * 8 + c]; }
+  float acc[MAXK * MAXK][8];
+#pragma unroll
+  for (int t = 0; t < MAXK * MAXK; ++t)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
+  const int64_t items = (int64_t)a.D * a.H * a.W * ncg;
+  const T* xb = (const T*)a.x + (int64_t)b * a.D * a.H * a.W * a.x_ld + a.x_coff + cg * 8;
+  const T* gb = (const T*)a.dy + (int64_t)b * a.D * a.H * a.W * a.dy_ld + a.dy_coff + cg * 8;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + tid; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = it / ncg;
+    const int w = (int)(r % a.W); r /= a.W;
+    const int h = (int)(r % a.H), d = (int)(r / a.H);
+    const int id = d + zd - pd;
+    if (id < 0 || id >= a.D) continue;
+    float g[8];
+    ld8<T>(gb + (((int64_t)d * a.H + h) * a.W + w) * a.dy_ld, g);
+#pragma unroll
+    for (int zh = 0; zh < MAXK; ++zh) {
+      const int ih = h + zh - ph;
+      if (zh >= a.kh || ih < 0 || ih >= a.H) continue;
+#pragma unroll
+      for (int zw = 0; zw < MAXK; ++zw) {
+        const int iw = w + zw - pw;
+        if (zw >= a.kw || iw < 0 || iw >= a.W) continue;
+        float v[8];
+        ld8<T>(xb + (((int64_t)id * a.H + ih) * a.W + iw) * a.x_ld, v);
+        if (norm) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { v[c] = fmaf(v[c], sc[c], sh[c]); if (relu) v[c] = fmaxf(v[c], 0.f); v[c] = Elem<T>::round(v[c]); }
+        } else if (relu) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[zh * MAXK + zw][c] = fmaf(g[c], v[c], acc[zh * MAXK + zw][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int zh = 0; zh < MAXK; ++zh)
+#pragma unroll
+    for (int zw = 0; zw < MAXK; ++zw)
+      if (zh < a.kh && zw < a.kw) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) atomicAdd(&s_acc[(zh * a.kw + zw) * C + cg * 8 + c], acc[zh * MAXK + zw][c]);
+      }
+  __syncthreads();
+  for (int o = tid; o < thw * C; o += blockDim.x) atomicAdd(&a.dw[(int64_t)zd * thw * C + o], s_acc[o]);
+}
+
+int check(const DwArgs& a, int dtype) {
+  if (a.B <= 0 || a.D <= 0 || a.H <= 0 || a.W <= 0 || a.C <= 0) return B200SEG_EINVAL;
+  if (dtype != B200SEG_F16 && dtype != B200SEG_F32) return B200SEG_EINVAL;
+  if ((a.kd != 1 && a.kd != 3) || (a.kh != 1 && a.kh != 3) || (a.kw != 1 && a.kw != 3)) return B200SEG_EUNSUPPORTED;
+  if (a.C % 8 || a.C > 1024 || a.x_ld % 8 || a.x_coff % 8) return B200SEG_EUNSUPPORTED;
+  if (a.act != 0 && a.act != 1) return B200SEG_EUNSUPPORTED;
+  return B200SEG_OK;
+}
+
+int pick_threads(int ncg) { int t = (256 / ncg) * ncg; return t > 0 ? t : ncg; }
+
+}  // namespace
+
+extern "C" int b200seg_dwconv3d_fwd(const void* x, int x_ld, int x_coff, const double* x_stats, float eps, int act,
+                                    const float* w, int flip, void* y, int y_ld, int y_coff, double* y_stats,
+                                    int B, int D, int H, int W, int C, int kd, int kh, int kw, int dtype, void* stream) {
+  DwArgs a; memset(&a, 0, sizeof(a));
+  a.x = x; a.x_ld = x_ld; a.x_coff = x_coff; a.x_stats = x_stats; a.eps = eps; a.act = act; a.w = w; a.flip = flip;
+  a.y = y; a.y_ld = y_ld; a.y_coff = y_coff; a.y_stats = y_stats;
+  a.B = B; a.D = D; a.H = H; a.W = W; a.C = C; a.kd = kd; a.kh = kh; a.kw = kw;
+  int rc = check(a, dtype);
+  if (rc) return rc;
+  if (!x || !w || !y || y_ld % 8 || y_coff % 8) return B200SEG_EINVAL;
+  const int ncg = C / 8, threads = pick_threads(ncg);
+  const int64_t items = (int64_t)D * H * ((W + RUN - 1) / RUN) * ncg;
+  int gx = (int)((items + threads - 1) / threads);
+  const int cap = (B200SEG_NUM_SMS * 8 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  const size_t sm = sizeof(float) * ((size_t)kd * kh * kw * C + 4 * C);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == B200SEG_F16) {
+    B200_CUDA(cudaFuncSetAttribute(dwconv_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dwconv_fwd_kernel<__half><<<dim3(gx, B), threads, sm, st>>>(a);
+  } else {
+    B200_CUDA(cudaFuncSetAttribute(dwconv_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dwconv_fwd_kernel<float><<<dim3(gx, B), threads, sm, st>>>(a);
+  }
+  B200_CHECK_LAUNCH("dwconv3d_fwd");
+  return B200SEG_OK;
+}
+
+extern "C" int b200seg_dwconv3d_wgrad(const void* x, int x_ld, int x_coff, const double* x_stats, float eps, int act,
+                                      const void* dy, int dy_ld, int dy_coff, float* dw,
+                                      int B, int D, int H, int W, int C, int kd, int kh, int kw, int dtype, void* stream) {
+  DwArgs a; memset(&a, 0, sizeof(a));
+  a.x = x; a.x_ld = x_ld; a.x_coff = x_coff; a.x_stats = x_stats; a.eps = eps; a.act = act;
+  a.dy = dy; a.dy_ld = dy_ld; a.dy_coff = dy_coff; a.dw = dw;
+  a.B = B; a.D = D; a.H = H; a.W = W; a.C = C; a.kd = kd; a.kh = kh; a.kw = kw;
+  int rc = check(a, dtype);
+  if (rc) return rc;
+  if (!x || !dy || !dw || dy_ld % 8 || dy_coff % 8) return B200SEG_EINVAL;
+  const int ncg = C / 8, threads = pick_threads(ncg);
+  const int64_t items = (int64_t)D * H * W * ncg;
+  int gx = (int)((items + threads - 1) / threads);
+  const int cap = (B200SEG_NUM_SMS * 4 + B * kd - 1) / (B * kd);
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  const size_t sm = sizeof(float) * ((size_t)kh * kw * C + 2 * C);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == B200SEG_F16) {
+    B200_CUDA(cudaFuncSetAttribute(dwconv_wgrad_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dwconv_wgrad_kernel<__half><<<dim3(gx, B * kd), threads, sm, st>>>(a);
+  } else {
+    B200_CUDA(cudaFuncSetAttribute(dwconv_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dwconv_wgrad_kernel<float><<<dim3(gx, B * kd), threads, sm, st>>>(a);
+  }
+  B200_CHECK_LAUNCH("dwconv3d_wgrad");
+  return B200SEG_OK;
+}

@@ -450,3 +450,103 @@ class DiceCEFn(torch.autograd.Function):
              wt.data_ptr() if has_w else None, B, V, C, ce_scale, dice_scale, out.data_ptr(), gg.data_ptr(),
              d.data_ptr(), _stream())
         return d.view(shape) if d.shape != shape else d, None, None, None, None
+
+
+# ----------------------------------------------------------------------------- MedFormer B-MHA core
+def biattn_fwd(fqv, mqv, heads, dim_head=32):
+    """fqv [B,D,H,W,2*inner], mqv [B,md,mh,mw,2*inner] channels-last (q block first, then v — the chunk(2, dim=1)
+    of medformer_utils.py:67-68).  Returns feat_out [B,D,H,W,inner], map_out [B,md,mh,mw,inner], colstat."""
+    _need_cuda(fqv)
+    inner = heads * dim_head
+    B = fqv.shape[0]
+    N = fqv.numel() // (B * fqv.shape[-1])
+    M = mqv.numel() // (B * mqv.shape[-1])
+    assert fqv.shape[-1] == 2 * inner and mqv.shape[-1] == 2 * inner and fqv.dtype == mqv.dtype
+    fo = torch.empty(*fqv.shape[:-1], inner, dtype=fqv.dtype, device=fqv.device)
+    mo = torch.empty(*mqv.shape[:-1], inner, dtype=fqv.dtype, device=fqv.device)
+    colstat = torch.empty(B, heads, M, 2, dtype=torch.float32, device=fqv.device)
+    ws = torch.empty(_lib.load().b200seg_biattn_workspace(B, N, M, heads), dtype=torch.uint8, device=fqv.device)
+    call("b200seg_biattn_fwd", fqv.data_ptr(), 2 * inner, 0, fqv.data_ptr(), 2 * inner, inner,
+         mqv.data_ptr(), 0, mqv.data_ptr(), inner, 2 * inner, fo.data_ptr(), inner, 0, mo.data_ptr(), inner, 0,
+         colstat.data_ptr(), ws.data_ptr(), B, N, M, heads, dim_head, float(dim_head) ** -0.5, _dt(fqv), _stream())
+    return fo, mo, colstat
+
+
+def biattn_bwd(fqv, mqv, mo, colstat, dfo, dmo, heads, dim_head=32):
+    inner = heads * dim_head
+    B = fqv.shape[0]
+    N = fqv.numel() // (B * fqv.shape[-1])
+    M = mqv.numel() // (B * mqv.shape[-1])
+    dfqv = torch.empty_like(fqv)
+    dmqv = torch.empty_like(mqv)
+    ws = torch.empty(_lib.load().b200seg_biattn_workspace(B, N, M, heads), dtype=torch.uint8, device=fqv.device)
+    call("b200seg_biattn_bwd", fqv.data_ptr(), 2 * inner, 0, fqv.data_ptr(), 2 * inner, inner,
+         mqv.data_ptr(), 0, mqv.data_ptr(), inner, 2 * inner, mo.data_ptr(), inner, 0, colstat.data_ptr(),
+         dfo.data_ptr(), inner, 0, dmo.data_ptr(), inner, 0,
+         dfqv.data_ptr(), 2 * inner, 0, dfqv.data_ptr(), 2 * inner, inner,
+         dmqv.data_ptr(), 0, dmqv.data_ptr(), inner, 2 * inner,
+         ws.data_ptr(), B, N, M, heads, dim_head, float(dim_head) ** -0.5, _dt(fqv), _stream())
+    return dfqv, dmqv
+
+
+class BiAttnFn(torch.autograd.Function):
+    """Differentiable B-MHA core on channels-last tensors (medformer_utils.py:63-97 minus the projections)."""
+
+    @staticmethod
+    def forward(ctx, fqv, mqv, heads, dim_head):
+        fqv = fqv.contiguous()
+        mqv = mqv.contiguous()
+        fo, mo, colstat = biattn_fwd(fqv, mqv, heads, dim_head)
+        ctx.save_for_backward(fqv, mqv, mo, colstat)
+        ctx.hd = (heads, dim_head)
+        return fo, mo
+
+    @staticmethod
+    def backward(ctx, dfo, dmo):
+        fqv, mqv, mo, colstat = ctx.saved_tensors
+        dfqv, dmqv = biattn_bwd(fqv, mqv, mo, colstat, dfo.contiguous(), dmo.contiguous(), *ctx.hd)
+        return dfqv, dmqv, None, None
+
+
+# ----------------------------------------------------------------------------- depthwise conv (MedFormer)
+def dwconv3d(x, w_taps, ksize, x_stats=None, act=ACT_NONE, flip=False, want_stats=False, eps=IN_EPS):
+    """x [B,D,H,W,C] channels-last; w_taps float32 [taps][C].  Returns (y, y_stats or None)."""
+    _need_cuda(x)
+    B, D, H, W, C = x.shape
+    y = torch.empty_like(x)
+    st = new_stats(B, C, x.device) if want_stats else None
+    call("b200seg_dwconv3d_fwd", x.data_ptr(), C, 0, _p(x_stats), eps, act, w_taps.data_ptr(), 1 if flip else 0,
+         y.data_ptr(), C, 0, _p(st), B, D, H, W, C, ksize[0], ksize[1], ksize[2], _dt(x), _stream())
+    return y, st
+
+
+def dwconv3d_wgrad(x, dy, ksize, x_stats=None, act=ACT_NONE, eps=IN_EPS):
+    B, D, H, W, C = x.shape
+    dw = torch.zeros(ksize[0] * ksize[1] * ksize[2], C, dtype=torch.float32, device=x.device)
+    call("b200seg_dwconv3d_wgrad", x.data_ptr(), C, 0, _p(x_stats), eps, act, dy.data_ptr(), C, 0, dw.data_ptr(),
+         B, D, H, W, C, ksize[0], ksize[1], ksize[2], _dt(x), _stream())
+    return dw
+
+
+class DepthwiseConvFn(torch.autograd.Function):
+    """nn.Conv3d(C, C, k, padding=k//2, groups=C, bias=False) on a channels-last tensor (conv_layers.py:135-143).
+    weight is the module's own [C,1,kd,kh,kw] parameter, so state_dicts stay interchangeable."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        ks = tuple(weight.shape[2:])
+        wt = weight.detach().reshape(weight.shape[0], -1).t().contiguous().float()      # [taps][C]
+        x = x.contiguous()
+        y, _ = dwconv3d(x, wt, ks)
+        ctx.save_for_backward(x, wt)
+        ctx.ks = ks
+        ctx.wdtype = weight.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wt = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx, _ = dwconv3d(dy, wt, ctx.ks, flip=True)
+        dw = dwconv3d_wgrad(x, dy, ctx.ks)
+        return dx, dw.t().reshape(x.shape[-1], 1, *ctx.ks).to(ctx.wdtype)

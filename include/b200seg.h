@@ -228,6 +228,53 @@ int b200seg_copy_channels(const void* x, int x_dtype, int x_ld, int x_coff,
                           void* y, int y_dtype, int y_ld, int y_coff, int accumulate,
                           int64_t nvox, int C, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * MedFormer bidirectional attention core (B-MHA), medformer_utils.py:63-97
+ * (BidirectionAttention.forward between the q/v projections and the output
+ * projections).  N = D*H*W feature voxels, M <= 32 semantic-map tokens,
+ * dim_head must be 32 (every BASELINE MedFormer level).  All tensors are
+ * channels-last with channel index  c = d*heads + h  inside the `inner` block
+ * (rearrange1, :43-51):
+ *   fq, fv : [B][N][*_ld] (+coff)      feature query / value
+ *   mq, mv : [B][M][m_ld] (+coff)      map query / value
+ *   fo     : [B][N][fo_ld]             softmax_j(S) @ map_v          (:80,84)
+ *   mo     : [B][M][mo_ld]             softmax_i(S)^T @ feat_v       (:82,89)
+ *   colstat: float[B][heads][M][2]     {max_i, sum_i exp} of the column softmax,
+ *                                      kept for the backward
+ *   workspace: b200seg_biattn_workspace() bytes (per-block partials)
+ * One pass over the voxels per direction; S/A1/A2 are never materialised.
+ * ------------------------------------------------------------------------- */
+size_t b200seg_biattn_workspace(int B, int64_t N, int M, int heads);
+int b200seg_biattn_fwd(const void* fq, int fq_ld, int fq_coff, const void* fv, int fv_ld, int fv_coff,
+                       const void* mq, int mq_coff, const void* mv, int mv_coff, int m_ld,
+                       void* fo, int fo_ld, int fo_coff, void* mo, int mo_ld, int mo_coff,
+                       float* colstat, float* workspace, int B, int64_t N, int M, int heads, int dim_head,
+                       float scale, int dtype, void* stream);
+int b200seg_biattn_bwd(const void* fq, int fq_ld, int fq_coff, const void* fv, int fv_ld, int fv_coff,
+                       const void* mq, int mq_coff, const void* mv, int mv_coff, int m_ld,
+                       const void* mo, int mo_ld, int mo_coff, const float* colstat,
+                       const void* dfo, int dfo_ld, int dfo_coff, const void* dmo, int dmo_ld, int dmo_coff,
+                       void* dfq, int dfq_ld, int dfq_coff, void* dfv, int dfv_ld, int dfv_coff,
+                       void* dmq, int dmq_coff, void* dmv, int dmv_coff, int dm_ld,
+                       float* workspace, int B, int64_t N, int M, int heads, int dim_head, float scale,
+                       int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Depthwise 3-D convolution (groups == C), stride 1, "same" padding, no bias:
+ * DepthwiseSeparableConv.depthwise conv_layers.py:135-143 (MedFormer attention
+ * projections medformer_utils.py:30-31, MBConv).  Channels-last, C % 8 == 0,
+ * kernel extents 1 or 3.  w: float[kd*kh*kw][C] (tap-major; flip != 0 reads the
+ * taps reversed = the data-gradient of the same layer).  Optional fused prologue
+ * a = act(IN(x)) from x_stats (NULL: raw x), optional IN sums of y (y_stats).
+ * wgrad: dw[tap][c] += sum dy * a   (float, caller zeroes / accumulates).
+ * ------------------------------------------------------------------------- */
+int b200seg_dwconv3d_fwd(const void* x, int x_ld, int x_coff, const double* x_stats, float eps, int act,
+                         const float* w, int flip, void* y, int y_ld, int y_coff, double* y_stats,
+                         int B, int D, int H, int W, int C, int kd, int kh, int kw, int dtype, void* stream);
+int b200seg_dwconv3d_wgrad(const void* x, int x_ld, int x_coff, const double* x_stats, float eps, int act,
+                           const void* dy, int dy_ld, int dy_coff, float* dw,
+                           int B, int D, int H, int W, int C, int kd, int kh, int kw, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

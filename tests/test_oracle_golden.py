@@ -57,3 +57,27 @@ def test_dice_alpha_is_differentiable():
         xd = x.detach().double()
         fd = (olosses.dice_loss(xd + e.double(), g["y"]) - olosses.dice_loss(xd - e.double(), g["y"])) / 2e-3
     assert abs(fd.item() - ga.view(-1)[17].item()) < 5e-3 * abs(fd.item()) + 1e-9
+
+
+@pytest.mark.parametrize("name", ["biattn_a", "biattn_b", "biattn_c"])
+def test_biattn_oracle_matches_reference_fixture(name):
+    """fixtures captured at the projection boundaries of the unmodified BidirectionAttention module."""
+    from oracle import medformer_ops as mops
+    g = load_golden(name)
+    fqv = g["fqv"].clone().requires_grad_(True)
+    mqv = g["mqv"].clone().requires_grad_(True)
+    fo, mo = mops.bidirection_attention_core(*fqv.chunk(2, 1), *mqv.chunk(2, 1), g["heads"])
+    assert rel_err(fo, g["fo"]) < 1e-5 and rel_err(mo, g["mo"]) < 1e-5
+    torch.autograd.backward([fo, mo], [g["dfo"], g["dmo"]])
+    assert rel_err(fqv.grad, g["dfqv"]) < 1e-4 and rel_err(mqv.grad, g["dmqv"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["dwconv_a", "dwconv_b"])
+def test_dwconv_oracle_matches_reference_fixture(name):
+    from oracle import medformer_ops as mops
+    g = load_golden(name)
+    x = g["x"].clone().requires_grad_(True)
+    w = g["w"].clone().requires_grad_(True)
+    y = mops.depthwise_conv3d(x, w)
+    y.backward(g["gy"])
+    assert rel_err(y, g["y"]) < 1e-6 and rel_err(x.grad, g["dx"]) < 1e-5 and rel_err(w.grad, g["dw"]) < 1e-5
