@@ -6,7 +6,8 @@ from . import _lib
 from ._lib import B200SegError, EXPORTED_SYMBOLS, LIB_PATH
 from .factory import get_model
 from .losses import CrossEntropyLoss, DiceCELoss, DiceLoss
+from .medformer import MedFormer
 from .unet3d import UNet
 
-__all__ = ["get_model", "UNet", "DiceLoss", "DiceCELoss", "CrossEntropyLoss", "B200SegError",
+__all__ = ["get_model", "UNet", "MedFormer", "DiceLoss", "DiceCELoss", "CrossEntropyLoss", "B200SegError",
            "EXPORTED_SYMBOLS", "LIB_PATH"]

@@ -45,13 +45,27 @@ _PROTOS = {
     "b200seg_copy_channels": [P, I, I, I, P, I, I, I, I, L, I, P],
     "b200seg_dwconv3d_fwd": [P, I, I, P, F, I, P, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P],
     "b200seg_dwconv3d_wgrad": [P, I, I, P, F, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P],
+    "b200seg_space_to_depth": [P, P, I, I, I, I, I, I, I, I, I, I, P],
+    "b200seg_mapgen_workspace": [I, L, I, I],
+    "b200seg_mapgen_fwd": [P, I, I, P, I, I, P, P, P, I, L, I, I, I, P],
+    "b200seg_mapgen_bwd": [P, I, I, P, I, I, P, P, P, P, I, I, P, I, I, I, I, L, I, I, I, P],
+    "b200seg_se_gate_fwd": [P, L, P, P, P, P, P, P, P, I, I, I, P],
+    "b200seg_se_gate_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P],
+    "b200seg_channel_scale_fwd": [P, P, P, I, L, I, I, P],
+    "b200seg_channel_scale_bwd_reduce": [P, P, P, I, L, I, I, P],
+    "b200seg_channel_scale_bwd_apply": [P, P, P, P, I, L, I, I, P],
+    "b200seg_layernorm_fwd": [P, P, P, P, P, I, I, F, I, P],
+    "b200seg_layernorm_bwd": [P, P, P, P, P, P, P, I, I, I, P],
+    "b200seg_gelu": [P, P, P, L, I, P],
+    "b200seg_mhsa": [P, P, P, P, I, I, I, I, F, I, P],
     "b200seg_biattn_workspace": [I, L, I, I],
     "b200seg_biattn_fwd": [P, I, I, P, I, I, P, I, P, I, I, P, I, I, P, I, I, P, P, I, L, I, I, I, F, I, P],
     "b200seg_biattn_bwd": [P, I, I, P, I, I, P, I, P, I, I, P, I, I, P, P, I, I, P, I, I, P, I, I, P, I, I,
                            P, I, P, I, I, P, I, L, I, I, I, F, I, P],
 }
 _RESTYPES = {"b200seg_strerror": c_char_p, "b200seg_last_cuda_error": c_char_p,
-             "b200seg_conv3d_wgrad_workspace": ctypes.c_size_t, "b200seg_biattn_workspace": ctypes.c_size_t}
+             "b200seg_conv3d_wgrad_workspace": ctypes.c_size_t, "b200seg_biattn_workspace": ctypes.c_size_t,
+             "b200seg_mapgen_workspace": ctypes.c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 
@@ -89,7 +103,8 @@ def check(rc, what):
 
 
 # kernels launched per entry point (dice fwd = reduce + finalize; its memset is not ours)
-_KERNELS = {"b200seg_dice_ce_fwd": 2, "b200seg_conv3d_wgrad": 3, "b200seg_biattn_fwd": 2, "b200seg_biattn_bwd": 2}
+_KERNELS = {"b200seg_dice_ce_fwd": 2, "b200seg_conv3d_wgrad": 3, "b200seg_biattn_fwd": 2, "b200seg_biattn_bwd": 2,
+            "b200seg_mapgen_fwd": 2}
 launch_count = 0
 
 

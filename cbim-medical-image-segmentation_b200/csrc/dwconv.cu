@@ -19,6 +19,7 @@ struct DwArgs {
   void* y; int y_ld, y_coff; double* y_stats;
   const void* dy; int dy_ld, dy_coff; float* dw;
   int B, D, H, W, C, kd, kh, kw;
+  int Ctot, c0;              // the launch covers channels [c0, c0+C) of a Ctot-channel layer (stats / weight rows)
 };
 
 template <typename T>
@@ -34,11 +35,11 @@ __global__ void dwconv_fwd_kernel(DwArgs a) {
   const double nvox = (double)a.D * a.H * a.W;
   for (int o = tid; o < taps * C; o += blockDim.x) {
     const int t = o / C, c = o % C;
-    s_w[o] = a.w[(a.flip ? taps - 1 - t : t) * C + c];
+    s_w[o] = a.w[(a.flip ? taps - 1 - t : t) * a.Ctot + a.c0 + c];
   }
   for (int c = tid; c < C; c += blockDim.x) {
     float mean = 0.f, rstd = 1.f;
-    if (a.x_stats) stats_to_mean_rstd(a.x_stats + ((int64_t)b * C + c) * 2, nvox, a.eps, mean, rstd);
+    if (a.x_stats) stats_to_mean_rstd(a.x_stats + ((int64_t)b * a.Ctot + a.c0 + c) * 2, nvox, a.eps, mean, rstd);
     s_scale[c] = rstd; s_shift[c] = -mean * rstd; s_sum[c] = 0.f; s_sq[c] = 0.f;
   }
   __syncthreads();
@@ -116,7 +117,7 @@ __global__ void dwconv_fwd_kernel(DwArgs a) {
     for (int c = 0; c < 8; ++c) { atomicAdd(&s_sum[cg * 8 + c], tsum[c]); atomicAdd(&s_sq[cg * 8 + c], tsq[c]); }
     __syncthreads();
     for (int c = tid; c < C; c += blockDim.x) {
-      double* st = a.y_stats + ((int64_t)b * C + c) * 2;
+      double* st = a.y_stats + ((int64_t)b * a.Ctot + a.c0 + c) * 2;
       atomicAdd(st, (double)s_sum[c]); atomicAdd(st + 1, (double)s_sq[c]);
     }
   }
@@ -200,7 +201,7 @@ int check(const DwArgs& a, int dtype) {
   if (a.B <= 0 || a.D <= 0 || a.H <= 0 || a.W <= 0 || a.C <= 0) return B200SEG_EINVAL;
   if (dtype != B200SEG_F16 && dtype != B200SEG_F32) return B200SEG_EINVAL;
   if ((a.kd != 1 && a.kd != 3) || (a.kh != 1 && a.kh != 3) || (a.kw != 1 && a.kw != 3)) return B200SEG_EUNSUPPORTED;
-  if (a.C % 8 || a.C > 1024 || a.x_ld % 8 || a.x_coff % 8) return B200SEG_EUNSUPPORTED;
+  if (a.C % 8 || a.C > 8192 || a.x_ld % 8 || a.x_coff % 8) return B200SEG_EUNSUPPORTED;
   if (a.act != 0 && a.act != 1) return B200SEG_EUNSUPPORTED;
   return B200SEG_OK;
 }
@@ -219,19 +220,28 @@ extern "C" int b200seg_dwconv3d_fwd(const void* x, int x_ld, int x_coff, const d
   int rc = check(a, dtype);
   if (rc) return rc;
   if (!x || !w || !y || y_ld % 8 || y_coff % 8) return B200SEG_EINVAL;
-  const int ncg = C / 8, threads = pick_threads(ncg);
-  const int64_t items = (int64_t)D * H * ((W + RUN - 1) / RUN) * ncg;
-  int gx = (int)((items + threads - 1) / threads);
-  const int cap = (B200SEG_NUM_SMS * 8 + B - 1) / B;
-  if (gx > cap) gx = cap;
-  const size_t sm = sizeof(float) * ((size_t)kd * kh * kw * C + 4 * C);
   cudaStream_t st = as_stream(stream);
-  if (dtype == B200SEG_F16) {
-    B200_CUDA(cudaFuncSetAttribute(dwconv_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    dwconv_fwd_kernel<__half><<<dim3(gx, B), threads, sm, st>>>(a);
-  } else {
-    B200_CUDA(cudaFuncSetAttribute(dwconv_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    dwconv_fwd_kernel<float><<<dim3(gx, B), threads, sm, st>>>(a);
+  const int taps = kd * kh * kw;
+  // shared memory holds taps+4 floats per channel: wide layers (PatchMerging's 2048 merged channels) go in slices
+  int chunk = C;
+  while (sizeof(float) * (size_t)(taps + 4) * chunk > 160 * 1024) chunk = ((chunk / 2 + 7) / 8) * 8;
+  a.Ctot = C;
+  for (int c0 = 0; c0 < C; c0 += chunk) {
+    const int cc = (C - c0 < chunk) ? C - c0 : chunk;
+    a.C = cc; a.c0 = c0; a.x_coff = x_coff + c0; a.y_coff = y_coff + c0;
+    const int ncg = cc / 8, threads = pick_threads(ncg);
+    const int64_t items = (int64_t)D * H * ((W + RUN - 1) / RUN) * ncg;
+    int gx = (int)((items + threads - 1) / threads);
+    const int cap = (B200SEG_NUM_SMS * 8 + B - 1) / B;
+    if (gx > cap) gx = cap;
+    const size_t sm = sizeof(float) * ((size_t)taps * cc + 4 * cc);
+    if (dtype == B200SEG_F16) {
+      B200_CUDA(cudaFuncSetAttribute(dwconv_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      dwconv_fwd_kernel<__half><<<dim3(gx, B), threads, sm, st>>>(a);
+    } else {
+      B200_CUDA(cudaFuncSetAttribute(dwconv_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      dwconv_fwd_kernel<float><<<dim3(gx, B), threads, sm, st>>>(a);
+    }
   }
   B200_CHECK_LAUNCH("dwconv3d_fwd");
   return B200SEG_OK;
@@ -242,7 +252,7 @@ extern "C" int b200seg_dwconv3d_wgrad(const void* x, int x_ld, int x_coff, const
                                       int B, int D, int H, int W, int C, int kd, int kh, int kw, int dtype, void* stream) {
   DwArgs a; memset(&a, 0, sizeof(a));
   a.x = x; a.x_ld = x_ld; a.x_coff = x_coff; a.x_stats = x_stats; a.eps = eps; a.act = act;
-  a.dy = dy; a.dy_ld = dy_ld; a.dy_coff = dy_coff; a.dw = dw;
+  a.dy = dy; a.dy_ld = dy_ld; a.dy_coff = dy_coff; a.dw = dw; a.Ctot = C; a.c0 = 0;
   a.B = B; a.D = D; a.H = H; a.W = W; a.C = C; a.kd = kd; a.kh = kh; a.kw = kw;
   int rc = check(a, dtype);
   if (rc) return rc;

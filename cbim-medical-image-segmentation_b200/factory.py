@@ -11,6 +11,16 @@ def get_model(args, pretrain=False):
                 raise ValueError('No pretrain model available')   # model/utils.py:77-78
             return UNet(args.in_chan, args.base_chan, num_classes=args.classes, scale=args.down_scale,
                         norm=args.norm, kernel_size=args.kernel_size, block=args.block)
+        if args.model == 'medformer':
+            from .medformer import MedFormer
+            if pretrain:
+                raise ValueError('No pretrain model available')   # model/utils.py:92-93
+            return MedFormer(args.in_chan, args.classes, args.base_chan, map_size=args.map_size,
+                             conv_block=args.conv_block, conv_num=args.conv_num, trans_num=args.trans_num,
+                             num_heads=args.num_heads, fusion_depth=args.fusion_depth, fusion_dim=args.fusion_dim,
+                             fusion_heads=args.fusion_heads, expansion=args.expansion, attn_drop=args.attn_drop,
+                             proj_drop=args.proj_drop, proj_type=args.proj_type, norm=args.norm, act=args.act,
+                             kernel_size=args.kernel_size, scale=args.down_scale, aux_loss=args.aux_loss)   # :95
         raise ValueError("model %r (3d) is not implemented by the B200 path yet" % (args.model,))
     if args.dimension == '2d':
         raise ValueError("2d models are outside the B200 hot path (SURVEY.md §2); use the reference")

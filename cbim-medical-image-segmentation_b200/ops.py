@@ -168,18 +168,21 @@ class PackedWeights:
         self._fwd = None
         self._bwd = None
 
-    def get(self, weights, dtype, B=1):
-        key = (dtype, B) + tuple((w.data_ptr(), w._version) for w in weights)
+    def get(self, weights, dtype, B=1, co_pad=0):
+        """co_pad extra all-zero output channels are appended (Cout not a multiple of 8/16, e.g. the 27 map codes
+        or 14 classes of MedFormer) so the wide-tile kernels and 16-byte stores apply; callers ignore them."""
+        key = (dtype, B, co_pad) + tuple((w.data_ptr(), w._version) for w in weights)
         if key != self._key:
-            co_total = sum(w.shape[0] for w in weights)
+            co_total = sum(w.shape[0] for w in weights) + co_pad
             Cin = weights[0].shape[1]
             ks = tuple(weights[0].shape[2:])
             taps = weights[0][0, 0].numel()
             dev = weights[0].device
             algo_f = conv_algo(Cin, co_total, ks, dtype, B)
             algo_b = conv_algo(co_total, Cin, ks, dtype, B)      # dgrad: channels swap roles
-            fwd = torch.empty(taps * co_total * Cin, dtype=dtype, device=dev)
-            bwd = torch.empty(taps * co_total * Cin, dtype=dtype, device=dev)
+            alloc = torch.zeros if co_pad else torch.empty
+            fwd = alloc(taps * co_total * Cin, dtype=dtype, device=dev)
+            bwd = alloc(taps * co_total * Cin, dtype=dtype, device=dev)
             off = 0
             for w in weights:
                 pack_weight(w, dtype, False, fwd, off, co_total, algo_f)

@@ -275,6 +275,54 @@ int b200seg_dwconv3d_wgrad(const void* x, int x_ld, int x_coff, const double* x_
                            const void* dy, int dy_ld, int dy_coff, float* dw,
                            int B, int D, int H, int W, int C, int kd, int kh, int kw, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * MedFormer operators that are not convolutions (all channels-last).
+ *
+ * space_to_depth: PatchMerging gather medformer_utils.py:165-171,
+ *   y[b,d,h,w,q*C+c] = x[b,d*sd+i,h*sh+j,w*sw+k,c], q=(i*sh+j)*sw+k; reverse!=0
+ *   scatters y back into x (the gradient).  Do/Ho/Wo are the OUTPUT extents.
+ * mapgen: SemanticMapGeneration medformer_utils.py:221-226,
+ *   map[b,k,c] = sum_j softmax_j(wl[b,j,k]) * f[b,j,c]   (K <= 32 map codes),
+ *   colstat float[B][K][2]; bwd writes df and dwl (dw_pad >= K logits channels,
+ *   the padding gets zeros) into the gradient of the fused projection output.
+ * se_gate: SEBlock conv_layers.py:159-174 on the channel means taken from IN
+ *   sums: gate = sigmoid(W2 relu(W1 mean + b1) + b2); w1 [R][C], w2 [C][R].
+ *   bwd accumulates (+=) dw1/db1/dw2/db2 and returns dmean.
+ * channel_scale: y = x*gate[b][c]; bwd_reduce: dgate += sum_vox dy*x;
+ *   bwd_apply: dx = dy*gate + dmean/V (dmean may be NULL).
+ * layernorm: nn.LayerNorm(C, eps) trans_layers.py:36-41 over rows [R][C];
+ *   mean_rstd float[R][2]; bwd accumulates (+=) dgamma/dbeta.
+ * gelu: exact erf GELU trans_layers.py:22; dy==NULL -> forward, else out=dy*gelu'(x).
+ * mhsa: Attention core trans_layers.py:84-93 for L<=128 tokens, dim_head 32;
+ *   qkv [B][L][3*inner] ('(heads dim_head)' order), out [B][L][inner];
+ *   forward when dout==NULL, otherwise writes dqkv.
+ * ------------------------------------------------------------------------- */
+int b200seg_space_to_depth(void* x, void* y, int B, int Do, int Ho, int Wo, int C, int sd, int sh, int sw,
+                           int reverse, int dtype, void* stream);
+size_t b200seg_mapgen_workspace(int B, int64_t N, int K, int C);
+int b200seg_mapgen_fwd(const void* f, int f_ld, int f_coff, const void* wl, int w_ld, int w_coff,
+                       void* map, float* colstat, float* workspace, int B, int64_t N, int K, int C,
+                       int dtype, void* stream);
+int b200seg_mapgen_bwd(const void* f, int f_ld, int f_coff, const void* wl, int w_ld, int w_coff,
+                       const void* map, const float* colstat, const void* dmap,
+                       void* df, int df_ld, int df_coff, void* dwl, int dw_ld, int dw_coff, int dw_pad,
+                       int B, int64_t N, int K, int C, int dtype, void* stream);
+int b200seg_se_gate_fwd(const double* stats, int64_t nvox, const float* w1, const float* b1, const float* w2,
+                        const float* b2, float* gate, float* hidden, float* mean, int B, int C, int R, void* stream);
+int b200seg_se_gate_bwd(const float* dgate, const float* gate, const float* hidden, const float* mean,
+                        const float* w1, const float* w2, float* dw1, float* db1, float* dw2, float* db2,
+                        float* dmean, int B, int C, int R, void* stream);
+int b200seg_channel_scale_fwd(const void* x, const float* gate, void* y, int B, int64_t V, int C, int dtype, void* stream);
+int b200seg_channel_scale_bwd_reduce(const void* dy, const void* x, float* dgate, int B, int64_t V, int C, int dtype, void* stream);
+int b200seg_channel_scale_bwd_apply(const void* dy, const float* gate, const float* dmean, void* dx, int B, int64_t V, int C, int dtype, void* stream);
+int b200seg_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean_rstd,
+                          int R, int C, float eps, int dtype, void* stream);
+int b200seg_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean_rstd, void* dx,
+                          float* dgamma, float* dbeta, int R, int C, int dtype, void* stream);
+int b200seg_gelu(const void* x, const void* dy, void* out, int64_t n, int dtype, void* stream);
+int b200seg_mhsa(const void* qkv, const void* dout, void* out, void* dqkv, int B, int L, int heads, int dim_head,
+                 float scale, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,315 @@
+"""GPU: MedFormer building blocks and the whole model through the C-ABI against the reference-pinned oracle
+(oracle/medformer.py, fixtures tests/golden/medformer_*.pt captured from the unmodified reference)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import losses as olosses
+from oracle import medformer as omed
+from oracle import medformer_ops as mops
+from oracle.synth import make_volume
+from oracle.unet3d import make_state_dict
+from util import global_l2, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float32: 2e-4, torch.float16: 6e-3}
+
+
+def cl(t):      # NCDHW -> channels-last contiguous
+    return t.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def cf(t):
+    return t.permute(0, 4, 1, 2, 3).contiguous()
+
+
+def l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def mo():
+    import b200seg  # noqa
+    from b200seg import medformer_ops as m
+    assert m._lib.load().b200seg_check_device() == 0, "not a B200"
+    return m
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("scale", [(1, 2, 2), (2, 2, 2)])
+def test_space_to_depth(mo, dtype, scale):
+    torch.manual_seed(0)
+    x = torch.randn(2, 16, 4, 6, 8).to(dtype)
+    parts = [x[:, :, i::scale[0], j::scale[1], k::scale[2]] for i in range(scale[0]) for j in range(scale[1]) for k in range(scale[2])]
+    ref = torch.cat(parts, 1)
+    xg = cl(x).cuda().requires_grad_(True)
+    y, st = mo.SpaceToDepthFn.apply(xg, scale)
+    assert torch.equal(cf(y.cpu()), ref)
+    yd = ref.double().flatten(2)
+    assert rel_err(st.cpu(), torch.stack([yd.sum(-1), (yd * yd).sum(-1)], -1)) < 1e-5
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr = x.clone().float().requires_grad_(True)
+    parts = [xr[:, :, i::scale[0], j::scale[1], k::scale[2]] for i in range(scale[0]) for j in range(scale[1]) for k in range(scale[2])]
+    torch.cat(parts, 1).backward(cf(gy.float().cpu()))
+    assert torch.equal(cf(xg.grad.float().cpu()), xr.grad)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("B,C,K,sp", [(2, 128, 27, (6, 12, 10)), (1, 320, 27, (3, 5, 7)), (1, 64, 18, (2, 9, 15))])
+def test_mapgen(mo, dtype, B, C, K, sp):
+    torch.manual_seed(1)
+    pad = (-(C + K)) % 16
+    fw = torch.randn(B, C + K + pad, *sp).to(dtype)
+    fw[:, C + K:] = 0
+    ms = {27: (3, 3, 3), 18: (2, 3, 3)}[K]
+    f64 = fw.double().requires_grad_(True)
+    wm = F.softmax(f64[:, C:C + K].flatten(2), dim=2)
+    ref = torch.einsum("bij,bkj->bik", f64[:, :C].flatten(2), wm)          # [B,C,K]
+    fg = cl(fw).cuda().requires_grad_(True)
+    smap = mo.MapGenFn.apply(fg, C, K, ms)
+    out = smap.reshape(B, K, C).permute(0, 2, 1)
+    assert rel_err(out, ref) < TOL[dtype]
+    gm = torch.randn(B, C, K).to(dtype)
+    ref.backward(gm.double())
+    smap.backward(gm.permute(0, 2, 1).reshape(B, *ms, C).contiguous().cuda())
+    got = cf(fg.grad.float().cpu())
+    assert rel_err(got[:, :C + K], f64.grad[:, :C + K]) < 2 * TOL[dtype]
+    assert got[:, C + K:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_se_scale(mo, dtype):
+    torch.manual_seed(2)
+    B, C, R = 2, 64, 16
+    x = (torch.randn(B, C, 4, 6, 5) + 0.3).to(dtype)
+    sd = {"excitation.0.weight": torch.randn(R, C, 1, 1, 1) * 0.2, "excitation.0.bias": torch.randn(R) * 0.1,
+          "excitation.2.weight": torch.randn(C, R, 1, 1, 1) * 0.2, "excitation.2.bias": torch.randn(C) * 0.1}
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    x64 = x.double().requires_grad_(True)
+    ref = omed.se_block(sd64, "", x64)
+    gy = torch.randn_like(ref)
+    ref.backward(gy)
+    ps = {k: v.cuda().requires_grad_(True) for k, v in sd.items()}
+    xg = cl(x).cuda().requires_grad_(True)
+    xd = x.double().flatten(2)
+    st = torch.stack([xd.sum(-1), (xd * xd).sum(-1)], -1).cuda()
+    y, yst = mo.SEScaleFn.apply(xg, st, ps["excitation.0.weight"], ps["excitation.0.bias"], ps["excitation.2.weight"], ps["excitation.2.bias"])
+    y.backward(cl(gy).to(dtype).cuda())
+    assert rel_err(cf(y.float().cpu()), ref) < TOL[dtype]
+    yd = cf(y.double().cpu()).flatten(2)
+    assert rel_err(yst.cpu(), torch.stack([yd.sum(-1), (yd * yd).sum(-1)], -1)) < 1e-4
+    assert rel_err(cf(xg.grad.float().cpu()), x64.grad) < 2 * TOL[dtype]
+    for k in sd:
+        assert rel_err(ps[k].grad.cpu(), sd64[k].grad) < 3 * TOL[dtype], k
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_token_transformer_pieces(mo, dtype):
+    """LayerNorm, GELU and the 81-token attention against torch fp64."""
+    torch.manual_seed(3)
+    B, L, C, heads = 2, 81, 320, 10
+    x = torch.randn(B, L, C).to(dtype)
+    g, b = 1 + 0.1 * torch.randn(C), 0.1 * torch.randn(C)
+    x64, g64, b64 = x.double().requires_grad_(True), g.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = F.layer_norm(x64, (C,), g64, b64)
+    gy = torch.randn_like(ref)
+    ref.backward(gy)
+    xg, gg, bg = x.cuda().requires_grad_(True), g.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = mo.LayerNormFn.apply(xg, gg, bg, 1e-5)
+    y.backward(gy.to(dtype).cuda())
+    assert rel_err(y, ref) < TOL[dtype] and rel_err(xg.grad, x64.grad) < 2 * TOL[dtype]
+    assert rel_err(gg.grad, g64.grad) < 2 * TOL[dtype] and rel_err(bg.grad, b64.grad) < 2 * TOL[dtype]
+    # GELU
+    x64 = x.double().requires_grad_(True)
+    ref = F.gelu(x64)
+    ref.backward(gy)
+    xg = x.cuda().requires_grad_(True)
+    y = mo.GeluFn.apply(xg)
+    y.backward(gy.to(dtype).cuda())
+    assert rel_err(y, ref) < TOL[dtype] and rel_err(xg.grad, x64.grad) < 2 * TOL[dtype]
+    # attention core
+    qkv = torch.randn(B, L, 3 * C).to(dtype)
+    q64 = qkv.double().requires_grad_(True)
+    q, k, v = (t.reshape(B, L, heads, -1).permute(0, 2, 1, 3) for t in q64.chunk(3, dim=-1))
+    att = F.softmax(torch.einsum("bhid,bhjd->bhij", q, k) * 32 ** -0.5, dim=-1)
+    ref = torch.einsum("bhij,bhjd->bhid", att, v).permute(0, 2, 1, 3).reshape(B, L, -1)
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    qg = qkv.cuda().requires_grad_(True)
+    out = mo.MHSAFn.apply(qg, heads, 32)
+    out.backward(go.to(dtype).cuda())
+    assert rel_err(out, ref) < TOL[dtype] and rel_err(qg.grad, q64.grad) < 2 * TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("cin,couts,k,pad,norm,act,bias,res,sp", [
+    (64, [128], (1, 1, 1), 0, True, 1, False, False, (4, 8, 8)),        # MBConv expand: conv1x1(relu(IN(x)))
+    (128, [64], (1, 1, 1), 0, True, 0, False, True, (4, 8, 8)),         # MBConv project: conv1x1(IN(x)) + residual
+    (64, [64, 27], (3, 3, 3), 5, False, 0, False, False, (4, 8, 8)),    # map generation: two raw 3x3x3 projections
+    (128, [14], (1, 1, 1), 2, False, 0, True, False, (3, 6, 5)),        # aux head with bias, padded to 16
+    (320, [640], (1, 1, 1), 0, True, 0, False, False, (3, 3, 3)),       # map_qv on the 27 tokens (eps 1e-5)
+])
+def test_conv_fn(mo, dtype, cin, couts, k, pad, norm, act, bias, res, sp):
+    from b200seg.medformer import _conv
+    from b200seg.ops import PackedWeights, instnorm_stats
+    torch.manual_seed(4)
+    B = 2
+    eps = 1e-5
+    x = torch.randn(B, cin, *sp).to(dtype)
+    ws = [torch.randn(c, cin, *k) * (cin * k[0] * k[1] * k[2]) ** -0.5 for c in couts]
+    bz = torch.randn(couts[0]) * 0.1 if bias else None
+    r = torch.randn(B, couts[0], *sp).to(dtype) if res else None
+    x64 = x.double().requires_grad_(True)
+    w64 = [w.to(dtype).double().requires_grad_(True) for w in ws]
+    a = F.instance_norm(x64, eps=eps) if norm else x64
+    a = F.relu(a) if act else a
+    ref = torch.cat([F.conv3d(a, w, None, padding=[i // 2 for i in k]) for w in w64], 1)
+    b64 = None
+    if bias:
+        b64 = bz.double().requires_grad_(True)
+        ref = ref + b64.view(1, -1, 1, 1, 1)
+    r64 = None
+    if res:
+        r64 = r.double().requires_grad_(True)
+        ref = ref + r64
+    gy = torch.randn_like(ref)
+    ref.backward(gy)
+    xg = cl(x).cuda().requires_grad_(True)
+    wg = [w.cuda().requires_grad_(True) for w in ws]
+    bg = bz.cuda().requires_grad_(True) if bias else None
+    rg = cl(r).cuda().requires_grad_(True) if res else None
+    st = instnorm_stats(xg.detach(), 0, cin) if norm else None
+    y, yst = _conv(PackedWeights(), xg, st, wg, k, act=act, bias=bg, residual=rg, co_pad=pad, eps=eps)
+    ctot = sum(couts)
+    gyp = torch.zeros(B, *sp, ctot + pad)
+    gyp[..., :ctot] = cl(gy.float())
+    y.backward(gyp.to(dtype).cuda())
+    tol = TOL[dtype]
+    assert rel_err(cf(y.float().cpu())[:, :ctot], ref) < tol
+    if pad:
+        assert y[..., ctot:].abs().max().item() == 0.0
+    assert l2(cf(xg.grad.float().cpu()), x64.grad) < (2e-3 if dtype == torch.float32 else 3e-2)
+    for w_, w6 in zip(wg, w64):
+        assert l2(w_.grad, w6.grad) < (2e-3 if dtype == torch.float32 else 3e-2)
+    if bias:
+        assert rel_err(bg.grad.cpu(), b64.grad) < 2 * tol
+    if res:
+        assert rel_err(cf(rg.grad.float().cpu()), r64.grad) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("C,k,act,sp", [(64, (3, 3, 3), 1, (4, 10, 9)), (2048, (3, 3, 3), 0, (2, 3, 3)), (256, (1, 3, 3), 0, (3, 6, 6))])
+def test_dwconv_fn_through_instnorm(mo, dtype, C, k, act, sp):
+    from b200seg.ops import instnorm_stats
+    torch.manual_seed(5)
+    B, eps = 2, 1e-5
+    x = (torch.randn(B, C, *sp) * 1.5 + 0.2).to(dtype)
+    w = torch.randn(C, 1, *k) * 0.3
+    x64, w64 = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    a = F.instance_norm(x64, eps=eps)
+    a = F.relu(a) if act else a
+    ref = mops.depthwise_conv3d(a, w64)
+    gy = torch.randn_like(ref)
+    ref.backward(gy)
+    xg, wg = cl(x).cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    st = instnorm_stats(xg.detach(), 0, C)
+    y, yst = mo.DwConvFn.apply(xg, st, wg, act, eps)
+    y.backward(cl(gy).to(dtype).cuda())
+    assert rel_err(cf(y.float().cpu()), ref) < TOL[dtype]
+    assert l2(cf(xg.grad.float().cpu()), x64.grad) < (2e-3 if dtype == torch.float32 else 3e-2)
+    assert l2(wg.grad, w64.grad) < (2e-3 if dtype == torch.float32 else 3e-2)
+
+
+def _build(g):
+    import b200seg
+    cfg = g["cfg"]
+    kw = {k: cfg[k] for k in ("map_size", "conv_num", "trans_num", "num_heads", "fusion_depth", "fusion_dim",
+                              "fusion_heads", "kernel_size", "scale", "aux_loss")}
+    net = b200seg.MedFormer(1, cfg["classes"], 32, conv_block="BasicBlock", expansion=4, attn_drop=0, proj_drop=0,
+                            proj_type="depthwise", norm="in", act="relu", **kw)
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == g["shapes"]
+    sd = make_state_dict(g["shapes"], seed=cfg["state_seed"])
+    for k in sd:
+        if k.endswith("norm.weight"):
+            sd[k] = 1.0 + 0.1 * sd[k] / sd[k].abs().max()
+    net.load_state_dict(sd)
+    return net.cuda(), sd, kw
+
+
+def _oracle64(sd, img, lab, w, aux_w, kw, dt=torch.float64):
+    s = {k: v.to(dt).clone().requires_grad_(True) for k, v in sd.items()}
+    r = omed.medformer_forward(s, img.to(dt), kw)
+    loss = olosses.total_loss(r, lab, w.to(dt), aux_w) if isinstance(r, list) else olosses.total_loss(r, lab, w.to(dt))
+    loss.backward()
+    return {k: v.grad.double() for k, v in s.items()}, [t.detach().double() for t in (r if isinstance(r, list) else [r])]
+
+
+def _our_loss(b200seg, res, lab, w, aux_w):
+    crit = b200seg.DiceCELoss(weight=w)
+    if isinstance(res, (list, tuple)):
+        return sum(aux_w[j] * crit(r, lab) for j, r in enumerate(res))
+    return crit(res, lab)
+
+
+@pytest.mark.parametrize("name", ["medformer_bcv", "medformer_var"])
+def test_medformer_fp32_matches_reference(name):
+    import b200seg
+    g = load_golden(name)
+    cfg = g["cfg"]
+    net, sd, kw = _build(g)
+    img, lab = make_volume(*cfg["shape"], cfg["classes"], seed=cfg["data_seed"])
+    w = torch.tensor(cfg["ce_weight"])
+    res = net(img.cuda())
+    outs = res if isinstance(res, list) else [res]
+    loss = _our_loss(b200seg, res, lab.cuda(), w, cfg["aux_weight"])
+    loss.backward()
+    for o, ref, am in zip(outs, g["logits"], g["argmax"]):
+        lg = o.detach().float().cpu()
+        assert lg.shape == ref.shape
+        assert rel_err(lg, ref.float()) < 2e-3                      # fixture stored in fp16
+        assert (lg.argmax(1).to(torch.uint8) == am).float().mean().item() > 0.9995
+    assert abs(loss.item() - g["loss"]) < 1e-4
+    g64, l64 = _oracle64(sd, img, lab, w, cfg["aux_weight"], kw)
+    g32, _ = _oracle64(sd, img, lab, w, cfg["aux_weight"], kw, torch.float32)
+    for o, ref in zip(outs, l64):
+        assert rel_err(o.detach().float().cpu(), ref) < 1e-3
+    ours = {k: p.grad for k, p in net.named_parameters()}
+    floor = global_l2(g32, g64)
+    err = global_l2(ours, g64)
+    gmax = max(v.abs().max().item() for v in g64.values())
+    worst = max(((ours[k].double().cpu() - g64[k]).abs().max() / (g64[k].abs().max() + 1e-4 * gmax)).item() for k in g64)
+    floor_w = max(((g32[k] - g64[k]).abs().max() / (g64[k].abs().max() + 1e-4 * gmax)).item() for k in g64)
+    print("%s: global L2 grad err %.2e (reference fp32 floor %.2e); worst tensor %.2e (floor %.2e)" % (name, err, floor, worst, floor_w))
+    assert err < max(1e-3, 3 * floor)
+    assert worst < max(1e-3, 3 * floor_w)
+
+
+@pytest.mark.parametrize("name", ["medformer_bcv"])
+def test_medformer_amp_close_to_fp32_reference(name):
+    import b200seg
+    g = load_golden(name)
+    cfg = g["cfg"]
+    net, sd, kw = _build(g)
+    img, lab = make_volume(*cfg["shape"], cfg["classes"], seed=cfg["data_seed"])
+    w = torch.tensor(cfg["ce_weight"])
+    scale = 1024.0
+    with torch.autocast("cuda", dtype=torch.float16):
+        res = net(img.cuda())
+        assert res[0].dtype == torch.float16
+        loss = _our_loss(b200seg, res, lab.cuda(), w, cfg["aux_weight"])
+    (loss * scale).backward()
+    for o, ref in zip(res, g["logits"]):
+        assert rel_err(o.detach().float().cpu(), ref.float()) < 5e-2
+    assert abs(loss.item() - g["loss"]) < 3e-2
+    g64, _ = _oracle64(sd, img, lab, w, cfg["aux_weight"], kw)
+    ours = {k: p.grad / scale for k, p in net.named_parameters()}
+    err = global_l2(ours, g64)
+    sdg = {k: v.cuda().requires_grad_(True) for k, v in sd.items()}
+    with torch.autocast("cuda", dtype=torch.float16):
+        lref = olosses.total_loss(omed.medformer_forward(sdg, img.cuda(), kw), lab.cuda(), w.cuda(), cfg["aux_weight"])
+    (lref * scale).backward()
+    amp_floor = global_l2({k: v.grad / scale for k, v in sdg.items()}, g64)
+    print("%s amp: global L2 grad err ours %.2e | stock torch autocast %.2e" % (name, err, amp_floor))
+    assert err < max(0.05, 2 * amp_floor)

@@ -94,7 +94,7 @@ def test_dwconv_golden(ops, name, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
 @pytest.mark.parametrize("B,C,sp,k", [(2, 64, (6, 24, 22), (3, 3, 3)), (1, 320, (3, 6, 6), (3, 3, 3)),
-                                      (1, 40, (5, 7, 9), (1, 3, 3)), (1, 8, (1, 1, 1), (3, 3, 3))])
+                                      (1, 40, (5, 7, 9), (1, 3, 3)), (1, 8, (1, 2, 3), (3, 3, 3))])
 def test_dwconv_fused_prologue_and_stats(ops, dtype, B, C, sp, k):
     """a = relu(IN(x)) prologue from producer sums + IN sums of the output, vs the oracle composition."""
     torch.manual_seed(9)
