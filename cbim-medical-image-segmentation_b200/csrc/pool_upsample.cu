@@ -189,7 +189,7 @@ upsample_fwd_kernel(const T* __restrict__ x, int x_ld, int x_coff, T* __restrict
 
 // gather-form backward: each INPUT voxel collects from the output voxels whose stencil touches it
 // (deterministic, no atomics, no zero-fill).  Per axis at most kMaxTaps output indices contribute.
-constexpr int kMaxTaps = 8;
+constexpr int kMaxTaps = 12;
 __device__ __forceinline__ int axis_taps(float scale, int i, int in_size, int out_size, int (&oo)[kMaxTaps], float (&ww)[kMaxTaps]) {
   int n = 0;
   int lo, hi;
