@@ -30,9 +30,54 @@ WORKLOADS = {
                          [[1, 3, 3], [1, 3, 3], [3, 3, 3], [3, 3, 3], [3, 3, 3]], 4, [0.5, 1, 1, 1], (1, 128, 128, 128)),
     "resunet_iso_128": ([[2, 2, 2]] * 4, [[3, 3, 3]] * 5, 4, [0.5, 1, 1, 1], (1, 128, 128, 128)),
     "resunet_kits_160": ([[2, 2, 2]] * 4, [[3, 3, 3]] * 5, 3, [0.5, 1, 2], (2, 160, 160, 80)),
+    # BASELINE.json configs[2]: MedFormer, config/bcv/medformer_3d.yaml:9-28,38-39,49 on a 96^3 crop, AMP
+    "medformer_bcv_96": (dict(map_size=[3, 3, 3], conv_num=[2, 0, 0, 0, 0, 0, 2, 2], trans_num=[0, 2, 4, 6, 4, 2, 0, 0],
+                              num_heads=[1, 4, 8, 10, 8, 4, 1, 1], fusion_depth=2, fusion_dim=320, fusion_heads=10,
+                              kernel_size=[[1, 3, 3], [1, 3, 3], [3, 3, 3], [3, 3, 3], [3, 3, 3]],
+                              scale=[[1, 2, 2], [1, 2, 2], [2, 2, 2], [2, 2, 2]], aux_loss=True),
+                         None, 14, [0.5] + [1.0] * 13, (1, 96, 96, 96)),
 }
 BASE = 32
 METRIC = "3D-UNet (ResBasicBlock) training voxels/sec, synthetic 128^3"
+METRIC_MEDFORMER = "3D MedFormer training voxels/sec, synthetic 96^3"
+AUX_WEIGHT = [0.5, 0.5]
+
+
+def is_medformer(wl):
+    return isinstance(wl[0], dict)
+
+
+def metric_of(wl):
+    return METRIC_MEDFORMER if is_medformer(wl) else METRIC
+
+
+def model_name(wl):
+    if is_medformer(wl):
+        return "MedFormer-3D BCV config (reference MedFormer(1,14,32,...,norm='in',act='relu',aux_loss=True))"
+    return "ResUNet-3D base32 BasicBlock IN (reference UNet(1,32,...,block='BasicBlock',norm='in'))"
+
+
+def oracle_state(wl):
+    """Seeded synthetic weights keyed like the reference's state_dict."""
+    import torch
+    from oracle import unet3d as ounet
+    if is_medformer(wl):
+        shapes = torch.load(os.path.join(ROOT, "tests", "golden", "medformer_bcv.pt"), weights_only=False)["shapes"]
+        sd = ounet.make_state_dict(shapes, seed=7)
+        for k in sd:
+            if k.endswith("norm.weight"):
+                sd[k] = 1.0 + 0.1 * sd[k] / sd[k].abs().max()
+        return sd
+    return ounet.make_state_dict(ounet.unet_param_shapes(1, BASE, wl[2], wl[1], "BasicBlock"), seed=7)
+
+
+def oracle_loss(wl, sd, img, lab, w):
+    from oracle import losses as olosses
+    if is_medformer(wl):
+        from oracle import medformer as omed
+        return olosses.total_loss(omed.medformer_forward(sd, img, wl[0]), lab, w, AUX_WEIGHT)
+    from oracle import unet3d as ounet
+    return olosses.total_loss(ounet.unet_forward(sd, img, wl[0], wl[1], "BasicBlock"), lab, w)
 
 
 def conv_layers(scale, kernel, classes, B, D, H, W, base=BASE):
@@ -140,51 +185,48 @@ def host_info():
 
 
 # --------------------------------------------------------------------------- CPU (reference) arm
-def oracle_step_fn(scale, kernel, classes, weight):
+def oracle_step_fn(wl):
     import torch
-    from oracle import losses as olosses
-    from oracle import unet3d as ounet
-    shapes = ounet.unet_param_shapes(1, BASE, classes, kernel, "BasicBlock")
-    sd = {k: v.requires_grad_(True) for k, v in ounet.make_state_dict(shapes, seed=7).items()}
+    sd = {k: v.requires_grad_(True) for k, v in oracle_state(wl).items()}
     params = list(sd.values())
     opt = torch.optim.AdamW(params, lr=1e-3, betas=(0.9, 0.999), weight_decay=0.05, eps=1e-5)
-    w = torch.tensor(weight, dtype=torch.float32)
+    w = torch.tensor(wl[3], dtype=torch.float32)
 
     def step(img, lab):
         opt.zero_grad(set_to_none=True)
-        loss = olosses.total_loss(ounet.unet_forward(sd, img, scale, kernel, "BasicBlock"), lab, w)
+        loss = oracle_loss(wl, sd, img, lab, w)
         loss.backward()
         opt.step()
         return loss.item()
     return step
 
 
-def cpu_sample_shape(scale, budget_s, steps_total, step, classes):
-    """Pick the largest depth-crop of the workload whose (steps_total) steps fit in budget_s."""
-    import torch
+def cpu_sample_shape(wl, step):
+    """Smallest legal depth-crop of the workload and the measured CPU rate on it (voxels/s)."""
     from oracle.synth import make_volume
+    scale = wl[0]["scale"] if is_medformer(wl) else wl[0]
+    classes, (_, _, H, W) = wl[2], wl[4]
     dmin = 1
     for s in scale:
         dmin *= s[0]
     dmin = max(dmin * 2, 8)
-    img, lab = make_volume(1, dmin, 128, 128, classes, seed=1)
+    img, lab = make_volume(1, dmin, H, W, classes, seed=1)
     step(img, lab)
     t0 = time.time(); step(img, lab); t = time.time() - t0
-    rate = dmin * 128 * 128 / t
-    return dmin, rate
+    return dmin, dmin * H * W / t
 
 
 def run_reference(args, wl):
     import torch
     from oracle.synth import make_volume
-    scale, kernel, classes, weight, (B, D, H, W) = wl
+    classes, (B, D, H, W) = wl[2], wl[4]
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = usable_cores()
     torch.set_num_threads(cores)
-    step = oracle_step_fn(scale, kernel, classes, weight)
-    dmin, rate = cpu_sample_shape(scale, 0, 0, step, classes)
+    step = oracle_step_fn(wl)
+    dmin, rate = cpu_sample_shape(wl, step)
     total = args.steps + args.warmup
     budget = 150.0
     d = dmin
@@ -200,10 +242,10 @@ def run_reference(args, wl):
     vps = args.steps * d * H * W / dt
     model, _ = host_info()
     sample = "depth-crop %dx%dx%d of the %dx%dx%d volume, batch 1, fp32, oracle port of the reference modules" % (d, H, W, D, H, W)
-    out = {"impl": "reference", "metric": METRIC, "value": vps, "unit": "voxels/s", "n_gpus": args.gpus,
+    out = {"impl": "reference", "metric": metric_of(wl), "value": vps, "unit": "voxels/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": args.workload, "model": "ResUNet-3D base32 BasicBlock IN", "sample": sample},
+           "config": {"workload": args.workload, "model": model_name(wl), "sample": sample},
            "cpu_baseline": {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample,
                             "cpu": model},
            "e2e": {"value": vps, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -219,9 +261,9 @@ def run_b200(args, wl):
     from b200seg import _lib, ops
     from b200seg.train import TrainStep
     from oracle.synth import make_volume
-    from oracle import unet3d as ounet
 
     scale, kernel, classes, weight, (B, D, H, W) = wl
+    med = is_medformer(wl)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -233,9 +275,12 @@ def run_b200(args, wl):
     assert _lib.load().b200seg_check_device() == 0, "not an sm_100 device"
 
     def make_net():
-        n = b200seg.UNet(1, BASE, scale=scale, kernel_size=kernel, num_classes=classes, block="BasicBlock", norm="in")
-        shapes = ounet.unet_param_shapes(1, BASE, classes, kernel, "BasicBlock")
-        n.load_state_dict(ounet.make_state_dict(shapes, seed=7))
+        if med:
+            n = b200seg.MedFormer(1, classes, BASE, conv_block="BasicBlock", expansion=4, attn_drop=0, proj_drop=0,
+                                  proj_type="depthwise", norm="in", act="relu", **wl[0])
+        else:
+            n = b200seg.UNet(1, BASE, scale=scale, kernel_size=kernel, num_classes=classes, block="BasicBlock", norm="in")
+        n.load_state_dict(oracle_state(wl))
         return n.to(dev)
     net, ema = make_net(), make_net()
     if world > 1:
@@ -243,7 +288,7 @@ def run_b200(args, wl):
         net = DDP(net, device_ids=[local], find_unused_parameters=True)      # train_ddp.py:353
     for p in ema.parameters():
         p.requires_grad_(False)                                             # train_ddp.py:360-361
-    ts = TrainStep(net, ema, ce_weight=torch.tensor(weight), amp=True)
+    ts = TrainStep(net, ema, ce_weight=torch.tensor(weight), amp=True, aux_weight=AUX_WEIGHT if med else None)
 
     img_h, lab_h = make_volume(B, D, H, W, classes, seed=2023 + rank)
     img_h, lab_h = img_h.pin_memory(), lab_h.pin_memory()
@@ -287,10 +332,10 @@ def run_b200(args, wl):
     ms_e2e = timed(e2e_step, args.steps)
     peak_mem = torch.cuda.max_memory_allocated() / 2**30
 
-    out = {"metric": METRIC, "value": world * vox * args.steps / (ms / 1e3), "unit": "voxels/s", "n_gpus": world,
+    out = {"metric": metric_of(wl), "value": world * vox * args.steps / (ms / 1e3), "unit": "voxels/s", "n_gpus": world,
            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-           "config": {"workload": args.workload, "model": "ResUNet-3D base32 BasicBlock IN (reference UNet(1,32,...,block='BasicBlock',norm='in'))",
+           "config": {"workload": args.workload, "model": model_name(wl),
                       "per_gpu_batch": B, "volume": [D, H, W], "classes": classes, "parallelism": "dp%d" % world,
                       "amp": "autocast fp16 + GradScaler", "optimizer": "AdamW(fused)+EMA",
                       "l2": "working set (%.1f GiB activations/step) >> 126 MB L2, no explicit flush" % peak_mem},
@@ -300,7 +345,11 @@ def run_b200(args, wl):
                    "ms_per_step": ms_e2e / args.steps},
            "gpu_launches": launches, "peak_mem_gib": peak_mem}
 
-    if rank == 0:
+    if rank == 0 and med:
+        out["config"]["algorithmic_gflop_per_step"] = 2128.0      # 3*709.5 - 0.5 (conv + bmm + mm)
+        out["achieved_tflops_step"] = 2128.0e9 / (ms / args.steps / 1e3) / 1e12
+        out["roofline"] = biattn_roofline(torch, ops, _lib, dev, B)
+    if rank == 0 and not med:
         # ---- roofline of the dominant kernel: conv3d forward on the costliest layer shape
         L = conv_layers(scale, kernel, classes, B, D, H, W)
         fl_step = 3 * conv_flops(L, B) - conv_flops(L[:1], B)
@@ -348,12 +397,13 @@ def run_b200(args, wl):
                            "kernel": "conv3d_fwd[%s] %d->%d k%s @%s (IN+ReLU loader, IN-sums epilogue)" % ("tcgen05" if algo == 2 else "direct", ci, co, list(k), list(d)),
                            "ms": kms, "step_frac_of_sustained_peak": out["achieved_tflops_step"] / peaks.get("bf16_tflops_sustained", 1400.0)}
         del x, wp
+    if rank == 0:
         # ---- CPU baseline: oracle port on the host cores, bounded sample
         if world == 1 and not args.no_cpu:
             cores = usable_cores()
             torch.set_num_threads(cores)
-            step = oracle_step_fn(scale, kernel, classes, weight)
-            dmin, rate = cpu_sample_shape(scale, 0, 0, step, classes)
+            step = oracle_step_fn(wl)
+            dmin, rate = cpu_sample_shape(wl, step)
             dd = dmin
             while dd * 2 <= D and (dd * 2) * H * W * 2 / rate <= 25.0:
                 dd *= 2
@@ -366,7 +416,7 @@ def run_b200(args, wl):
         # ---- the bar to beat: the same algorithm through stock PyTorch + cuDNN on this GPU (AMP)
         if world == 1 and not args.no_cudnn:
             try:
-                out["torch_cudnn_same_gpu"] = cudnn_baseline(scale, kernel, classes, weight, img, lab, args.steps)
+                out["torch_cudnn_same_gpu"] = cudnn_baseline(wl, img, lab, args.steps)
             except Exception as e:       # noqa
                 out["torch_cudnn_same_gpu"] = {"error": str(e)[:200]}
         print(json.dumps(out), flush=True)
@@ -374,23 +424,52 @@ def run_b200(args, wl):
         dist.destroy_process_group()
 
 
-def cudnn_baseline(scale, kernel, classes, weight, img, lab, steps):
+def biattn_roofline(torch, ops, _lib, dev, B):
+    """HBM roofline of the B-MHA forward at MedFormer's largest attention level (down2/up2: N = 96*24*24 voxels,
+    4 heads x 32): algorithmic bytes = read Q_f,V_f + write O_f = 3*B*N*inner*2."""
+    heads, N = 4, 96 * 24 * 24
+    inner = 32 * heads
+    f = torch.randn(B, 96, 24, 24, 2 * inner, device=dev).half()
+    m = torch.randn(B, 3, 3, 3, 2 * inner, device=dev).half()
+    for _ in range(3):
+        ops.biattn_fwd(f, m, heads)
+    torch.cuda.synchronize()
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ops.biattn_fwd(f, m, heads)
+    e1.record()
+    torch.cuda.synchronize()
+    kms = e0.elapsed_time(e1) / reps
+    nbytes = 3.0 * B * N * inner * 2
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 7700.0)
+    ach = nbytes / (kms / 1e3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 7.7 TB/s",
+            "kernel": "biattn_fwd N=%d heads=%d dim_head=32 M=27 (B-MHA core, both softmax directions)" % (N, heads),
+            "ms": kms}
+
+
+def cudnn_baseline(wl, img, lab, steps):
     """Stock PyTorch (+cuDNN) evaluation of the reference's algorithm on the same GPU, AMP fp16, same step."""
     import torch
-    from oracle import losses as olosses
-    from oracle import unet3d as ounet
     dev = img.device
-    shapes = ounet.unet_param_shapes(1, BASE, classes, kernel, "BasicBlock")
-    sd = {k: v.to(dev).requires_grad_(True) for k, v in ounet.make_state_dict(shapes, seed=7).items()}
+    sd = {k: v.to(dev).requires_grad_(True) for k, v in oracle_state(wl).items()}
     ema = [v.detach().clone() for v in sd.values()]
     opt = torch.optim.AdamW(list(sd.values()), lr=1e-3, betas=(0.9, 0.999), weight_decay=0.05, eps=1e-5, fused=True)
     scaler = torch.amp.GradScaler("cuda")
-    w = torch.tensor(weight, device=dev)
+    w = torch.tensor(wl[3], device=dev)
 
     def step():
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.float16):
-            loss = olosses.total_loss(ounet.unet_forward(sd, img, scale, kernel, "BasicBlock"), lab, w)
+            loss = oracle_loss(wl, sd, img, lab, w)
         scaler.scale(loss).backward()
         scaler.step(opt)
         scaler.update()

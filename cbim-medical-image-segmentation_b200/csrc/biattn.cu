@@ -118,24 +118,32 @@ biattn_fwd_kernel(BiArgs a) {
   }
 }
 
-// merge the per-block column partials: map_out[j][:] and the {max, sum} the backward needs
+// merge the per-block column partials: map_out[j][:] and the {max, sum} the backward needs.
+// grid (M, heads, B), 128 threads = 4 partitions of the block axis x 32 head channels, online-softmax combine.
 template <typename T>
 __global__ void biattn_fwd_merge_kernel(BiArgs a, int nblk) {
-  const int h = blockIdx.x, b = blockIdx.y, M = a.M, heads = a.heads;
-  const float* pb = a.partial + (((int64_t)b * heads + h) * nblk) * M * (2 + DH);
-  for (int o = threadIdx.x; o < M * DH; o += blockDim.x) {
-    const int j = o / DH, d = o % DH;
-    float gmax = -INFINITY;
-    for (int k = 0; k < nblk; ++k) gmax = fmaxf(gmax, pb[((int64_t)k * M + j) * (2 + DH)]);
-    float sum = 0.f, acc = 0.f;
-    for (int k = 0; k < nblk; ++k) {
-      const float* q = pb + ((int64_t)k * M + j) * (2 + DH);
-      const float sc = __expf(q[0] - gmax);
-      sum = fmaf(q[1], sc, sum);
-      acc = fmaf(q[2 + d], sc, acc);
-    }
-    Elem<T>::st((T*)a.mo + ((int64_t)b * M + j) * a.mo_ld + a.mo_coff + d * heads + h, acc / sum);
-    if (d == 0) { float* cs = a.colstat + (((int64_t)b * heads + h) * M + j) * 2; cs[0] = gmax; cs[1] = sum; }
+  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z, M = a.M, heads = a.heads;
+  const int d = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const float* pb = a.partial + ((((int64_t)b * heads + h) * nblk) * M + j) * (2 + DH);
+  float m = -INFINITY, sum = 0.f, acc = 0.f;
+  for (int k = part; k < nblk; k += 4) {
+    const float* q = pb + (int64_t)k * M * (2 + DH);
+    const float mk = q[0];
+    if (mk > m) { const float sc = __expf(m - mk); sum *= sc; acc *= sc; m = mk; }
+    const float e = __expf(mk - m);
+    sum = fmaf(q[1], e, sum); acc = fmaf(q[2 + d], e, acc);
+  }
+  __shared__ float s_m[4], s_s[4], s_a[4][DH];
+  if (d == 0) { s_m[part] = m; s_s[part] = sum; }
+  s_a[part][d] = acc;
+  __syncthreads();
+  if (part == 0) {
+    const float gm = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+    float gs = 0.f, ga = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { const float e = __expf(s_m[p] - gm); gs = fmaf(s_s[p], e, gs); ga = fmaf(s_a[p][d], e, ga); }
+    Elem<T>::st((T*)a.mo + ((int64_t)b * M + j) * a.mo_ld + a.mo_coff + d * heads + h, ga / gs);
+    if (d == 0) { float* cs = a.colstat + (((int64_t)b * heads + h) * M + j) * 2; cs[0] = gm; cs[1] = gs; }
   }
 }
 
@@ -264,15 +272,20 @@ biattn_bwd_kernel(BiArgs a) {
 
 template <typename T>
 __global__ void biattn_bwd_merge_kernel(BiArgs a, int nblk) {
-  const int h = blockIdx.x, b = blockIdx.y, M = a.M, heads = a.heads;
-  const float* pb = a.partial + (((int64_t)b * heads + h) * nblk) * M * (2 * DH);
-  for (int o = threadIdx.x; o < M * DH; o += blockDim.x) {
-    const int j = o / DH, d = o % DH;
-    float sq = 0.f, sv = 0.f;
-    for (int k = 0; k < nblk; ++k) { const float* q = pb + ((int64_t)k * M + j) * (2 * DH); sq += q[d]; sv += q[DH + d]; }
+  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z, M = a.M, heads = a.heads;
+  const int c = threadIdx.x & 63, part = threadIdx.x >> 6;            // 64 values (dq | dv) x 4 partitions
+  const float* pb = a.partial + ((((int64_t)b * heads + h) * nblk) * M + j) * (2 * DH);
+  float acc = 0.f;
+  for (int k = part; k < nblk; k += 4) acc += pb[(int64_t)k * M * (2 * DH) + c];
+  __shared__ float s_a[4][2 * DH];
+  s_a[part][c] = acc;
+  __syncthreads();
+  if (part == 0) {
+    const float v = s_a[0][c] + s_a[1][c] + s_a[2][c] + s_a[3][c];
+    const int d = c & 31;
     const int64_t off = ((int64_t)b * M + j) * a.dm_ld + d * heads + h;
-    Elem<T>::st((T*)a.dmq + off + a.dmq_coff, sq);
-    Elem<T>::st((T*)a.dmv + off + a.dmv_coff, sv);
+    if (c < DH) Elem<T>::st((T*)a.dmq + off + a.dmq_coff, v);
+    else Elem<T>::st((T*)a.dmv + off + a.dmv_coff, v);
   }
 }
 
@@ -311,11 +324,11 @@ extern "C" int b200seg_biattn_fwd(const void* fq, int fq_ld, int fq_coff, const 
   if (dtype == B200SEG_F16) {
     cudaFuncSetAttribute(biattn_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     biattn_fwd_kernel<__half><<<grid, kT, sm, st>>>(a);
-    biattn_fwd_merge_kernel<__half><<<dim3(heads, B), 256, 0, st>>>(a, nblk);
+    biattn_fwd_merge_kernel<__half><<<dim3(M, heads, B), 128, 0, st>>>(a, nblk);
   } else {
     cudaFuncSetAttribute(biattn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     biattn_fwd_kernel<float><<<grid, kT, sm, st>>>(a);
-    biattn_fwd_merge_kernel<float><<<dim3(heads, B), 256, 0, st>>>(a, nblk);
+    biattn_fwd_merge_kernel<float><<<dim3(M, heads, B), 128, 0, st>>>(a, nblk);
   }
   B200_CHECK_LAUNCH("biattn_fwd");
   return B200SEG_OK;
@@ -347,11 +360,11 @@ extern "C" int b200seg_biattn_bwd(const void* fq, int fq_ld, int fq_coff, const 
   if (dtype == B200SEG_F16) {
     cudaFuncSetAttribute(biattn_bwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     biattn_bwd_kernel<__half><<<grid, kT, sm, st>>>(a);
-    biattn_bwd_merge_kernel<__half><<<dim3(heads, B), 256, 0, st>>>(a, nblk);
+    biattn_bwd_merge_kernel<__half><<<dim3(M, heads, B), 256, 0, st>>>(a, nblk);
   } else {
     cudaFuncSetAttribute(biattn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     biattn_bwd_kernel<float><<<grid, kT, sm, st>>>(a);
-    biattn_bwd_merge_kernel<float><<<dim3(heads, B), 256, 0, st>>>(a, nblk);
+    biattn_bwd_merge_kernel<float><<<dim3(M, heads, B), 256, 0, st>>>(a, nblk);
   }
   B200_CHECK_LAUNCH("biattn_bwd");
   return B200SEG_OK;

@@ -22,8 +22,29 @@ struct DwArgs {
   int Ctot, c0;              // the launch covers channels [c0, c0+C) of a Ctot-channel layer (stats / weight rows)
 };
 
+// 8 channels as loaded (no conversion yet) + validity, so a whole row of loads can be issued back to back
+template <typename T> struct Raw;
+template <> struct Raw<__half> {
+  uint4 u; bool ok;
+  __device__ __forceinline__ void load(const __half* p, bool valid) { ok = valid; u = valid ? *reinterpret_cast<const uint4*>(p) : make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+};
+template <> struct Raw<float> {
+  float4 a, b; bool ok;
+  __device__ __forceinline__ void load(const float* p, bool valid) {
+    ok = valid;
+    a = valid ? *reinterpret_cast<const float4*>(p) : make_float4(0, 0, 0, 0);
+    b = valid ? *reinterpret_cast<const float4*>(p + 4) : make_float4(0, 0, 0, 0);
+  }
+  __device__ __forceinline__ void get(float (&v)[8]) const { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+};
+
 template <typename T>
-__global__ void dwconv_fwd_kernel(DwArgs a) {
+__global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
   extern __shared__ float sm[];
   const int C = a.C, taps = a.kd * a.kh * a.kw;
   float* s_w = sm;                         // [taps][C]
@@ -47,9 +68,11 @@ __global__ void dwconv_fwd_kernel(DwArgs a) {
   const int cg = tid % ncg;                // blockDim.x and the grid stride are multiples of ncg
   const int pd = a.kd >> 1, ph = a.kh >> 1, pw = a.kw >> 1;
   const bool norm = a.x_stats != nullptr, relu = a.act == 1;
-  float sc[8], sh[8], tsum[8], tsq[8];
+  const float* sc = s_scale + cg * 8;     // read from shared memory at the use site: keeps 16 registers free
+  const float* sh = s_shift + cg * 8;
+  float tsum[8], tsq[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) { sc[c] = s_scale[cg * 8 + c]; sh[c] = s_shift[cg * 8 + c]; tsum[c] = 0.f; tsq[c] = 0.f; }
+  for (int c = 0; c < 8; ++c) { tsum[c] = 0.f; tsq[c] = 0.f; }
   const int64_t items = (int64_t)a.D * a.H * WR * ncg;
   const T* xb = (const T*)a.x + (int64_t)b * a.D * a.H * a.W * a.x_ld + a.x_coff + cg * 8;
   T* yb = (T*)a.y + (int64_t)b * a.D * a.H * a.W * a.y_ld + a.y_coff + cg * 8;
@@ -71,17 +94,31 @@ __global__ void dwconv_fwd_kernel(DwArgs a) {
         if (ih < 0 || ih >= a.H) continue;
         const T* row = xb + ((int64_t)id * a.H + ih) * a.W * a.x_ld;
         const float* wrow = s_w + (zd * a.kh + zh) * a.kw * C + cg * 8;
-        float wt[MAXK][8];
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) wt[k][c] = (k < a.kw) ? wrow[k * C + c] : 0.f;
+        // all loads of the row first (independent, in flight together), then the arithmetic
+        Raw<T> raw[RUN + MAXK - 1];
 #pragma unroll
         for (int j = 0; j < RUN + MAXK - 1; ++j) {            // input column w0 - pw + j
           const int iw = w0 - pw + j;
-          if (j >= RUN + a.kw - 1 || iw < 0 || iw >= a.W) continue;
+          const bool ok = (j < RUN + a.kw - 1) && iw >= 0 && iw < a.W;
+          raw[j].load(row + (int64_t)(ok ? iw : w0) * a.x_ld, ok);
+        }
+        float wt[MAXK][8];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) {
+          if (k < a.kw) {
+            const float4 w0v = *reinterpret_cast<const float4*>(wrow + k * C), w1v = *reinterpret_cast<const float4*>(wrow + k * C + 4);
+            wt[k][0] = w0v.x; wt[k][1] = w0v.y; wt[k][2] = w0v.z; wt[k][3] = w0v.w;
+            wt[k][4] = w1v.x; wt[k][5] = w1v.y; wt[k][6] = w1v.z; wt[k][7] = w1v.w;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) wt[k][c] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < RUN + MAXK - 1; ++j) {
+          if (!raw[j].ok) continue;
           float v[8];
-          ld8<T>(row + (int64_t)iw * a.x_ld, v);
+          raw[j].get(v);
           if (norm) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) { v[c] = fmaf(v[c], sc[c], sh[c]); if (relu) v[c] = fmaxf(v[c], 0.f); v[c] = Elem<T>::round(v[c]); }
@@ -125,7 +162,7 @@ __global__ void dwconv_fwd_kernel(DwArgs a) {
 
 // dw[tap][c] += sum_{b,voxel} dy[voxel][c] * a[voxel + tap][c];  grid.y = B * kd (one depth tap per block row)
 template <typename T>
-__global__ void dwconv_wgrad_kernel(DwArgs a) {
+__global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
   extern __shared__ float sm[];
   const int C = a.C;
   float* s_scale = sm;                     // [C]
@@ -144,9 +181,8 @@ __global__ void dwconv_wgrad_kernel(DwArgs a) {
   const int ncg = C >> 3, cg = tid % ncg;
   const int pd = a.kd >> 1, ph = a.kh >> 1, pw = a.kw >> 1;
   const bool norm = a.x_stats != nullptr, relu = a.act == 1;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) { sc[c] = s_scale[cg * 8 + c]; sh[c] = s_shift[cg * 8 + c]; }
+  const float* sc = s_scale + cg * 8;
+  const float* sh = s_shift + cg * 8;
   float acc[MAXK * MAXK][8];
 #pragma unroll
   for (int t = 0; t < MAXK * MAXK; ++t)
@@ -161,28 +197,33 @@ __global__ void dwconv_wgrad_kernel(DwArgs a) {
     const int h = (int)(r % a.H), d = (int)(r / a.H);
     const int id = d + zd - pd;
     if (id < 0 || id >= a.D) continue;
-    float g[8];
-    ld8<T>(gb + (((int64_t)d * a.H + h) * a.W + w) * a.dy_ld, g);
+    Raw<T> rg, rx[MAXK * MAXK];
+    rg.load(gb + (((int64_t)d * a.H + h) * a.W + w) * a.dy_ld, true);
 #pragma unroll
     for (int zh = 0; zh < MAXK; ++zh) {
-      const int ih = h + zh - ph;
-      if (zh >= a.kh || ih < 0 || ih >= a.H) continue;
 #pragma unroll
       for (int zw = 0; zw < MAXK; ++zw) {
-        const int iw = w + zw - pw;
-        if (zw >= a.kw || iw < 0 || iw >= a.W) continue;
-        float v[8];
-        ld8<T>(xb + (((int64_t)id * a.H + ih) * a.W + iw) * a.x_ld, v);
-        if (norm) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) { v[c] = fmaf(v[c], sc[c], sh[c]); if (relu) v[c] = fmaxf(v[c], 0.f); v[c] = Elem<T>::round(v[c]); }
-        } else if (relu) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[zh * MAXK + zw][c] = fmaf(g[c], v[c], acc[zh * MAXK + zw][c]);
+        const int ih = h + zh - ph, iw = w + zw - pw;
+        const bool ok = zh < a.kh && zw < a.kw && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
+        rx[zh * MAXK + zw].load(xb + (((int64_t)id * a.H + (ok ? ih : h)) * a.W + (ok ? iw : w)) * a.x_ld, ok);
       }
+    }
+    float g[8];
+    rg.get(g);
+#pragma unroll
+    for (int t = 0; t < MAXK * MAXK; ++t) {
+      if (!rx[t].ok) continue;
+      float v[8];
+      rx[t].get(v);
+      if (norm) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { v[c] = fmaf(v[c], sc[c], sh[c]); if (relu) v[c] = fmaxf(v[c], 0.f); v[c] = Elem<T>::round(v[c]); }
+      } else if (relu) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[t][c] = fmaf(g[c], v[c], acc[t][c]);
     }
   }
 #pragma unroll
@@ -258,6 +299,7 @@ extern "C" int b200seg_dwconv3d_wgrad(const void* x, int x_ld, int x_coff, const
   if (rc) return rc;
   if (!x || !dy || !dw || dy_ld % 8 || dy_coff % 8) return B200SEG_EINVAL;
   const int ncg = C / 8, threads = pick_threads(ncg);
+  if (threads > 256) return B200SEG_EUNSUPPORTED;
   const int64_t items = (int64_t)D * H * W * ncg;
   int gx = (int)((items + threads - 1) / threads);
   const int cap = (B200SEG_NUM_SMS * 4 + B * kd - 1) / (B * kd);

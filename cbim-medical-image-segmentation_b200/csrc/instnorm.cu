@@ -209,12 +209,16 @@ inline bool vec_ok(const void* p, int ld, int coff, int C, int esz) {
   return (C % 8 == 0) && (ld % 8 == 0) && (coff % 8 == 0) && (C / 8 <= kThreads) &&
          ((reinterpret_cast<uintptr_t>(p) % 16) == 0) && esz > 0;
 }
-inline int64_t pick_vpb(int64_t V, int B) {
-  // aim for >= ~6 blocks per SM in total
+inline int64_t pick_vpb(int64_t V, int B, int C) {
+  // aim for >= ~6 blocks per SM in total, but keep >= 8 passes per block: a pass covers kThreads/(C/8) voxels,
+  // so wide-channel / few-voxel tensors (MedFormer's 1280 x 864) still spread over the whole GPU
   int64_t want = (int64_t)B200SEG_NUM_SMS * 6 / (B > 0 ? B : 1);
   if (want < 1) want = 1;
   int64_t vpb = (V + want - 1) / want;
-  if (vpb < 512) vpb = 512;
+  int cpv = C % 8 ? C : C / 8;
+  int64_t vpp = kThreads / (cpv > 0 ? cpv : 1);
+  if (vpp < 1) vpp = 1;
+  if (vpb < 8 * vpp) vpb = 8 * vpp;
   return vpb;
 }
 
@@ -233,7 +237,7 @@ extern "C" int b200seg_instnorm_stats(const void* x, int dtype, int ld, int coff
                                       double* stats, void* stream) {
   if (!x || !stats || B <= 0 || V <= 0 || C <= 0 || C > 4096) return B200SEG_EINVAL;
   cudaStream_t st = as_stream(stream);
-  int64_t vpb = pick_vpb(V, B);
+  int64_t vpb = pick_vpb(V, B, C);
   dim3 grid(ceil_div(V, vpb), B);
   bool vok = vec_ok(x, ld, coff, C, 1);
   if (!vok && C > kThreads) return B200SEG_EUNSUPPORTED;
@@ -250,7 +254,7 @@ extern "C" int b200seg_instnorm_apply(const void* x, int dtype, int x_ld, int x_
                                       int C, void* stream) {
   if (!x || !y || !stats || B <= 0 || V <= 0 || C <= 0) return B200SEG_EINVAL;
   cudaStream_t st = as_stream(stream);
-  int64_t vpb = pick_vpb(V, B);
+  int64_t vpb = pick_vpb(V, B, C);
   dim3 grid(ceil_div(V, vpb), B);
   bool vok = vec_ok(x, x_ld, x_coff, C, 1) && vec_ok(y, y_ld, y_coff, C, 1);
   if (!vok && C > kThreads) return B200SEG_EUNSUPPORTED;
@@ -267,7 +271,7 @@ extern "C" int b200seg_instnorm_bwd_reduce(const void* dy, int dy_ld, int dy_cof
                                            int C, void* stream) {
   if (!dy || !x || !stats || !g || !bstats || B <= 0 || V <= 0 || C <= 0) return B200SEG_EINVAL;
   cudaStream_t st = as_stream(stream);
-  int64_t vpb = pick_vpb(V, B);
+  int64_t vpb = pick_vpb(V, B, C);
   dim3 grid(ceil_div(V, vpb), B);
   bool vok = vec_ok(dy, dy_ld, dy_coff, C, 1) && vec_ok(x, x_ld, x_coff, C, 1) && vec_ok(g, g_ld, g_coff, C, 1);
   if (!vok && C > kThreads) return B200SEG_EUNSUPPORTED;
@@ -287,7 +291,7 @@ extern "C" int b200seg_instnorm_bwd_apply(const void* g, int g_ld, int g_coff, c
                                           int C, void* stream) {
   if (!g || !x || !stats || !bstats || !dx || B <= 0 || V <= 0 || C <= 0) return B200SEG_EINVAL;
   cudaStream_t st = as_stream(stream);
-  int64_t vpb = pick_vpb(V, B);
+  int64_t vpb = pick_vpb(V, B, C);
   dim3 grid(ceil_div(V, vpb), B);
   bool vok = vec_ok(g, g_ld, g_coff, C, 1) && vec_ok(x, x_ld, x_coff, C, 1) && vec_ok(dx, dx_ld, dx_coff, C, 1) &&
              (!add || vec_ok(add, add_ld, add_coff, C, 1));
@@ -303,7 +307,7 @@ extern "C" int b200seg_instnorm_bwd_apply(const void* g, int g_ld, int g_coff, c
 template <typename TX, typename TY>
 static int copy_t(const void* x, int x_ld, int x_coff, void* y, int y_ld, int y_coff, int accumulate,
                   int64_t nvox, int C, cudaStream_t st) {
-  int64_t vpb = pick_vpb(nvox, 1);
+  int64_t vpb = pick_vpb(nvox, 1, C);
   dim3 grid(ceil_div(nvox, vpb), 1);
   bool vok = vec_ok(x, x_ld, x_coff, C, 1) && vec_ok(y, y_ld, y_coff, C, 1);
   if (!vok && C > kThreads) return B200SEG_EUNSUPPORTED;

@@ -91,25 +91,23 @@ __global__ void __launch_bounds__(MG_T) mapgen_fwd_kernel(MgArgs a) {
   }
 }
 
+// grid (K, B): threads stride the channels; every thread runs the online max/sum over the blocks itself
+// (reads of q[0], q[1] are warp-broadcasts), so no serial prologue.
 template <typename T>
 __global__ void mapgen_merge_kernel(MgArgs a, int nblk) {
   const int k = blockIdx.x, b = blockIdx.y, K = a.K, C = a.C;
-  const float* pb = a.partial + ((int64_t)b * nblk * K) * (2 + C);
-  __shared__ float s_g[2];
-  if (threadIdx.x == 0) {
-    float gmax = -INFINITY;
-    for (int n = 0; n < nblk; ++n) gmax = fmaxf(gmax, pb[((int64_t)n * K + k) * (2 + C)]);
-    float sum = 0.f;
-    for (int n = 0; n < nblk; ++n) { const float* q = pb + ((int64_t)n * K + k) * (2 + C); sum = fmaf(q[1], __expf(q[0] - gmax), sum); }
-    s_g[0] = gmax; s_g[1] = sum;
-    a.colstat[((int64_t)b * K + k) * 2] = gmax; a.colstat[((int64_t)b * K + k) * 2 + 1] = sum;
-  }
-  __syncthreads();
-  const float gmax = s_g[0], inv = 1.f / s_g[1];
+  const float* pb = a.partial + ((int64_t)b * nblk * K + k) * (2 + C);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
-    for (int n = 0; n < nblk; ++n) { const float* q = pb + ((int64_t)n * K + k) * (2 + C); acc = fmaf(q[2 + c], __expf(q[0] - gmax), acc); }
-    Elem<T>::st((T*)a.map + ((int64_t)b * K + k) * a.map_ld + c, acc * inv);
+    float m = -INFINITY, sum = 0.f, acc = 0.f;
+    for (int n = 0; n < nblk; ++n) {
+      const float* q = pb + (int64_t)n * K * (2 + C);
+      const float mk = q[0];
+      if (mk > m) { const float sc = __expf(m - mk); sum *= sc; acc *= sc; m = mk; }
+      const float e = __expf(mk - m);
+      sum = fmaf(q[1], e, sum); acc = fmaf(q[2 + c], e, acc);
+    }
+    Elem<T>::st((T*)a.map + ((int64_t)b * K + k) * a.map_ld + c, acc / sum);
+    if (c == 0) { a.colstat[((int64_t)b * K + k) * 2] = m; a.colstat[((int64_t)b * K + k) * 2 + 1] = sum; }
   }
 }
 
@@ -166,50 +164,87 @@ struct SeArgs {
   int B, C, R;
 };
 
+// forward: every block recomputes the R hidden units (R*C MACs, cheap) and produces its slice of the C gates;
+// warps walk weight rows so the loads are coalesced.
 __global__ void se_gate_fwd_kernel(SeArgs a) {
   extern __shared__ float sm[];
   float* s_mean = sm; float* s_h = sm + a.C;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int cper = (a.C + gridDim.x - 1) / gridDim.x, c0 = blockIdx.x * cper, c1 = min(a.C, c0 + cper);
   for (int b = 0; b < a.B; ++b) {
-    for (int c = threadIdx.x; c < a.C; c += blockDim.x) { const float m = (float)(a.stats[((int64_t)b * a.C + c) * 2] / a.n); s_mean[c] = m; a.mean[b * a.C + c] = m; }
-    __syncthreads();
-    for (int r = threadIdx.x >> 5; r < a.R; r += blockDim.x >> 5) {
-      float acc = 0.f;
-      for (int c = threadIdx.x & 31; c < a.C; c += 32) acc = fmaf(a.w1[(int64_t)r * a.C + c], s_mean[c], acc);
-      acc = warp_sum(acc);
-      if ((threadIdx.x & 31) == 0) { const float h = fmaxf(acc + a.b1[r], 0.f); s_h[r] = h; a.hidden[b * a.R + r] = h; }
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      const float m = (float)(a.stats[((int64_t)b * a.C + c) * 2] / a.n);
+      s_mean[c] = m;
+      if (blockIdx.x == 0) a.mean[b * a.C + c] = m;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-      float acc = a.b2[c];
-      for (int r = 0; r < a.R; ++r) acc = fmaf(a.w2[(int64_t)c * a.R + r], s_h[r], acc);
-      a.gate[b * a.C + c] = 1.f / (1.f + __expf(-acc));
+    for (int r = wid; r < a.R; r += nw) {
+      float acc = 0.f;
+      for (int c = lane; c < a.C; c += 32) acc = fmaf(a.w1[(int64_t)r * a.C + c], s_mean[c], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) { const float h = fmaxf(acc + a.b1[r], 0.f); s_h[r] = h; if (blockIdx.x == 0) a.hidden[b * a.R + r] = h; }
+    }
+    __syncthreads();
+    for (int c = c0 + wid; c < c1; c += nw) {
+      float acc = 0.f;
+      for (int r = lane; r < a.R; r += 32) acc = fmaf(a.w2[(int64_t)c * a.R + r], s_h[r], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) a.gate[b * a.C + c] = 1.f / (1.f + __expf(-(acc + a.b2[c])));
     }
     __syncthreads();
   }
 }
 
+// backward: every block recomputes dz2 (C) and dz1 (R, a C x R column reduction) and owns a slice of the C axis
+// for dw2/db2/dw1/dmean; block 0 also writes db1.  Each output element is touched by exactly one thread.
 __global__ void se_gate_bwd_kernel(SeArgs a) {
   extern __shared__ float sm[];
-  float* s_dz2 = sm; float* s_dz1 = sm + a.C;     // [C], [R]
+  float* s_dz2 = sm; float* s_dz1 = sm + a.C; float* s_h = s_dz1 + a.R;     // [C], [R], [R]
+  const int tid = threadIdx.x;
+  const int cper = (a.C + gridDim.x - 1) / gridDim.x, c0 = blockIdx.x * cper, c1 = min(a.C, c0 + cper);
   for (int b = 0; b < a.B; ++b) {
-    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    for (int c = tid; c < a.C; c += blockDim.x) {
       const float s = a.gate[b * a.C + c];
-      const float dz = a.dgate[b * a.C + c] * s * (1.f - s);
-      s_dz2[c] = dz; a.db2[c] += dz;
-      for (int r = 0; r < a.R; ++r) a.dw2[(int64_t)c * a.R + r] += dz * a.hidden[b * a.R + r];
+      s_dz2[c] = a.dgate[b * a.C + c] * s * (1.f - s);
+    }
+    for (int r = tid; r < a.R; r += blockDim.x) { s_dz1[r] = 0.f; s_h[r] = a.hidden[b * a.R + r]; }
+    __syncthreads();
+    // dh[r] = sum_c w2[c][r] dz2[c]: threads (r, part) stride the c axis, coalesced along r
+    {
+      const int parts = max(1, (int)blockDim.x / a.R), part = tid / a.R, r = tid % a.R;
+      if (part < parts) {
+        float dh = 0.f;
+        for (int c = part; c < a.C; c += parts) dh = fmaf(a.w2[(int64_t)c * a.R + r], s_dz2[c], dh);
+        atomicAdd(&s_dz1[r], dh);
+      }
+      if (blockDim.x < a.R) {                    // R wider than the block: remaining rows serially per thread
+        for (int r2 = tid + blockDim.x; r2 < a.R; r2 += blockDim.x) {
+          float dh = 0.f;
+          for (int c = 0; c < a.C; ++c) dh = fmaf(a.w2[(int64_t)c * a.R + r2], s_dz2[c], dh);
+          s_dz1[r2] = dh;
+        }
+      }
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < a.R; r += blockDim.x) {
-      float dh = 0.f;
-      for (int c = 0; c < a.C; ++c) dh = fmaf(a.w2[(int64_t)c * a.R + r], s_dz2[c], dh);
-      const float dz1 = a.hidden[b * a.R + r] > 0.f ? dh : 0.f;
-      s_dz1[r] = dz1; a.db1[r] += dz1;
+    for (int r = tid; r < a.R; r += blockDim.x) {
+      const float dz1 = s_h[r] > 0.f ? s_dz1[r] : 0.f;
+      s_dz1[r] = dz1;
+      if (blockIdx.x == 0) a.db1[r] += dz1;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    // slice-owned outputs
+    for (int o = tid; o < (c1 - c0) * a.R; o += blockDim.x) {
+      const int c = c0 + o / a.R, r = o % a.R;
+      a.dw2[(int64_t)c * a.R + r] += s_dz2[c] * s_h[r];
+    }
+    for (int o = tid; o < (c1 - c0) * a.R; o += blockDim.x) {      // dw1[r][c], c fastest for coalescing
+      const int r = o / (c1 - c0), c = c0 + o % (c1 - c0);
+      a.dw1[(int64_t)r * a.C + c] += s_dz1[r] * a.mean[b * a.C + c];
+    }
+    for (int c = c0 + tid; c < c1; c += blockDim.x) {
+      a.db2[c] += s_dz2[c];
       float dm = 0.f;
-      const float m = a.mean[b * a.C + c];
-      for (int r = 0; r < a.R; ++r) { dm = fmaf(a.w1[(int64_t)r * a.C + c], s_dz1[r], dm); a.dw1[(int64_t)r * a.C + c] += s_dz1[r] * m; }
+      for (int r = 0; r < a.R; ++r) dm = fmaf(a.w1[(int64_t)r * a.C + c], s_dz1[r], dm);
       a.dmean[b * a.C + c] = dm;
     }
     __syncthreads();
@@ -466,7 +501,7 @@ extern "C" int b200seg_se_gate_fwd(const double* stats, int64_t nvox, const floa
   SeArgs a; memset(&a, 0, sizeof(a));
   a.stats = stats; a.n = (double)nvox; a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.gate = gate; a.hidden = hidden; a.mean = mean;
   a.B = B; a.C = C; a.R = R;
-  se_gate_fwd_kernel<<<1, 1024, sizeof(float) * (C + R), as_stream(stream)>>>(a);
+  se_gate_fwd_kernel<<<(C + 63) / 64 < 148 ? (C + 63) / 64 : 148, 512, sizeof(float) * (C + R), as_stream(stream)>>>(a);
   B200_CHECK_LAUNCH("se_gate_fwd");
   return B200SEG_OK;
 }
@@ -478,7 +513,7 @@ extern "C" int b200seg_se_gate_bwd(const float* dgate, const float* gate, const 
   SeArgs a; memset(&a, 0, sizeof(a));
   a.dgate = dgate; a.gate = const_cast<float*>(gate); a.hidden = const_cast<float*>(hidden); a.mean = const_cast<float*>(mean);
   a.w1 = w1; a.w2 = w2; a.dw1 = dw1; a.db1 = db1; a.dw2 = dw2; a.db2 = db2; a.dmean = dmean; a.B = B; a.C = C; a.R = R;
-  se_gate_bwd_kernel<<<1, 1024, sizeof(float) * (C + R), as_stream(stream)>>>(a);
+  se_gate_bwd_kernel<<<(C + 31) / 32 < 148 ? (C + 31) / 32 : 148, 512, sizeof(float) * (C + 2 * R), as_stream(stream)>>>(a);
   B200_CHECK_LAUNCH("se_gate_bwd");
   return B200SEG_OK;
 }
