@@ -192,36 +192,38 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
   const T* xb = (const T*)a.x + (int64_t)b * a.D * a.H * a.W * a.x_ld + a.x_coff + cg * 8;
   const T* gb = (const T*)a.dy + (int64_t)b * a.D * a.H * a.W * a.dy_ld + a.dy_coff + cg * 8;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + tid; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+    // input-stationary: the thread owns one INPUT vector (normalised once) and meets the 9 output gradients
+    // of this depth tap that it contributes to:  dw[zd][zh][zw] += dy[id-zd+pd, ih-zh+ph, iw-zw+pw] * a[id,ih,iw]
     int64_t r = it / ncg;
-    const int w = (int)(r % a.W); r /= a.W;
-    const int h = (int)(r % a.H), d = (int)(r / a.H);
-    const int id = d + zd - pd;
-    if (id < 0 || id >= a.D) continue;
-    Raw<T> rg, rx[MAXK * MAXK];
-    rg.load(gb + (((int64_t)d * a.H + h) * a.W + w) * a.dy_ld, true);
+    const int iw = (int)(r % a.W); r /= a.W;
+    const int ih = (int)(r % a.H), id = (int)(r / a.H);
+    const int d = id - zd + pd;
+    if (d < 0 || d >= a.D) continue;
+    Raw<T> rx, rg[MAXK * MAXK];
+    rx.load(xb + (((int64_t)id * a.H + ih) * a.W + iw) * a.x_ld, true);
 #pragma unroll
     for (int zh = 0; zh < MAXK; ++zh) {
 #pragma unroll
       for (int zw = 0; zw < MAXK; ++zw) {
-        const int ih = h + zh - ph, iw = w + zw - pw;
-        const bool ok = zh < a.kh && zw < a.kw && ih >= 0 && ih < a.H && iw >= 0 && iw < a.W;
-        rx[zh * MAXK + zw].load(xb + (((int64_t)id * a.H + (ok ? ih : h)) * a.W + (ok ? iw : w)) * a.x_ld, ok);
+        const int h = ih - zh + ph, w = iw - zw + pw;
+        const bool ok = zh < a.kh && zw < a.kw && h >= 0 && h < a.H && w >= 0 && w < a.W;
+        rg[zh * MAXK + zw].load(gb + (((int64_t)d * a.H + (ok ? h : ih)) * a.W + (ok ? w : iw)) * a.dy_ld, ok);
       }
     }
-    float g[8];
-    rg.get(g);
+    float v[8];
+    rx.get(v);
+    if (norm) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { v[c] = fmaf(v[c], sc[c], sh[c]); if (relu) v[c] = fmaxf(v[c], 0.f); v[c] = Elem<T>::round(v[c]); }
+    } else if (relu) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
+    }
 #pragma unroll
     for (int t = 0; t < MAXK * MAXK; ++t) {
-      if (!rx[t].ok) continue;
-      float v[8];
-      rx[t].get(v);
-      if (norm) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) { v[c] = fmaf(v[c], sc[c], sh[c]); if (relu) v[c] = fmaxf(v[c], 0.f); v[c] = Elem<T>::round(v[c]); }
-      } else if (relu) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
-      }
+      if (!rg[t].ok) continue;
+      float g[8];
+      rg[t].get(g);
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[t][c] = fmaf(g[c], v[c], acc[t][c]);
     }

@@ -209,20 +209,22 @@ __global__ void se_gate_bwd_kernel(SeArgs a) {
     }
     for (int r = tid; r < a.R; r += blockDim.x) { s_dz1[r] = 0.f; s_h[r] = a.hidden[b * a.R + r]; }
     __syncthreads();
-    // dh[r] = sum_c w2[c][r] dz2[c]: threads (r, part) stride the c axis, coalesced along r
+    // dh[r] = sum_c w2[c][r] dz2[c]: a warp strides the c axis, its lanes hold up to 8 r values each (8 loads in
+    // flight per lane, coalesced along r); partials meet in shared memory
     {
-      const int parts = max(1, (int)blockDim.x / a.R), part = tid / a.R, r = tid % a.R;
-      if (part < parts) {
-        float dh = 0.f;
-        for (int c = part; c < a.C; c += parts) dh = fmaf(a.w2[(int64_t)c * a.R + r], s_dz2[c], dh);
-        atomicAdd(&s_dz1[r], dh);
-      }
-      if (blockDim.x < a.R) {                    // R wider than the block: remaining rows serially per thread
-        for (int r2 = tid + blockDim.x; r2 < a.R; r2 += blockDim.x) {
-          float dh = 0.f;
-          for (int c = 0; c < a.C; ++c) dh = fmaf(a.w2[(int64_t)c * a.R + r2], s_dz2[c], dh);
-          s_dz1[r2] = dh;
+      const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+      for (int rb = 0; rb < a.R; rb += 256) {
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+        for (int c = wid; c < a.C; c += nw) {
+          const float z = s_dz2[c];
+          const float* wr = a.w2 + (int64_t)c * a.R + rb + lane;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) if (rb + u * 32 + lane < a.R) acc[u] = fmaf(wr[u * 32], z, acc[u]);
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (rb + u * 32 + lane < a.R) atomicAdd(&s_dz1[rb + u * 32 + lane], acc[u]);
       }
     }
     __syncthreads();
@@ -241,12 +243,23 @@ __global__ void se_gate_bwd_kernel(SeArgs a) {
       const int r = o / (c1 - c0), c = c0 + o % (c1 - c0);
       a.dw1[(int64_t)r * a.C + c] += s_dz1[r] * a.mean[b * a.C + c];
     }
-    for (int c = c0 + tid; c < c1; c += blockDim.x) {
-      a.db2[c] += s_dz2[c];
-      float dm = 0.f;
-      for (int r = 0; r < a.R; ++r) dm = fmaf(a.w1[(int64_t)r * a.C + c], s_dz1[r], dm);
-      a.dmean[b * a.C + c] = dm;
+    for (int c = c0 + tid; c < c1; c += blockDim.x) a.db2[c] += s_dz2[c];
+    // dmean[c] = sum_r w1[r][c] dz1[r] for the slice: threads (c, r-part), combined through shared memory
+    __syncthreads();
+    float* s_dm = s_dz2;                       // dz2 is no longer needed in this batch iteration
+    const int ncs = c1 - c0;
+    for (int c = tid; c < ncs; c += blockDim.x) s_dm[c] = 0.f;
+    __syncthreads();
+    if (ncs > 0) {
+      const int parts = max(1, (int)blockDim.x / ncs), part = tid / ncs, cc = tid % ncs;
+      if (part < parts) {
+        float dm = 0.f;
+        for (int r = part; r < a.R; r += parts) dm = fmaf(a.w1[(int64_t)r * a.C + c0 + cc], s_dz1[r], dm);
+        atomicAdd(&s_dm[cc], dm);
+      }
     }
+    __syncthreads();
+    for (int c = tid; c < ncs; c += blockDim.x) a.dmean[b * a.C + c0 + c] = s_dm[c];
     __syncthreads();
   }
 }
