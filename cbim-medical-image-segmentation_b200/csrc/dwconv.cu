@@ -53,14 +53,15 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
   float* s_sum = s_shift + C;              // [C]
   float* s_sq = s_sum + C;                 // [C]
   const int b = blockIdx.y, tid = threadIdx.x;
+  const int c0 = blockIdx.z * C;            // this block's channel slice [c0, c0 + C) of the Ctot-channel layer
   const double nvox = (double)a.D * a.H * a.W;
   for (int o = tid; o < taps * C; o += blockDim.x) {
     const int t = o / C, c = o % C;
-    s_w[o] = a.w[(a.flip ? taps - 1 - t : t) * a.Ctot + a.c0 + c];
+    s_w[o] = a.w[(a.flip ? taps - 1 - t : t) * a.Ctot + c0 + c];
   }
   for (int c = tid; c < C; c += blockDim.x) {
     float mean = 0.f, rstd = 1.f;
-    if (a.x_stats) stats_to_mean_rstd(a.x_stats + ((int64_t)b * a.Ctot + a.c0 + c) * 2, nvox, a.eps, mean, rstd);
+    if (a.x_stats) stats_to_mean_rstd(a.x_stats + ((int64_t)b * a.Ctot + c0 + c) * 2, nvox, a.eps, mean, rstd);
     s_scale[c] = rstd; s_shift[c] = -mean * rstd; s_sum[c] = 0.f; s_sq[c] = 0.f;
   }
   __syncthreads();
@@ -74,8 +75,8 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
 #pragma unroll
   for (int c = 0; c < 8; ++c) { tsum[c] = 0.f; tsq[c] = 0.f; }
   const int64_t items = (int64_t)a.D * a.H * WR * ncg;
-  const T* xb = (const T*)a.x + (int64_t)b * a.D * a.H * a.W * a.x_ld + a.x_coff + cg * 8;
-  T* yb = (T*)a.y + (int64_t)b * a.D * a.H * a.W * a.y_ld + a.y_coff + cg * 8;
+  const T* xb = (const T*)a.x + (int64_t)b * a.D * a.H * a.W * a.x_ld + a.x_coff + c0 + cg * 8;
+  T* yb = (T*)a.y + (int64_t)b * a.D * a.H * a.W * a.y_ld + a.y_coff + c0 + cg * 8;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + tid; it < items; it += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = it / ncg;
     const int wr = (int)(r % WR); r /= WR;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
     for (int c = 0; c < 8; ++c) { atomicAdd(&s_sum[cg * 8 + c], tsum[c]); atomicAdd(&s_sq[cg * 8 + c], tsq[c]); }
     __syncthreads();
     for (int c = tid; c < C; c += blockDim.x) {
-      double* st = a.y_stats + ((int64_t)b * a.Ctot + a.c0 + c) * 2;
+      double* st = a.y_stats + ((int64_t)b * a.Ctot + c0 + c) * 2;
       atomicAdd(st, (double)s_sum[c]); atomicAdd(st + 1, (double)s_sq[c]);
     }
   }
@@ -169,11 +170,12 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
   float* s_shift = s_scale + C;
   float* s_acc = s_shift + C;              // [kh*kw][C]
   const int b = blockIdx.y / a.kd, zd = blockIdx.y % a.kd, tid = threadIdx.x;
+  const int c0 = blockIdx.z * C;
   const int thw = a.kh * a.kw;
   const double nvox = (double)a.D * a.H * a.W;
   for (int c = tid; c < C; c += blockDim.x) {
     float mean = 0.f, rstd = 1.f;
-    if (a.x_stats) stats_to_mean_rstd(a.x_stats + ((int64_t)b * C + c) * 2, nvox, a.eps, mean, rstd);
+    if (a.x_stats) stats_to_mean_rstd(a.x_stats + ((int64_t)b * a.Ctot + c0 + c) * 2, nvox, a.eps, mean, rstd);
     s_scale[c] = rstd; s_shift[c] = -mean * rstd;
   }
   for (int o = tid; o < thw * C; o += blockDim.x) s_acc[o] = 0.f;
@@ -189,8 +191,8 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
   const int64_t items = (int64_t)a.D * a.H * a.W * ncg;
-  const T* xb = (const T*)a.x + (int64_t)b * a.D * a.H * a.W * a.x_ld + a.x_coff + cg * 8;
-  const T* gb = (const T*)a.dy + (int64_t)b * a.D * a.H * a.W * a.dy_ld + a.dy_coff + cg * 8;
+  const T* xb = (const T*)a.x + (int64_t)b * a.D * a.H * a.W * a.x_ld + a.x_coff + c0 + cg * 8;
+  const T* gb = (const T*)a.dy + (int64_t)b * a.D * a.H * a.W * a.dy_ld + a.dy_coff + c0 + cg * 8;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + tid; it < items; it += (int64_t)gridDim.x * blockDim.x) {
     // input-stationary: the thread owns one INPUT vector (normalised once) and meets the 9 output gradients
     // of this depth tap that it contributes to:  dw[zd][zh][zw] += dy[id-zd+pd, ih-zh+ph, iw-zw+pw] * a[id,ih,iw]
@@ -237,7 +239,8 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
         for (int c = 0; c < 8; ++c) atomicAdd(&s_acc[(zh * a.kw + zw) * C + cg * 8 + c], acc[zh * MAXK + zw][c]);
       }
   __syncthreads();
-  for (int o = tid; o < thw * C; o += blockDim.x) atomicAdd(&a.dw[(int64_t)zd * thw * C + o], s_acc[o]);
+  for (int o = tid; o < thw * C; o += blockDim.x)
+    atomicAdd(&a.dw[((int64_t)zd * thw + o / C) * a.Ctot + c0 + o % C], s_acc[o]);
 }
 
 int check(const DwArgs& a, int dtype) {
@@ -248,6 +251,9 @@ int check(const DwArgs& a, int dtype) {
   if (a.act != 0 && a.act != 1) return B200SEG_EUNSUPPORTED;
   return B200SEG_OK;
 }
+
+// largest multiple-of-8 divisor of C not above 128
+int pick_chunk(int C) { for (int ch = 128; ch >= 8; ch -= 8) if (C % ch == 0) return ch; return C; }
 
 int pick_threads(int ncg) { int t = (256 / ncg) * ncg; return t > 0 ? t : ncg; }
 
@@ -265,26 +271,22 @@ extern "C" int b200seg_dwconv3d_fwd(const void* x, int x_ld, int x_coff, const d
   if (!x || !w || !y || y_ld % 8 || y_coff % 8) return B200SEG_EINVAL;
   cudaStream_t st = as_stream(stream);
   const int taps = kd * kh * kw;
-  // shared memory holds taps+4 floats per channel: wide layers (PatchMerging's 2048 merged channels) go in slices
-  int chunk = C;
-  while (sizeof(float) * (size_t)(taps + 4) * chunk > 160 * 1024) chunk = ((chunk / 2 + 7) / 8) * 8;
-  a.Ctot = C;
-  for (int c0 = 0; c0 < C; c0 += chunk) {
-    const int cc = (C - c0 < chunk) ? C - c0 : chunk;
-    a.C = cc; a.c0 = c0; a.x_coff = x_coff + c0; a.y_coff = y_coff + c0;
-    const int ncg = cc / 8, threads = pick_threads(ncg);
-    const int64_t items = (int64_t)D * H * ((W + RUN - 1) / RUN) * ncg;
-    int gx = (int)((items + threads - 1) / threads);
-    const int cap = (B200SEG_NUM_SMS * 8 + B - 1) / B;
-    if (gx > cap) gx = cap;
-    const size_t sm = sizeof(float) * ((size_t)taps * cc + 4 * cc);
-    if (dtype == B200SEG_F16) {
-      B200_CUDA(cudaFuncSetAttribute(dwconv_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      dwconv_fwd_kernel<__half><<<dim3(gx, B), threads, sm, st>>>(a);
-    } else {
-      B200_CUDA(cudaFuncSetAttribute(dwconv_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      dwconv_fwd_kernel<float><<<dim3(gx, B), threads, sm, st>>>(a);
-    }
+  // channel slices ride in grid.z: a block stages only its slice's filter taps / IN constants and issues only
+  // 2*slice statistics atomics, so wide layers (1280-2048 channels on a few hundred voxels) do not drown in
+  // per-block setup
+  const int chunk = pick_chunk(C);
+  a.Ctot = C; a.C = chunk; a.c0 = 0;
+  const int nchunk = C / chunk, ncg = chunk / 8, threads = pick_threads(ncg);
+  const int64_t items = (int64_t)D * H * ((W + RUN - 1) / RUN) * ncg;
+  int gx = (int)((items + threads - 1) / threads);
+  int cap = (B200SEG_NUM_SMS * 8 + B * nchunk - 1) / (B * nchunk);
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  const size_t sm = sizeof(float) * ((size_t)taps * chunk + 4 * chunk);
+  if (dtype == B200SEG_F16) {
+    dwconv_fwd_kernel<__half><<<dim3(gx, B, nchunk), threads, sm, st>>>(a);
+  } else {
+    dwconv_fwd_kernel<float><<<dim3(gx, B, nchunk), threads, sm, st>>>(a);
   }
   B200_CHECK_LAUNCH("dwconv3d_fwd");
   return B200SEG_OK;
@@ -300,21 +302,20 @@ extern "C" int b200seg_dwconv3d_wgrad(const void* x, int x_ld, int x_coff, const
   int rc = check(a, dtype);
   if (rc) return rc;
   if (!x || !dy || !dw || dy_ld % 8 || dy_coff % 8) return B200SEG_EINVAL;
-  const int ncg = C / 8, threads = pick_threads(ncg);
-  if (threads > 256) return B200SEG_EUNSUPPORTED;
+  const int chunk = pick_chunk(C), nchunk = C / chunk;
+  a.Ctot = C; a.C = chunk; a.c0 = 0;
+  const int ncg = chunk / 8, threads = pick_threads(ncg);
   const int64_t items = (int64_t)D * H * W * ncg;
   int gx = (int)((items + threads - 1) / threads);
-  const int cap = (B200SEG_NUM_SMS * 4 + B * kd - 1) / (B * kd);
+  int cap = (B200SEG_NUM_SMS * 4 + B * kd * nchunk - 1) / (B * kd * nchunk);
+  if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  const size_t sm = sizeof(float) * ((size_t)kh * kw * C + 2 * C);
+  const size_t sm = sizeof(float) * ((size_t)kh * kw * chunk + 2 * chunk);
   cudaStream_t st = as_stream(stream);
   if (dtype == B200SEG_F16) {
-    B200_CUDA(cudaFuncSetAttribute(dwconv_wgrad_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    dwconv_wgrad_kernel<__half><<<dim3(gx, B * kd), threads, sm, st>>>(a);
+    dwconv_wgrad_kernel<__half><<<dim3(gx, B * kd, nchunk), threads, sm, st>>>(a);
   } else {
-    B200_CUDA(cudaFuncSetAttribute(dwconv_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    dwconv_wgrad_kernel<float><<<dim3(gx, B * kd), threads, sm, st>>>(a);
+    dwconv_wgrad_kernel<float><<<dim3(gx, B * kd, nchunk), threads, sm, st>>>(a);
   }
   B200_CHECK_LAUNCH("dwconv3d_wgrad");
   return B200SEG_OK;
