@@ -22,6 +22,18 @@ struct DwArgs {
   int Ctot, c0;              // the launch covers channels [c0, c0+C) of a Ctot-channel layer (stats / weight rows)
 };
 
+// spatial tile covered by one pass of a block (rb = threads / channel-groups positions)
+struct Tile { int td, th, tw, nd, nh, nw; int64_t ntiles; };
+__host__ __device__ inline Tile make_tile(int rb, int D, int H, int Wn) {
+  Tile t;
+  if (rb % 8 == 0 && D > 1) { t.td = 2; t.th = 4; t.tw = rb / 8; }
+  else if (rb % 4 == 0) { t.td = 1; t.th = 4; t.tw = rb / 4; }
+  else { t.td = 1; t.th = 1; t.tw = rb; }
+  t.nd = (D + t.td - 1) / t.td; t.nh = (H + t.th - 1) / t.th; t.nw = (Wn + t.tw - 1) / t.tw;
+  t.ntiles = (int64_t)t.nd * t.nh * t.nw;
+  return t;
+}
+
 // 8 channels as loaded (no conversion yet) + validity, so a whole row of loads can be issued back to back
 template <typename T> struct Raw;
 template <> struct Raw<__half> {
@@ -74,13 +86,17 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
   float tsum[8], tsq[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) { tsum[c] = 0.f; tsq[c] = 0.f; }
-  const int64_t items = (int64_t)a.D * a.H * WR * ncg;
   const T* xb = (const T*)a.x + (int64_t)b * a.D * a.H * a.W * a.x_ld + a.x_coff + c0 + cg * 8;
   T* yb = (T*)a.y + (int64_t)b * a.D * a.H * a.W * a.y_ld + a.y_coff + c0 + cg * 8;
-  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + tid; it < items; it += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = it / ncg;
-    const int wr = (int)(r % WR); r /= WR;
-    const int h = (int)(r % a.H), d = (int)(r / a.H);
+  // a block pass covers a compact 2(d) x 4(h) x TWR(w-runs) tile so the 3x3x3 neighbourhoods of its threads
+  // overlap in L1 instead of each being fetched from L2
+  const Tile tl = make_tile(blockDim.x / ncg, a.D, a.H, WR);
+  const int rl = tid / ncg, lw = rl % tl.tw, lh = (rl / tl.tw) % tl.th, ldp = rl / (tl.tw * tl.th);
+  for (int64_t tile = blockIdx.x; tile < tl.ntiles; tile += gridDim.x) {
+    const int wr = (int)(tile % tl.nw) * tl.tw + lw;
+    const int h = (int)((tile / tl.nw) % tl.nh) * tl.th + lh;
+    const int d = (int)(tile / ((int64_t)tl.nw * tl.nh)) * tl.td + ldp;
+    if (wr >= WR || h >= a.H || d >= a.D) continue;
     const int w0 = wr * RUN;
     float acc[RUN][8];
 #pragma unroll
@@ -190,17 +206,18 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
   for (int t = 0; t < MAXK * MAXK; ++t)
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
-  const int64_t items = (int64_t)a.D * a.H * a.W * ncg;
   const T* xb = (const T*)a.x + (int64_t)b * a.D * a.H * a.W * a.x_ld + a.x_coff + c0 + cg * 8;
   const T* gb = (const T*)a.dy + (int64_t)b * a.D * a.H * a.W * a.dy_ld + a.dy_coff + c0 + cg * 8;
-  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + tid; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+  const Tile tl = make_tile(blockDim.x / ncg, a.D, a.H, a.W);
+  const int rl = tid / ncg, lw = rl % tl.tw, lh = (rl / tl.tw) % tl.th, ldp = rl / (tl.tw * tl.th);
+  for (int64_t tile = blockIdx.x; tile < tl.ntiles; tile += gridDim.x) {
     // input-stationary: the thread owns one INPUT vector (normalised once) and meets the 9 output gradients
     // of this depth tap that it contributes to:  dw[zd][zh][zw] += dy[id-zd+pd, ih-zh+ph, iw-zw+pw] * a[id,ih,iw]
-    int64_t r = it / ncg;
-    const int iw = (int)(r % a.W); r /= a.W;
-    const int ih = (int)(r % a.H), id = (int)(r / a.H);
+    const int iw = (int)(tile % tl.nw) * tl.tw + lw;
+    const int ih = (int)((tile / tl.nw) % tl.nh) * tl.th + lh;
+    const int id = (int)(tile / ((int64_t)tl.nw * tl.nh)) * tl.td + ldp;
     const int d = id - zd + pd;
-    if (d < 0 || d >= a.D) continue;
+    if (iw >= a.W || ih >= a.H || id >= a.D || d < 0 || d >= a.D) continue;
     Raw<T> rx, rg[MAXK * MAXK];
     rx.load(xb + (((int64_t)id * a.H + ih) * a.W + iw) * a.x_ld, true);
 #pragma unroll
@@ -277,8 +294,8 @@ extern "C" int b200seg_dwconv3d_fwd(const void* x, int x_ld, int x_coff, const d
   const int chunk = pick_chunk(C);
   a.Ctot = C; a.C = chunk; a.c0 = 0;
   const int nchunk = C / chunk, ncg = chunk / 8, threads = pick_threads(ncg);
-  const int64_t items = (int64_t)D * H * ((W + RUN - 1) / RUN) * ncg;
-  int gx = (int)((items + threads - 1) / threads);
+  const Tile tl = make_tile(threads / ncg, D, H, (W + RUN - 1) / RUN);
+  int gx = (int)(tl.ntiles < (1 << 30) ? tl.ntiles : (1 << 30));
   int cap = (B200SEG_NUM_SMS * 8 + B * nchunk - 1) / (B * nchunk);
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
@@ -305,8 +322,8 @@ extern "C" int b200seg_dwconv3d_wgrad(const void* x, int x_ld, int x_coff, const
   const int chunk = pick_chunk(C), nchunk = C / chunk;
   a.Ctot = C; a.C = chunk; a.c0 = 0;
   const int ncg = chunk / 8, threads = pick_threads(ncg);
-  const int64_t items = (int64_t)D * H * W * ncg;
-  int gx = (int)((items + threads - 1) / threads);
+  const Tile tl = make_tile(threads / ncg, D, H, W);
+  int gx = (int)(tl.ntiles < (1 << 30) ? tl.ntiles : (1 << 30));
   int cap = (B200SEG_NUM_SMS * 4 + B * kd * nchunk - 1) / (B * kd * nchunk);
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
