@@ -36,22 +36,34 @@ struct BiArgs {
   int B, M, heads; int64_t N; float scale;
 };
 
+constexpr int VFS = DH + 4;        // row stride of the staged value tile: 16-byte aligned rows
+
+__device__ __forceinline__ float dot4(float q0, float q1, float q2, float q3, const float4& w, float acc) {
+  return fmaf(q0, w.x, fmaf(q1, w.y, fmaf(q2, w.z, fmaf(q3, w.w, acc))));
+}
+
+// The map-side operands live in shared memory zero-padded to MAXM rows, so the token loops run unpredicated over
+// 32 rows with one broadcast LDS.128 per four FMAs; padded tokens get S = -inf after the contraction.
 template <typename T>
 __global__ void __launch_bounds__(kT)
 biattn_fwd_kernel(BiArgs a) {
   extern __shared__ float sm[];
-  float* s_qm = sm;                       // [M][DH] (pre-scaled)
-  float* s_vm = s_qm + MAXM * DH;         // [M][DH]
+  float* s_qm = sm;                       // [MAXM][DH] (pre-scaled, rows >= M zero)
+  float* s_vm = s_qm + MAXM * DH;         // [MAXM][DH]
   float* s_e = s_vm + MAXM * DH;          // [kT][MAXM+1]
-  float* s_vf = s_e + kT * (MAXM + 1);    // [kT][DH+1]
-  float* s_cmax = s_vf + kT * (DH + 1);   // [4 warps][MAXM] then [MAXM]
+  float* s_vf = s_e + kT * (MAXM + 1);    // [kT][VFS]
+  float* s_cmax = s_vf + kT * VFS;        // [4 warps][MAXM] then [MAXM]
   const int h = blockIdx.y, b = blockIdx.z, M = a.M, heads = a.heads;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (int o = tid; o < M * DH; o += kT) {
+  for (int o = tid; o < MAXM * DH; o += kT) {
     const int j = o / DH, d = o % DH;
-    const int64_t off = ((int64_t)b * M + j) * a.m_ld + d * heads + h;
-    s_qm[o] = Elem<T>::ld((const T*)a.mq + off + a.mq_coff) * a.scale;
-    s_vm[o] = Elem<T>::ld((const T*)a.mv + off + a.mv_coff);
+    float q = 0.f, v = 0.f;
+    if (j < M) {
+      const int64_t off = ((int64_t)b * M + j) * a.m_ld + d * heads + h;
+      q = Elem<T>::ld((const T*)a.mq + off + a.mq_coff) * a.scale;
+      v = Elem<T>::ld((const T*)a.mv + off + a.mv_coff);
+    }
+    s_qm[o] = q; s_vm[o] = v;
   }
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * kT + tid;
@@ -59,39 +71,51 @@ biattn_fwd_kernel(BiArgs a) {
   float S[MAXM];
 #pragma unroll
   for (int j = 0; j < MAXM; ++j) S[j] = 0.f;
-  float v[DH];
+  float* my_v = s_vf + tid * VFS;
   if (valid) {
     const T* qp = (const T*)a.fq + ((int64_t)b * a.N + i) * a.fq_ld + a.fq_coff + h;
     const T* vp = (const T*)a.fv + ((int64_t)b * a.N + i) * a.fv_ld + a.fv_coff + h;
-#pragma unroll 4
-    for (int d = 0; d < DH; ++d) {
-      const float qd = Elem<T>::ld(qp + d * heads);
 #pragma unroll
-      for (int j = 0; j < MAXM; ++j) if (j < M) S[j] = fmaf(qd, s_qm[j * DH + d], S[j]);
+    for (int d0 = 0; d0 < DH; d0 += 4) {
+      const float q0 = Elem<T>::ld(qp + d0 * heads), q1 = Elem<T>::ld(qp + (d0 + 1) * heads);
+      const float q2 = Elem<T>::ld(qp + (d0 + 2) * heads), q3 = Elem<T>::ld(qp + (d0 + 3) * heads);
+      *reinterpret_cast<float4*>(my_v + d0) = make_float4(Elem<T>::ld(vp + d0 * heads), Elem<T>::ld(vp + (d0 + 1) * heads),
+                                                          Elem<T>::ld(vp + (d0 + 2) * heads), Elem<T>::ld(vp + (d0 + 3) * heads));
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j) S[j] = dot4(q0, q1, q2, q3, *reinterpret_cast<const float4*>(s_qm + j * DH + d0), S[j]);
     }
 #pragma unroll
-    for (int d = 0; d < DH; ++d) v[d] = Elem<T>::ld(vp + d * heads);
+    for (int j = 0; j < MAXM; ++j) if (j >= M) S[j] = -INFINITY;
     // ---- row softmax over the map tokens + feat_out
     float m = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < MAXM; ++j) if (j < M) m = fmaxf(m, S[j]);
+    for (int j = 0; j < MAXM; ++j) m = fmaxf(m, S[j]);
     float p[MAXM], sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAXM; ++j) { p[j] = (j < M) ? __expf(S[j] - m) : 0.f; sum += p[j]; }
+    for (int j = 0; j < MAXM; ++j) { p[j] = __expf(S[j] - m); sum += p[j]; }
     const float inv = 1.f / sum;
     T* op = (T*)a.fo + ((int64_t)b * a.N + i) * a.fo_ld + a.fo_coff + h;
-#pragma unroll 4
-    for (int d = 0; d < DH; ++d) {
-      float o = 0.f;
 #pragma unroll
-      for (int j = 0; j < MAXM; ++j) if (j < M) o = fmaf(p[j], s_vm[j * DH + d], o);
-      Elem<T>::st(op + d * heads, o * inv);
+    for (int d0 = 0; d0 < DH; d0 += 4) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(s_vm + j * DH + d0);
+        o.x = fmaf(p[j], w.x, o.x); o.y = fmaf(p[j], w.y, o.y); o.z = fmaf(p[j], w.z, o.z); o.w = fmaf(p[j], w.w, o.w);
+      }
+      Elem<T>::st(op + d0 * heads, o.x * inv); Elem<T>::st(op + (d0 + 1) * heads, o.y * inv);
+      Elem<T>::st(op + (d0 + 2) * heads, o.z * inv); Elem<T>::st(op + (d0 + 3) * heads, o.w * inv);
     }
+  } else {
+#pragma unroll
+    for (int d0 = 0; d0 < DH; d0 += 4) *reinterpret_cast<float4*>(my_v + d0) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j) S[j] = -INFINITY;
   }
   // ---- column softmax partials of this block: max_j, sum_j exp(S - max_j), sum_i exp(S_ij - max_j) v_f[i][:]
 #pragma unroll
   for (int j = 0; j < MAXM; ++j) {
-    float mj = (valid && j < M) ? S[j] : -INFINITY;
+    float mj = S[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mj = fmaxf(mj, __shfl_xor_sync(0xffffffffu, mj, o));
     if (lane == 0) s_cmax[wid * MAXM + j] = mj;
@@ -104,17 +128,30 @@ biattn_fwd_kernel(BiArgs a) {
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < MAXM; ++j) s_e[tid * (MAXM + 1) + j] = (valid && j < M) ? __expf(S[j] - s_cmax[4 * MAXM + j]) : 0.f;
-#pragma unroll
-  for (int d = 0; d < DH; ++d) s_vf[tid * (DH + 1) + d] = valid ? v[d] : 0.f;
+  for (int j = 0; j < MAXM; ++j) {
+    const float cm = s_cmax[4 * MAXM + j];
+    s_e[tid * (MAXM + 1) + j] = (cm == -INFINITY) ? 0.f : __expf(S[j] - cm);      // padded tokens / empty blocks
+  }
   __syncthreads();
+  // 128 threads = 32 tokens x 4 channel octets; each accumulates its 1x8 patch of E^T V over the block's voxels
   const int nblk = gridDim.x;
   float* pb = a.partial + ((((int64_t)b * heads + h) * nblk + blockIdx.x) * M) * (2 + DH);
-  for (int o = tid; o < M * (DH + 1); o += kT) {
-    const int j = o / (DH + 1), d = o % (DH + 1);     // d == DH -> the column sum
-    float acc = 0.f;
-    if (d < DH) { for (int r = 0; r < kT; ++r) acc = fmaf(s_e[r * (MAXM + 1) + j], s_vf[r * (DH + 1) + d], acc); pb[j * (2 + DH) + 2 + d] = acc; }
-    else { for (int r = 0; r < kT; ++r) acc += s_e[r * (MAXM + 1) + j]; pb[j * (2 + DH) + 1] = acc; pb[j * (2 + DH)] = s_cmax[4 * MAXM + j]; }
+  const int j = tid >> 2, dg = (tid & 3) * 8;
+  float acc[8], esum = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < kT; ++r) {
+    const float e = s_e[r * (MAXM + 1) + j];
+    const float4 v0 = *reinterpret_cast<const float4*>(s_vf + r * VFS + dg), v1 = *reinterpret_cast<const float4*>(s_vf + r * VFS + dg + 4);
+    esum += e;
+    acc[0] = fmaf(e, v0.x, acc[0]); acc[1] = fmaf(e, v0.y, acc[1]); acc[2] = fmaf(e, v0.z, acc[2]); acc[3] = fmaf(e, v0.w, acc[3]);
+    acc[4] = fmaf(e, v1.x, acc[4]); acc[5] = fmaf(e, v1.y, acc[5]); acc[6] = fmaf(e, v1.z, acc[6]); acc[7] = fmaf(e, v1.w, acc[7]);
+  }
+  if (j < M) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) pb[j * (2 + DH) + 2 + dg + c] = acc[c];
+    if (dg == 0) { pb[j * (2 + DH)] = s_cmax[4 * MAXM + j]; pb[j * (2 + DH) + 1] = esum; }
   }
 }
 
@@ -151,37 +188,44 @@ template <typename T>
 __global__ void __launch_bounds__(kT)
 biattn_bwd_kernel(BiArgs a) {
   extern __shared__ float sm[];
-  float* s_qm = sm;                        // [M][DH]  (unscaled)
+  float* s_qm = sm;                        // [MAXM][DH]  (unscaled; rows >= M zero)
   float* s_vm = s_qm + MAXM * DH;
-  float* s_dmo = s_vm + MAXM * DH;         // [M][DH]
-  float* s_col = s_dmo + MAXM * DH;        // [M][3] = {gmax, 1/gsum, c_j}
+  float* s_dmo = s_vm + MAXM * DH;         // [MAXM][DH]
+  float* s_col = s_dmo + MAXM * DH;        // [MAXM][4] = {gmax, 1/gsum, c_j, -}
   float* s_p1 = s_col + MAXM * 4;          // [kT][MAXM+1]
   float* s_ds = s_p1 + kT * (MAXM + 1);    // [kT][MAXM+1]
-  float* s_do = s_ds + kT * (MAXM + 1);    // [kT][DH+1]
-  float* s_q = s_do + kT * (DH + 1);       // [kT][DH+1]
+  float* s_do = s_ds + kT * (MAXM + 1);    // [kT][VFS]
+  float* s_q = s_do + kT * VFS;            // [kT][VFS]
   const int h = blockIdx.y, b = blockIdx.z, M = a.M, heads = a.heads;
   const int tid = threadIdx.x;
-  for (int o = tid; o < M * DH; o += kT) {
+  for (int o = tid; o < MAXM * DH; o += kT) {
     const int j = o / DH, d = o % DH;
-    const int64_t off = ((int64_t)b * M + j) * a.m_ld + d * heads + h;
-    s_qm[o] = Elem<T>::ld((const T*)a.mq + off + a.mq_coff);
-    s_vm[o] = Elem<T>::ld((const T*)a.mv + off + a.mv_coff);
-    s_dmo[o] = Elem<T>::ld((const T*)a.dmo + ((int64_t)b * M + j) * a.dmo_ld + a.dmo_coff + d * heads + h);
+    float q = 0.f, v = 0.f, g = 0.f;
+    if (j < M) {
+      const int64_t off = ((int64_t)b * M + j) * a.m_ld + d * heads + h;
+      q = Elem<T>::ld((const T*)a.mq + off + a.mq_coff);
+      v = Elem<T>::ld((const T*)a.mv + off + a.mv_coff);
+      g = Elem<T>::ld((const T*)a.dmo + ((int64_t)b * M + j) * a.dmo_ld + a.dmo_coff + d * heads + h);
+    }
+    s_qm[o] = q; s_vm[o] = v; s_dmo[o] = g;
   }
   __syncthreads();
-  if (tid < M) {
-    const float* cs = a.colstat + (((int64_t)b * heads + h) * M + tid) * 2;
-    float c = 0.f;
-    for (int d = 0; d < DH; ++d)
-      c = fmaf(s_dmo[tid * DH + d], Elem<T>::ld((const T*)a.mo + ((int64_t)b * M + tid) * a.mo_ld + a.mo_coff + d * heads + h), c);
-    s_col[tid * 4] = cs[0]; s_col[tid * 4 + 1] = 1.f / cs[1]; s_col[tid * 4 + 2] = c;
+  if (tid < MAXM) {
+    float g0 = 0.f, g1 = 0.f, c = 0.f;
+    if (tid < M) {
+      const float* cs = a.colstat + (((int64_t)b * heads + h) * M + tid) * 2;
+      for (int d = 0; d < DH; ++d)
+        c = fmaf(s_dmo[tid * DH + d], Elem<T>::ld((const T*)a.mo + ((int64_t)b * M + tid) * a.mo_ld + a.mo_coff + d * heads + h), c);
+      g0 = cs[0]; g1 = 1.f / cs[1];
+    }
+    s_col[tid * 4] = g0; s_col[tid * 4 + 1] = g1; s_col[tid * 4 + 2] = c;
   }
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * kT + tid;
   const bool valid = i < a.N;
   float S[MAXM], v[DH];
-  float* my_q = s_q + tid * (DH + 1);      // own rows double as register relief; re-read below without a barrier
-  float* my_do = s_do + tid * (DH + 1);
+  float* my_q = s_q + tid * VFS;           // own rows double as register relief; re-read below without a barrier
+  float* my_do = s_do + tid * VFS;
 #pragma unroll
   for (int j = 0; j < MAXM; ++j) S[j] = 0.f;
   if (valid) {
@@ -190,38 +234,45 @@ biattn_bwd_kernel(BiArgs a) {
     const T* vp = (const T*)a.fv + row * a.fv_ld + a.fv_coff + h;
     const T* gp = (const T*)a.dfo + row * a.dfo_ld + a.dfo_coff + h;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) {
-      const float qd = Elem<T>::ld(qp + d * heads);
-      v[d] = Elem<T>::ld(vp + d * heads);
-      my_q[d] = qd; my_do[d] = Elem<T>::ld(gp + d * heads);
+    for (int d0 = 0; d0 < DH; d0 += 4) {
+      const float q0 = Elem<T>::ld(qp + d0 * heads), q1 = Elem<T>::ld(qp + (d0 + 1) * heads);
+      const float q2 = Elem<T>::ld(qp + (d0 + 2) * heads), q3 = Elem<T>::ld(qp + (d0 + 3) * heads);
 #pragma unroll
-      for (int j = 0; j < MAXM; ++j) if (j < M) S[j] = fmaf(qd, s_qm[j * DH + d], S[j]);
+      for (int u = 0; u < 4; ++u) v[d0 + u] = Elem<T>::ld(vp + (d0 + u) * heads);
+      *reinterpret_cast<float4*>(my_q + d0) = make_float4(q0, q1, q2, q3);
+      *reinterpret_cast<float4*>(my_do + d0) = make_float4(Elem<T>::ld(gp + d0 * heads), Elem<T>::ld(gp + (d0 + 1) * heads),
+                                                           Elem<T>::ld(gp + (d0 + 2) * heads), Elem<T>::ld(gp + (d0 + 3) * heads));
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j) S[j] = dot4(q0, q1, q2, q3, *reinterpret_cast<const float4*>(s_qm + j * DH + d0), S[j]);
     }
   } else {
 #pragma unroll
-    for (int d = 0; d < DH; ++d) { v[d] = 0.f; my_q[d] = 0.f; my_do[d] = 0.f; }
+    for (int d0 = 0; d0 < DH; d0 += 4) {
+      *reinterpret_cast<float4*>(my_q + d0) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(my_do + d0) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[d0 + u] = 0.f;
+    }
   }
   float p1[MAXM], dS[MAXM];
   {
     float m = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < MAXM; ++j) { S[j] *= a.scale; if (j < M) m = fmaxf(m, S[j]); }
+    for (int j = 0; j < MAXM; ++j) { S[j] = (j < M && valid) ? S[j] * a.scale : -INFINITY; m = fmaxf(m, S[j]); }
     float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAXM; ++j) { p1[j] = (j < M && valid) ? __expf(S[j] - m) : 0.f; sum += p1[j]; }
+    for (int j = 0; j < MAXM; ++j) { p1[j] = valid ? __expf(S[j] - m) : 0.f; sum += p1[j]; dS[j] = 0.f; }
     const float inv = valid ? 1.f / sum : 0.f;
+    // dA1_j = <dO, Vm_j>
+#pragma unroll
+    for (int d0 = 0; d0 < DH; d0 += 4) {
+      const float4 g = *reinterpret_cast<const float4*>(my_do + d0);
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j) dS[j] = dot4(g.x, g.y, g.z, g.w, *reinterpret_cast<const float4*>(s_vm + j * DH + d0), dS[j]);
+    }
     float t1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAXM; ++j) {
-      p1[j] *= inv;
-      float dA1 = 0.f;
-      if (j < M) {
-#pragma unroll
-        for (int d = 0; d < DH; ++d) dA1 = fmaf(my_do[d], s_vm[j * DH + d], dA1);
-      }
-      dS[j] = dA1;
-      t1 = fmaf(p1[j], dA1, t1);
-    }
+    for (int j = 0; j < MAXM; ++j) { p1[j] *= inv; t1 = fmaf(p1[j], dS[j], t1); }
 #pragma unroll
     for (int j = 0; j < MAXM; ++j) dS[j] = p1[j] * (dS[j] - t1);
   }
@@ -231,42 +282,58 @@ biattn_bwd_kernel(BiArgs a) {
   for (int d = 0; d < DH; ++d) dv[d] = 0.f;
 #pragma unroll
   for (int j = 0; j < MAXM; ++j) {
-    if (j < M) {
-      const float p2 = valid ? __expf(S[j] - s_col[j * 4]) * s_col[j * 4 + 1] : 0.f;
-      float dA2 = 0.f;
+    const float p2 = __expf(S[j] - s_col[j * 4]) * s_col[j * 4 + 1];       // 0 for padded tokens / invalid voxels
+    float dA2 = 0.f;
 #pragma unroll
-      for (int d = 0; d < DH; ++d) { dA2 = fmaf(s_dmo[j * DH + d], v[d], dA2); dv[d] = fmaf(p2, s_dmo[j * DH + d], dv[d]); }
-      dS[j] += p2 * (dA2 - s_col[j * 4 + 2]);
+    for (int d0 = 0; d0 < DH; d0 += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(s_dmo + j * DH + d0);
+      dA2 = dot4(v[d0], v[d0 + 1], v[d0 + 2], v[d0 + 3], w, dA2);
+      dv[d0] = fmaf(p2, w.x, dv[d0]); dv[d0 + 1] = fmaf(p2, w.y, dv[d0 + 1]);
+      dv[d0 + 2] = fmaf(p2, w.z, dv[d0 + 2]); dv[d0 + 3] = fmaf(p2, w.w, dv[d0 + 3]);
     }
+    dS[j] += p2 * (dA2 - s_col[j * 4 + 2]);
   }
   if (valid) {
     const int64_t row = (int64_t)b * a.N + i;
     T* dqp = (T*)a.dfq + row * a.dfq_ld + a.dfq_coff + h;
     T* dvp = (T*)a.dfv + row * a.dfv_ld + a.dfv_coff + h;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) {
-      float dq = 0.f;
+    for (int d0 = 0; d0 < DH; d0 += 4) {
+      float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < MAXM; ++j) if (j < M) dq = fmaf(dS[j], s_qm[j * DH + d], dq);
-      Elem<T>::st(dqp + d * heads, dq * a.scale);
-      Elem<T>::st(dvp + d * heads, dv[d]);
+      for (int j = 0; j < MAXM; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(s_qm + j * DH + d0);
+        dq.x = fmaf(dS[j], w.x, dq.x); dq.y = fmaf(dS[j], w.y, dq.y); dq.z = fmaf(dS[j], w.z, dq.z); dq.w = fmaf(dS[j], w.w, dq.w);
+      }
+      Elem<T>::st(dqp + d0 * heads, dq.x * a.scale); Elem<T>::st(dqp + (d0 + 1) * heads, dq.y * a.scale);
+      Elem<T>::st(dqp + (d0 + 2) * heads, dq.z * a.scale); Elem<T>::st(dqp + (d0 + 3) * heads, dq.w * a.scale);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Elem<T>::st(dvp + (d0 + u) * heads, dv[d0 + u]);
     }
   }
   // block partials of the map-side gradients: dVm[j][d] = sum_i p1_ij dO_i[d] ; dQm[j][d] = scale sum_i dS_ij q_i[d]
 #pragma unroll
-  for (int j = 0; j < MAXM; ++j) { s_p1[tid * (MAXM + 1) + j] = p1[j]; s_ds[tid * (MAXM + 1) + j] = (j < M) ? dS[j] : 0.f; }
+  for (int j = 0; j < MAXM; ++j) { s_p1[tid * (MAXM + 1) + j] = p1[j]; s_ds[tid * (MAXM + 1) + j] = dS[j]; }
   __syncthreads();
   const int nblk = gridDim.x;
   float* pb = a.partial + ((((int64_t)b * heads + h) * nblk + blockIdx.x) * M) * (2 * DH);
-  for (int o = tid; o < M * DH; o += kT) {
-    const int j = o / DH, d = o % DH;
-    float av = 0.f, aq = 0.f;
-    for (int r = 0; r < kT; ++r) {
-      av = fmaf(s_p1[r * (MAXM + 1) + j], s_do[r * (DH + 1) + d], av);
-      aq = fmaf(s_ds[r * (MAXM + 1) + j], s_q[r * (DH + 1) + d], aq);
-    }
-    pb[j * 2 * DH + d] = aq * a.scale;
-    pb[j * 2 * DH + DH + d] = av;
+  const int j = tid >> 2, dg = (tid & 3) * 8;          // 32 tokens x 4 channel octets, 1x8 register patch each
+  float av[8], aq[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { av[c] = 0.f; aq[c] = 0.f; }
+#pragma unroll 2
+  for (int r = 0; r < kT; ++r) {
+    const float pp = s_p1[r * (MAXM + 1) + j], dd = s_ds[r * (MAXM + 1) + j];
+    const float4 g0 = *reinterpret_cast<const float4*>(s_do + r * VFS + dg), g1 = *reinterpret_cast<const float4*>(s_do + r * VFS + dg + 4);
+    const float4 q0 = *reinterpret_cast<const float4*>(s_q + r * VFS + dg), q1 = *reinterpret_cast<const float4*>(s_q + r * VFS + dg + 4);
+    av[0] = fmaf(pp, g0.x, av[0]); av[1] = fmaf(pp, g0.y, av[1]); av[2] = fmaf(pp, g0.z, av[2]); av[3] = fmaf(pp, g0.w, av[3]);
+    av[4] = fmaf(pp, g1.x, av[4]); av[5] = fmaf(pp, g1.y, av[5]); av[6] = fmaf(pp, g1.z, av[6]); av[7] = fmaf(pp, g1.w, av[7]);
+    aq[0] = fmaf(dd, q0.x, aq[0]); aq[1] = fmaf(dd, q0.y, aq[1]); aq[2] = fmaf(dd, q0.z, aq[2]); aq[3] = fmaf(dd, q0.w, aq[3]);
+    aq[4] = fmaf(dd, q1.x, aq[4]); aq[5] = fmaf(dd, q1.y, aq[5]); aq[6] = fmaf(dd, q1.z, aq[6]); aq[7] = fmaf(dd, q1.w, aq[7]);
+  }
+  if (j < M) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { pb[j * 2 * DH + dg + c] = aq[c] * a.scale; pb[j * 2 * DH + DH + dg + c] = av[c]; }
   }
 }
 
@@ -320,7 +387,7 @@ extern "C" int b200seg_biattn_fwd(const void* fq, int fq_ld, int fq_coff, const 
   cudaStream_t st = as_stream(stream);
   const int nblk = (int)((N + kT - 1) / kT);
   dim3 grid(nblk, heads, B);
-  const size_t sm = sizeof(float) * (2 * MAXM * DH + kT * (MAXM + 1) + kT * (DH + 1) + 5 * MAXM);
+  const size_t sm = sizeof(float) * (2 * MAXM * DH + kT * (MAXM + 1) + kT * VFS + 5 * MAXM);
   if (dtype == B200SEG_F16) {
     cudaFuncSetAttribute(biattn_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     biattn_fwd_kernel<__half><<<grid, kT, sm, st>>>(a);
@@ -356,7 +423,7 @@ extern "C" int b200seg_biattn_bwd(const void* fq, int fq_ld, int fq_coff, const 
   cudaStream_t st = as_stream(stream);
   const int nblk = (int)((N + kT - 1) / kT);
   dim3 grid(nblk, heads, B);
-  const size_t sm = sizeof(float) * (3 * MAXM * DH + 4 * MAXM + 2 * kT * (MAXM + 1) + 2 * kT * (DH + 1));
+  const size_t sm = sizeof(float) * (3 * MAXM * DH + 4 * MAXM + 2 * kT * (MAXM + 1) + 2 * kT * VFS);
   if (dtype == B200SEG_F16) {
     cudaFuncSetAttribute(biattn_bwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     biattn_bwd_kernel<__half><<<grid, kT, sm, st>>>(a);

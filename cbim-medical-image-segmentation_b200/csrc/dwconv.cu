@@ -69,20 +69,23 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
   const double nvox = (double)a.D * a.H * a.W;
   for (int o = tid; o < taps * C; o += blockDim.x) {
     const int t = o / C, c = o % C;
-    s_w[o] = a.w[(a.flip ? taps - 1 - t : t) * a.Ctot + c0 + c];
+    // [tap][half][cg][4]: a warp's float4 reads (lane = channel group) are contiguous -> no bank conflicts
+    s_w[((t * 2 + ((c & 7) >> 2)) * (C >> 3) + (c >> 3)) * 4 + (c & 3)] = a.w[(a.flip ? taps - 1 - t : t) * a.Ctot + c0 + c];
   }
   for (int c = tid; c < C; c += blockDim.x) {
     float mean = 0.f, rstd = 1.f;
     if (a.x_stats) stats_to_mean_rstd(a.x_stats + ((int64_t)b * a.Ctot + c0 + c) * 2, nvox, a.eps, mean, rstd);
-    s_scale[c] = rstd; s_shift[c] = -mean * rstd; s_sum[c] = 0.f; s_sq[c] = 0.f;
+    // IN constants transposed [c%8][cg] for the same reason
+    s_scale[(c & 7) * (C >> 3) + (c >> 3)] = rstd; s_shift[(c & 7) * (C >> 3) + (c >> 3)] = -mean * rstd;
+    s_sum[c] = 0.f; s_sq[c] = 0.f;
   }
   __syncthreads();
   const int ncg = C >> 3, WR = (a.W + RUN - 1) / RUN;
   const int cg = tid % ncg;                // blockDim.x and the grid stride are multiples of ncg
   const int pd = a.kd >> 1, ph = a.kh >> 1, pw = a.kw >> 1;
   const bool norm = a.x_stats != nullptr, relu = a.act == 1;
-  const float* sc = s_scale + cg * 8;     // read from shared memory at the use site: keeps 16 registers free
-  const float* sh = s_shift + cg * 8;
+  const float* sc = s_scale + cg;          // element c at sc[c * ncg]; read at the use site (keeps 16 registers free)
+  const float* sh = s_shift + cg;
   float tsum[8], tsq[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) { tsum[c] = 0.f; tsq[c] = 0.f; }
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
         const int ih = h + zh - ph;
         if (ih < 0 || ih >= a.H) continue;
         const T* row = xb + ((int64_t)id * a.H + ih) * a.W * a.x_ld;
-        const float* wrow = s_w + (zd * a.kh + zh) * a.kw * C + cg * 8;
+        const float* wrow = s_w + (zd * a.kh + zh) * a.kw * C + cg * 4;
         // all loads of the row first (independent, in flight together), then the arithmetic
         Raw<T> raw[RUN + MAXK - 1];
 #pragma unroll
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
 #pragma unroll
         for (int k = 0; k < MAXK; ++k) {
           if (k < a.kw) {
-            const float4 w0v = *reinterpret_cast<const float4*>(wrow + k * C), w1v = *reinterpret_cast<const float4*>(wrow + k * C + 4);
+            const float4 w0v = *reinterpret_cast<const float4*>(wrow + k * C), w1v = *reinterpret_cast<const float4*>(wrow + k * C + ncg * 4);
             wt[k][0] = w0v.x; wt[k][1] = w0v.y; wt[k][2] = w0v.z; wt[k][3] = w0v.w;
             wt[k][4] = w1v.x; wt[k][5] = w1v.y; wt[k][6] = w1v.z; wt[k][7] = w1v.w;
           } else {
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
           raw[j].get(v);
           if (norm) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) { v[c] = fmaf(v[c], sc[c], sh[c]); if (relu) v[c] = fmaxf(v[c], 0.f); v[c] = Elem<T>::round(v[c]); }
+            for (int c = 0; c < 8; ++c) { v[c] = fmaf(v[c], sc[c * ncg], sh[c * ncg]); if (relu) v[c] = fmaxf(v[c], 0.f); v[c] = Elem<T>::round(v[c]); }
           } else if (relu) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
@@ -192,15 +195,15 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
   for (int c = tid; c < C; c += blockDim.x) {
     float mean = 0.f, rstd = 1.f;
     if (a.x_stats) stats_to_mean_rstd(a.x_stats + ((int64_t)b * a.Ctot + c0 + c) * 2, nvox, a.eps, mean, rstd);
-    s_scale[c] = rstd; s_shift[c] = -mean * rstd;
+    s_scale[(c & 7) * (C >> 3) + (c >> 3)] = rstd; s_shift[(c & 7) * (C >> 3) + (c >> 3)] = -mean * rstd;
   }
   for (int o = tid; o < thw * C; o += blockDim.x) s_acc[o] = 0.f;
   __syncthreads();
   const int ncg = C >> 3, cg = tid % ncg;
   const int pd = a.kd >> 1, ph = a.kh >> 1, pw = a.kw >> 1;
   const bool norm = a.x_stats != nullptr, relu = a.act == 1;
-  const float* sc = s_scale + cg * 8;
-  const float* sh = s_shift + cg * 8;
+  const float* sc = s_scale + cg;
+  const float* sh = s_shift + cg;
   float acc[MAXK * MAXK][8];
 #pragma unroll
   for (int t = 0; t < MAXK * MAXK; ++t)
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
     rx.get(v);
     if (norm) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) { v[c] = fmaf(v[c], sc[c], sh[c]); if (relu) v[c] = fmaxf(v[c], 0.f); v[c] = Elem<T>::round(v[c]); }
+      for (int c = 0; c < 8; ++c) { v[c] = fmaf(v[c], sc[c * ncg], sh[c * ncg]); if (relu) v[c] = fmaxf(v[c], 0.f); v[c] = Elem<T>::round(v[c]); }
     } else if (relu) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
