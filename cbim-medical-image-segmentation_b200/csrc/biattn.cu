@@ -15,7 +15,7 @@
 namespace {
 
 constexpr int kT = 128;           // voxels per block (one per thread)
-constexpr int MAXM = 32;          // map tokens (27 in the BASELINE config)
+constexpr int MAXM_CAP = 64;      // map tokens: 27 (BCV 3x3x3) run the 32-row build, 64 (4x4x4 maps) the 64-row one
 constexpr int DH = 32;            // head dimension (all BASELINE MedFormer levels use 32)
 
 struct BiArgs {
@@ -42,9 +42,10 @@ __device__ __forceinline__ float dot4(float q0, float q1, float q2, float q3, co
   return fmaf(q0, w.x, fmaf(q1, w.y, fmaf(q2, w.z, fmaf(q3, w.w, acc))));
 }
 
-// The map-side operands live in shared memory zero-padded to MAXM rows, so the token loops run unpredicated over
-// 32 rows with one broadcast LDS.128 per four FMAs; padded tokens get S = -inf after the contraction.
-template <typename T>
+// The map-side operands live in shared memory zero-padded to MAXM rows (MAXM = 32 or 64: BCV's 27 tokens / the
+// 64 of the 4x4x4 maps), so the token loops run unpredicated with one broadcast LDS.128 per four FMAs; padded
+// tokens get S = -inf after the contraction.
+template <typename T, int MAXM>
 __global__ void __launch_bounds__(kT)
 biattn_fwd_kernel(BiArgs a) {
   extern __shared__ float sm[];
@@ -86,33 +87,13 @@ biattn_fwd_kernel(BiArgs a) {
     }
 #pragma unroll
     for (int j = 0; j < MAXM; ++j) if (j >= M) S[j] = -INFINITY;
-    // ---- row softmax over the map tokens + feat_out
-    float m = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < MAXM; ++j) m = fmaxf(m, S[j]);
-    float p[MAXM], sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < MAXM; ++j) { p[j] = __expf(S[j] - m); sum += p[j]; }
-    const float inv = 1.f / sum;
-    T* op = (T*)a.fo + ((int64_t)b * a.N + i) * a.fo_ld + a.fo_coff + h;
-#pragma unroll
-    for (int d0 = 0; d0 < DH; d0 += 4) {
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < MAXM; ++j) {
-        const float4 w = *reinterpret_cast<const float4*>(s_vm + j * DH + d0);
-        o.x = fmaf(p[j], w.x, o.x); o.y = fmaf(p[j], w.y, o.y); o.z = fmaf(p[j], w.z, o.z); o.w = fmaf(p[j], w.w, o.w);
-      }
-      Elem<T>::st(op + d0 * heads, o.x * inv); Elem<T>::st(op + (d0 + 1) * heads, o.y * inv);
-      Elem<T>::st(op + (d0 + 2) * heads, o.z * inv); Elem<T>::st(op + (d0 + 3) * heads, o.w * inv);
-    }
   } else {
 #pragma unroll
     for (int d0 = 0; d0 < DH; d0 += 4) *reinterpret_cast<float4*>(my_v + d0) = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < MAXM; ++j) S[j] = -INFINITY;
   }
-  // ---- column softmax partials of this block: max_j, sum_j exp(S - max_j), sum_i exp(S_ij - max_j) v_f[i][:]
+  // ---- column direction first (it needs the raw scores): block max per token, exp into shared memory
 #pragma unroll
   for (int j = 0; j < MAXM; ++j) {
     float mj = S[j];
@@ -132,26 +113,52 @@ biattn_fwd_kernel(BiArgs a) {
     const float cm = s_cmax[4 * MAXM + j];
     s_e[tid * (MAXM + 1) + j] = (cm == -INFINITY) ? 0.f : __expf(S[j] - cm);      // padded tokens / empty blocks
   }
+  // ---- row softmax over the map tokens (probabilities overwrite the scores) + feat_out
+  if (valid) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j) m = fmaxf(m, S[j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j) { S[j] = __expf(S[j] - m); sum += S[j]; }
+    const float inv = 1.f / sum;
+    T* op = (T*)a.fo + ((int64_t)b * a.N + i) * a.fo_ld + a.fo_coff + h;
+#pragma unroll
+    for (int d0 = 0; d0 < DH; d0 += 4) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(s_vm + j * DH + d0);
+        o.x = fmaf(S[j], w.x, o.x); o.y = fmaf(S[j], w.y, o.y); o.z = fmaf(S[j], w.z, o.z); o.w = fmaf(S[j], w.w, o.w);
+      }
+      Elem<T>::st(op + d0 * heads, o.x * inv); Elem<T>::st(op + (d0 + 1) * heads, o.y * inv);
+      Elem<T>::st(op + (d0 + 2) * heads, o.z * inv); Elem<T>::st(op + (d0 + 3) * heads, o.w * inv);
+    }
+  }
   __syncthreads();
   // 128 threads = 32 tokens x 4 channel octets; each accumulates its 1x8 patch of E^T V over the block's voxels
   const int nblk = gridDim.x;
   float* pb = a.partial + ((((int64_t)b * heads + h) * nblk + blockIdx.x) * M) * (2 + DH);
-  const int j = tid >> 2, dg = (tid & 3) * 8;
-  float acc[8], esum = 0.f;
+  const int dg = (tid & 3) * 8;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  for (int jh = 0; jh < MAXM; jh += 32) {
+    const int j = jh + (tid >> 2);
+    float acc[8], esum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
 #pragma unroll 4
-  for (int r = 0; r < kT; ++r) {
-    const float e = s_e[r * (MAXM + 1) + j];
-    const float4 v0 = *reinterpret_cast<const float4*>(s_vf + r * VFS + dg), v1 = *reinterpret_cast<const float4*>(s_vf + r * VFS + dg + 4);
-    esum += e;
-    acc[0] = fmaf(e, v0.x, acc[0]); acc[1] = fmaf(e, v0.y, acc[1]); acc[2] = fmaf(e, v0.z, acc[2]); acc[3] = fmaf(e, v0.w, acc[3]);
-    acc[4] = fmaf(e, v1.x, acc[4]); acc[5] = fmaf(e, v1.y, acc[5]); acc[6] = fmaf(e, v1.z, acc[6]); acc[7] = fmaf(e, v1.w, acc[7]);
-  }
-  if (j < M) {
+    for (int r = 0; r < kT; ++r) {
+      const float e = s_e[r * (MAXM + 1) + j];
+      const float4 v0 = *reinterpret_cast<const float4*>(s_vf + r * VFS + dg), v1 = *reinterpret_cast<const float4*>(s_vf + r * VFS + dg + 4);
+      esum += e;
+      acc[0] = fmaf(e, v0.x, acc[0]); acc[1] = fmaf(e, v0.y, acc[1]); acc[2] = fmaf(e, v0.z, acc[2]); acc[3] = fmaf(e, v0.w, acc[3]);
+      acc[4] = fmaf(e, v1.x, acc[4]); acc[5] = fmaf(e, v1.y, acc[5]); acc[6] = fmaf(e, v1.z, acc[6]); acc[7] = fmaf(e, v1.w, acc[7]);
+    }
+    if (j < M) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) pb[j * (2 + DH) + 2 + dg + c] = acc[c];
-    if (dg == 0) { pb[j * (2 + DH)] = s_cmax[4 * MAXM + j]; pb[j * (2 + DH) + 1] = esum; }
+      for (int c = 0; c < 8; ++c) pb[j * (2 + DH) + 2 + dg + c] = acc[c];
+      if (dg == 0) { pb[j * (2 + DH)] = s_cmax[4 * MAXM + j]; pb[j * (2 + DH) + 1] = esum; }
+    }
   }
 }
 
@@ -184,7 +191,7 @@ __global__ void biattn_fwd_merge_kernel(BiArgs a, int nblk) {
   }
 }
 
-template <typename T>
+template <typename T, int MAXM>
 __global__ void __launch_bounds__(kT)
 biattn_bwd_kernel(BiArgs a) {
   extern __shared__ float sm[];
@@ -254,15 +261,17 @@ biattn_bwd_kernel(BiArgs a) {
       for (int u = 0; u < 4; ++u) v[d0 + u] = 0.f;
     }
   }
-  float p1[MAXM], dS[MAXM];
+  // row softmax: p1_j = exp(S_j - m) * inv is recomputed where needed (keeps MAXM registers free for 64 tokens)
+  float dS[MAXM];
+  float m = -INFINITY, inv = 0.f;
   {
-    float m = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < MAXM; ++j) { S[j] = (j < M && valid) ? S[j] * a.scale : -INFINITY; m = fmaxf(m, S[j]); }
+    for (int j = 0; j < MAXM; ++j) { S[j] = (j < M && valid) ? S[j] * a.scale : -INFINITY; m = fmaxf(m, S[j]); dS[j] = 0.f; }
+    if (!valid) m = 0.f;                   // keeps exp(S - m) = exp(-inf) = 0 instead of NaN for padding threads
     float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAXM; ++j) { p1[j] = valid ? __expf(S[j] - m) : 0.f; sum += p1[j]; dS[j] = 0.f; }
-    const float inv = valid ? 1.f / sum : 0.f;
+    for (int j = 0; j < MAXM; ++j) sum += __expf(S[j] - m);
+    inv = valid ? 1.f / sum : 0.f;
     // dA1_j = <dO, Vm_j>
 #pragma unroll
     for (int d0 = 0; d0 < DH; d0 += 4) {
@@ -272,9 +281,9 @@ biattn_bwd_kernel(BiArgs a) {
     }
     float t1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAXM; ++j) { p1[j] *= inv; t1 = fmaf(p1[j], dS[j], t1); }
+    for (int j = 0; j < MAXM; ++j) t1 = fmaf(__expf(S[j] - m) * inv, dS[j], t1);
 #pragma unroll
-    for (int j = 0; j < MAXM; ++j) dS[j] = p1[j] * (dS[j] - t1);
+    for (int j = 0; j < MAXM; ++j) dS[j] = __expf(S[j] - m) * inv * (dS[j] - t1);
   }
   // column direction: p2_ij = exp(S_ij - gmax_j) / gsum_j ; dS += p2 (dA2 - c_j) ; dVf = sum_j p2 dmo_j
   float dv[DH];
@@ -313,27 +322,31 @@ biattn_bwd_kernel(BiArgs a) {
   }
   // block partials of the map-side gradients: dVm[j][d] = sum_i p1_ij dO_i[d] ; dQm[j][d] = scale sum_i dS_ij q_i[d]
 #pragma unroll
-  for (int j = 0; j < MAXM; ++j) { s_p1[tid * (MAXM + 1) + j] = p1[j]; s_ds[tid * (MAXM + 1) + j] = dS[j]; }
+  for (int j = 0; j < MAXM; ++j) { s_p1[tid * (MAXM + 1) + j] = __expf(S[j] - m) * inv; s_ds[tid * (MAXM + 1) + j] = dS[j]; }
   __syncthreads();
   const int nblk = gridDim.x;
   float* pb = a.partial + ((((int64_t)b * heads + h) * nblk + blockIdx.x) * M) * (2 * DH);
-  const int j = tid >> 2, dg = (tid & 3) * 8;          // 32 tokens x 4 channel octets, 1x8 register patch each
-  float av[8], aq[8];
+  const int dg = (tid & 3) * 8;                        // 32 tokens x 4 channel octets per pass, 1x8 register patch each
 #pragma unroll
-  for (int c = 0; c < 8; ++c) { av[c] = 0.f; aq[c] = 0.f; }
+  for (int jh = 0; jh < MAXM; jh += 32) {
+    const int j = jh + (tid >> 2);
+    float av[8], aq[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { av[c] = 0.f; aq[c] = 0.f; }
 #pragma unroll 2
-  for (int r = 0; r < kT; ++r) {
-    const float pp = s_p1[r * (MAXM + 1) + j], dd = s_ds[r * (MAXM + 1) + j];
-    const float4 g0 = *reinterpret_cast<const float4*>(s_do + r * VFS + dg), g1 = *reinterpret_cast<const float4*>(s_do + r * VFS + dg + 4);
-    const float4 q0 = *reinterpret_cast<const float4*>(s_q + r * VFS + dg), q1 = *reinterpret_cast<const float4*>(s_q + r * VFS + dg + 4);
-    av[0] = fmaf(pp, g0.x, av[0]); av[1] = fmaf(pp, g0.y, av[1]); av[2] = fmaf(pp, g0.z, av[2]); av[3] = fmaf(pp, g0.w, av[3]);
-    av[4] = fmaf(pp, g1.x, av[4]); av[5] = fmaf(pp, g1.y, av[5]); av[6] = fmaf(pp, g1.z, av[6]); av[7] = fmaf(pp, g1.w, av[7]);
-    aq[0] = fmaf(dd, q0.x, aq[0]); aq[1] = fmaf(dd, q0.y, aq[1]); aq[2] = fmaf(dd, q0.z, aq[2]); aq[3] = fmaf(dd, q0.w, aq[3]);
-    aq[4] = fmaf(dd, q1.x, aq[4]); aq[5] = fmaf(dd, q1.y, aq[5]); aq[6] = fmaf(dd, q1.z, aq[6]); aq[7] = fmaf(dd, q1.w, aq[7]);
-  }
-  if (j < M) {
+    for (int r = 0; r < kT; ++r) {
+      const float pp = s_p1[r * (MAXM + 1) + j], dd = s_ds[r * (MAXM + 1) + j];
+      const float4 g0 = *reinterpret_cast<const float4*>(s_do + r * VFS + dg), g1 = *reinterpret_cast<const float4*>(s_do + r * VFS + dg + 4);
+      const float4 q0 = *reinterpret_cast<const float4*>(s_q + r * VFS + dg), q1 = *reinterpret_cast<const float4*>(s_q + r * VFS + dg + 4);
+      av[0] = fmaf(pp, g0.x, av[0]); av[1] = fmaf(pp, g0.y, av[1]); av[2] = fmaf(pp, g0.z, av[2]); av[3] = fmaf(pp, g0.w, av[3]);
+      av[4] = fmaf(pp, g1.x, av[4]); av[5] = fmaf(pp, g1.y, av[5]); av[6] = fmaf(pp, g1.z, av[6]); av[7] = fmaf(pp, g1.w, av[7]);
+      aq[0] = fmaf(dd, q0.x, aq[0]); aq[1] = fmaf(dd, q0.y, aq[1]); aq[2] = fmaf(dd, q0.z, aq[2]); aq[3] = fmaf(dd, q0.w, aq[3]);
+      aq[4] = fmaf(dd, q1.x, aq[4]); aq[5] = fmaf(dd, q1.y, aq[5]); aq[6] = fmaf(dd, q1.z, aq[6]); aq[7] = fmaf(dd, q1.w, aq[7]);
+    }
+    if (j < M) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { pb[j * 2 * DH + dg + c] = aq[c] * a.scale; pb[j * 2 * DH + DH + dg + c] = av[c]; }
+      for (int c = 0; c < 8; ++c) { pb[j * 2 * DH + dg + c] = aq[c] * a.scale; pb[j * 2 * DH + DH + dg + c] = av[c]; }
+    }
   }
 }
 
@@ -365,7 +378,7 @@ extern "C" size_t b200seg_biattn_workspace(int B, int64_t N, int M, int heads) {
 
 static int check_args(int B, int64_t N, int M, int heads, int dim_head, int dtype) {
   if (B <= 0 || N <= 0 || M <= 0 || heads <= 0) return B200SEG_EINVAL;
-  if (dim_head != DH || M > MAXM) return B200SEG_EUNSUPPORTED;
+  if (dim_head != DH || M > MAXM_CAP) return B200SEG_EUNSUPPORTED;
   if (dtype != B200SEG_F16 && dtype != B200SEG_F32) return B200SEG_EINVAL;
   if ((N + kT - 1) / kT > 65535 * 1024) return B200SEG_EUNSUPPORTED;
   return B200SEG_OK;
@@ -387,16 +400,17 @@ extern "C" int b200seg_biattn_fwd(const void* fq, int fq_ld, int fq_coff, const 
   cudaStream_t st = as_stream(stream);
   const int nblk = (int)((N + kT - 1) / kT);
   dim3 grid(nblk, heads, B);
-  const size_t sm = sizeof(float) * (2 * MAXM * DH + kT * (MAXM + 1) + kT * VFS + 5 * MAXM);
-  if (dtype == B200SEG_F16) {
-    cudaFuncSetAttribute(biattn_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    biattn_fwd_kernel<__half><<<grid, kT, sm, st>>>(a);
-    biattn_fwd_merge_kernel<__half><<<dim3(M, heads, B), 128, 0, st>>>(a, nblk);
-  } else {
-    cudaFuncSetAttribute(biattn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    biattn_fwd_kernel<float><<<grid, kT, sm, st>>>(a);
-    biattn_fwd_merge_kernel<float><<<dim3(M, heads, B), 128, 0, st>>>(a, nblk);
-  }
+  const int MM = M <= 32 ? 32 : 64;
+  const size_t sm = sizeof(float) * (2 * MM * DH + kT * (MM + 1) + kT * VFS + 5 * MM);
+#define B200_BIATTN_FWD(TT, MMM)                                                                              \
+  do {                                                                                                        \
+    B200_CUDA(cudaFuncSetAttribute(biattn_fwd_kernel<TT, MMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    biattn_fwd_kernel<TT, MMM><<<grid, kT, sm, st>>>(a);                                                      \
+    biattn_fwd_merge_kernel<TT><<<dim3(M, heads, B), 128, 0, st>>>(a, nblk);                                  \
+  } while (0)
+  if (dtype == B200SEG_F16) { if (MM == 32) B200_BIATTN_FWD(__half, 32); else B200_BIATTN_FWD(__half, 64); }
+  else { if (MM == 32) B200_BIATTN_FWD(float, 32); else B200_BIATTN_FWD(float, 64); }
+#undef B200_BIATTN_FWD
   B200_CHECK_LAUNCH("biattn_fwd");
   return B200SEG_OK;
 }
@@ -423,16 +437,17 @@ extern "C" int b200seg_biattn_bwd(const void* fq, int fq_ld, int fq_coff, const 
   cudaStream_t st = as_stream(stream);
   const int nblk = (int)((N + kT - 1) / kT);
   dim3 grid(nblk, heads, B);
-  const size_t sm = sizeof(float) * (3 * MAXM * DH + 4 * MAXM + 2 * kT * (MAXM + 1) + 2 * kT * VFS);
-  if (dtype == B200SEG_F16) {
-    cudaFuncSetAttribute(biattn_bwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    biattn_bwd_kernel<__half><<<grid, kT, sm, st>>>(a);
-    biattn_bwd_merge_kernel<__half><<<dim3(M, heads, B), 256, 0, st>>>(a, nblk);
-  } else {
-    cudaFuncSetAttribute(biattn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    biattn_bwd_kernel<float><<<grid, kT, sm, st>>>(a);
-    biattn_bwd_merge_kernel<float><<<dim3(M, heads, B), 256, 0, st>>>(a, nblk);
-  }
+  const int MM = M <= 32 ? 32 : 64;
+  const size_t sm = sizeof(float) * (3 * MM * DH + 4 * MM + 2 * kT * (MM + 1) + 2 * kT * VFS);
+#define B200_BIATTN_BWD(TT, MMM)                                                                              \
+  do {                                                                                                        \
+    B200_CUDA(cudaFuncSetAttribute(biattn_bwd_kernel<TT, MMM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    biattn_bwd_kernel<TT, MMM><<<grid, kT, sm, st>>>(a);                                                      \
+    biattn_bwd_merge_kernel<TT><<<dim3(M, heads, B), 256, 0, st>>>(a, nblk);                                  \
+  } while (0)
+  if (dtype == B200SEG_F16) { if (MM == 32) B200_BIATTN_BWD(__half, 32); else B200_BIATTN_BWD(__half, 64); }
+  else { if (MM == 32) B200_BIATTN_BWD(float, 32); else B200_BIATTN_BWD(float, 64); }
+#undef B200_BIATTN_BWD
   B200_CHECK_LAUNCH("biattn_bwd");
   return B200SEG_OK;
 }

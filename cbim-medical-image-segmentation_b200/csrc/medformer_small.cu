@@ -35,7 +35,7 @@ __global__ void s2d_kernel(const T* __restrict__ x, T* __restrict__ y, int B, in
 }
 
 // ------------------------------------------------------------------ semantic map generation
-constexpr int MG_T = 128, MG_K = 32, MG_CC = 48;
+constexpr int MG_T = 128, MG_KCAP = 64, MG_CC = 48;   // kernels are built for 32 and 64 map codes
 
 struct MgArgs {
   const void* f; int f_ld, f_coff; const void* wl; int w_ld, w_coff;   // features [B][N][*], logits [B][N][*]
@@ -45,11 +45,12 @@ struct MgArgs {
   int B, K, C; int64_t N;
 };
 
-template <typename T>
+template <typename T, int MG_K>
 __global__ void __launch_bounds__(MG_T) mapgen_fwd_kernel(MgArgs a) {
-  __shared__ float s_e[MG_T][MG_K + 1];
-  __shared__ float s_f[MG_T][MG_CC + 1];
-  __shared__ float s_max[5][MG_K];
+  extern __shared__ float mg_sm[];
+  float (*s_e)[MG_K + 1] = reinterpret_cast<float (*)[MG_K + 1]>(mg_sm);
+  float (*s_f)[MG_CC + 1] = reinterpret_cast<float (*)[MG_CC + 1]>(mg_sm + MG_T * (MG_K + 1));
+  float (*s_max)[MG_K] = reinterpret_cast<float (*)[MG_K]>(mg_sm + MG_T * (MG_K + 1) + MG_T * (MG_CC + 1));
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, K = a.K, C = a.C;
   const int64_t i = (int64_t)blockIdx.x * MG_T + tid;
   const bool valid = i < a.N;
@@ -112,7 +113,7 @@ __global__ void mapgen_merge_kernel(MgArgs a, int nblk) {
 }
 
 // backward: p_jk = exp(w_jk - gmax_k)/gsum_k ; df_j = sum_k p_jk dmap_k ; dw_jk = p_jk (<dmap_k, f_j> - <dmap_k, map_k>)
-template <typename T>
+template <typename T, int MG_K>
 __global__ void __launch_bounds__(MG_T) mapgen_bwd_kernel(MgArgs a) {
   extern __shared__ float sm[];
   const int K = a.K, C = a.C, b = blockIdx.y, tid = threadIdx.x;
@@ -357,87 +358,109 @@ __global__ void gelu_kernel(const T* x, const T* dy, T* out, int64_t n) {
   }
 }
 
-// ------------------------------------------------------------------ MHSA over L <= 128 tokens, dim_head 32
+// ------------------------------------------------------------------ MHSA over L <= 192 tokens, dim_head 32
 // qkv [B][L][3*inner], channel = which*inner + h*32 + d ('b l (heads dim_head)', trans_layers.py:58-66);
 // out [B][L][inner] with channel h*32 + d (rearrange2 really yields (heads dim_head)).
-constexpr int MH_D = 32;
+constexpr int MH_D = 32, MH_RT = 64;       // head dim; query rows per score tile
+// One block per (head, batch).  q/k/v (and dO) of the head live in shared memory; the L x L scores are walked in
+// tiles of MH_RT query rows so L = 192 (three 4x4x4 maps) fits; dK/dV accumulate in shared fp32 across the tiles.
 template <typename T>
 __global__ void mhsa_kernel(const T* qkv, const T* dout, T* out, T* dqkv, int L, int heads, float scale) {
   extern __shared__ float sm[];
   const int inner = heads * MH_D, h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  float* s_q = sm; float* s_k = s_q + L * (MH_D + 1); float* s_v = s_k + L * (MH_D + 1);
-  float* s_p = s_v + L * (MH_D + 1);                 // [L][L+1]
-  float* s_do = s_p + L * (L + 1);                   // [L][33] (backward only)
+  const int P33 = MH_D + 1;
+  float* s_q = sm; float* s_k = s_q + L * P33; float* s_v = s_k + L * P33;
+  float* s_p = s_v + L * P33;                        // [MH_RT][L+1]
+  float* s_do = s_p + MH_RT * (L + 1);               // backward only: [L][33], then dK and dV accumulators
+  float* s_dk = s_do + L * P33; float* s_dv = s_dk + L * P33;
+  const bool bwd = dout != nullptr;
   const T* base = qkv + (int64_t)b * L * 3 * inner + h * MH_D;
   for (int o = tid; o < L * MH_D; o += blockDim.x) {
     const int l = o / MH_D, d = o % MH_D;
-    s_q[l * (MH_D + 1) + d] = Elem<T>::ld(base + (int64_t)l * 3 * inner + d);
-    s_k[l * (MH_D + 1) + d] = Elem<T>::ld(base + (int64_t)l * 3 * inner + inner + d);
-    s_v[l * (MH_D + 1) + d] = Elem<T>::ld(base + (int64_t)l * 3 * inner + 2 * inner + d);
-    if (dout) s_do[l * (MH_D + 1) + d] = Elem<T>::ld(dout + ((int64_t)b * L + l) * inner + h * MH_D + d);
+    s_q[l * P33 + d] = Elem<T>::ld(base + (int64_t)l * 3 * inner + d);
+    s_k[l * P33 + d] = Elem<T>::ld(base + (int64_t)l * 3 * inner + inner + d);
+    s_v[l * P33 + d] = Elem<T>::ld(base + (int64_t)l * 3 * inner + 2 * inner + d);
+    if (bwd) {
+      s_do[l * P33 + d] = Elem<T>::ld(dout + ((int64_t)b * L + l) * inner + h * MH_D + d);
+      s_dk[l * P33 + d] = 0.f; s_dv[l * P33 + d] = 0.f;
+    }
   }
   __syncthreads();
-  for (int o = tid; o < L * L; o += blockDim.x) {
-    const int i = o / L, j = o % L;
-    float acc = 0.f;
-#pragma unroll
-    for (int d = 0; d < MH_D; ++d) acc = fmaf(s_q[i * (MH_D + 1) + d], s_k[j * (MH_D + 1) + d], acc);
-    s_p[i * (L + 1) + j] = acc * scale;
-  }
-  __syncthreads();
-  for (int i = tid; i < L; i += blockDim.x) {
-    float m = -INFINITY;
-    for (int j = 0; j < L; ++j) m = fmaxf(m, s_p[i * (L + 1) + j]);
-    float s = 0.f;
-    for (int j = 0; j < L; ++j) { const float e = __expf(s_p[i * (L + 1) + j] - m); s_p[i * (L + 1) + j] = e; s += e; }
-    const float inv = 1.f / s;
-    for (int j = 0; j < L; ++j) s_p[i * (L + 1) + j] *= inv;
-  }
-  __syncthreads();
-  if (!dout) {
-    for (int o = tid; o < L * MH_D; o += blockDim.x) {
-      const int i = o / MH_D, d = o % MH_D;
+  T* dbase = bwd ? dqkv + (int64_t)b * L * 3 * inner + h * MH_D : nullptr;
+  for (int r0 = 0; r0 < L; r0 += MH_RT) {
+    const int rows = min(MH_RT, L - r0);
+    for (int o = tid; o < rows * L; o += blockDim.x) {
+      const int i = o / L, j = o % L;
       float acc = 0.f;
-      for (int j = 0; j < L; ++j) acc = fmaf(s_p[i * (L + 1) + j], s_v[j * (MH_D + 1) + d], acc);
-      Elem<T>::st(out + ((int64_t)b * L + i) * inner + h * MH_D + d, acc);
-    }
-    return;
-  }
-  T* dbase = dqkv + (int64_t)b * L * 3 * inner + h * MH_D;
-  // dV = P^T dO
-  for (int o = tid; o < L * MH_D; o += blockDim.x) {
-    const int j = o / MH_D, d = o % MH_D;
-    float acc = 0.f;
-    for (int i = 0; i < L; ++i) acc = fmaf(s_p[i * (L + 1) + j], s_do[i * (MH_D + 1) + d], acc);
-    Elem<T>::st(dbase + (int64_t)j * 3 * inner + 2 * inner + d, acc);
-  }
-  __syncthreads();
-  // dS = P o (dP - rowsum(dP o P)), dP = dO V^T   (written over P row by row)
-  for (int i = tid; i < L; i += blockDim.x) {
-    float t = 0.f;
-    for (int j = 0; j < L; ++j) {
-      float dp = 0.f;
 #pragma unroll
-      for (int d = 0; d < MH_D; ++d) dp = fmaf(s_do[i * (MH_D + 1) + d], s_v[j * (MH_D + 1) + d], dp);
-      t = fmaf(dp, s_p[i * (L + 1) + j], t);
+      for (int d = 0; d < MH_D; ++d) acc = fmaf(s_q[(r0 + i) * P33 + d], s_k[j * P33 + d], acc);
+      s_p[i * (L + 1) + j] = acc * scale;
     }
-    for (int j = 0; j < L; ++j) {
-      float dp = 0.f;
+    __syncthreads();
+    for (int i = tid; i < rows; i += blockDim.x) {
+      float m = -INFINITY;
+      for (int j = 0; j < L; ++j) m = fmaxf(m, s_p[i * (L + 1) + j]);
+      float sum = 0.f;
+      for (int j = 0; j < L; ++j) { const float e = __expf(s_p[i * (L + 1) + j] - m); s_p[i * (L + 1) + j] = e; sum += e; }
+      const float inv = 1.f / sum;
+      for (int j = 0; j < L; ++j) s_p[i * (L + 1) + j] *= inv;
+    }
+    __syncthreads();
+    if (!bwd) {
+      for (int o = tid; o < rows * MH_D; o += blockDim.x) {
+        const int i = o / MH_D, d = o % MH_D;
+        float acc = 0.f;
+        for (int j = 0; j < L; ++j) acc = fmaf(s_p[i * (L + 1) + j], s_v[j * P33 + d], acc);
+        Elem<T>::st(out + ((int64_t)b * L + r0 + i) * inner + h * MH_D + d, acc);
+      }
+      __syncthreads();
+      continue;
+    }
+    // dV += P^T dO over this tile's rows
+    for (int o = tid; o < L * MH_D; o += blockDim.x) {
+      const int j = o / MH_D, d = o % MH_D;
+      float acc = 0.f;
+      for (int i = 0; i < rows; ++i) acc = fmaf(s_p[i * (L + 1) + j], s_do[(r0 + i) * P33 + d], acc);
+      s_dv[j * P33 + d] += acc;
+    }
+    __syncthreads();
+    // dS = P o (dP - rowsum(dP o P)) * scale, dP = dO V^T   (written over P row by row)
+    for (int i = tid; i < rows; i += blockDim.x) {
+      float t = 0.f;
+      for (int j = 0; j < L; ++j) {
+        float dp = 0.f;
 #pragma unroll
-      for (int d = 0; d < MH_D; ++d) dp = fmaf(s_do[i * (MH_D + 1) + d], s_v[j * (MH_D + 1) + d], dp);
-      s_p[i * (L + 1) + j] *= (dp - t) * scale;
+        for (int d = 0; d < MH_D; ++d) dp = fmaf(s_do[(r0 + i) * P33 + d], s_v[j * P33 + d], dp);
+        t = fmaf(dp, s_p[i * (L + 1) + j], t);
+      }
+      for (int j = 0; j < L; ++j) {
+        float dp = 0.f;
+#pragma unroll
+        for (int d = 0; d < MH_D; ++d) dp = fmaf(s_do[(r0 + i) * P33 + d], s_v[j * P33 + d], dp);
+        s_p[i * (L + 1) + j] *= (dp - t) * scale;
+      }
     }
+    __syncthreads();
+    for (int o = tid; o < rows * MH_D; o += blockDim.x) {          // dQ rows of this tile
+      const int i = o / MH_D, d = o % MH_D;
+      float aq = 0.f;
+      for (int j = 0; j < L; ++j) aq = fmaf(s_p[i * (L + 1) + j], s_k[j * P33 + d], aq);
+      Elem<T>::st(dbase + (int64_t)(r0 + i) * 3 * inner + d, aq);
+    }
+    for (int o = tid; o < L * MH_D; o += blockDim.x) {             // dK += dS^T Q over this tile's rows
+      const int j = o / MH_D, d = o % MH_D;
+      float ak = 0.f;
+      for (int i = 0; i < rows; ++i) ak = fmaf(s_p[i * (L + 1) + j], s_q[(r0 + i) * P33 + d], ak);
+      s_dk[j * P33 + d] += ak;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int o = tid; o < L * MH_D; o += blockDim.x) {
-    const int i = o / MH_D, d = o % MH_D;
-    float aq = 0.f, ak = 0.f;
-    for (int j = 0; j < L; ++j) {
-      aq = fmaf(s_p[i * (L + 1) + j], s_k[j * (MH_D + 1) + d], aq);
-      ak = fmaf(s_p[j * (L + 1) + i], s_q[j * (MH_D + 1) + d], ak);
+  if (bwd) {
+    for (int o = tid; o < L * MH_D; o += blockDim.x) {
+      const int j = o / MH_D, d = o % MH_D;
+      Elem<T>::st(dbase + (int64_t)j * 3 * inner + inner + d, s_dk[j * P33 + d]);
+      Elem<T>::st(dbase + (int64_t)j * 3 * inner + 2 * inner + d, s_dv[j * P33 + d]);
     }
-    Elem<T>::st(dbase + (int64_t)i * 3 * inner + d, aq);
-    Elem<T>::st(dbase + (int64_t)i * 3 * inner + inner + d, ak);
   }
 }
 
@@ -471,13 +494,23 @@ extern "C" int b200seg_mapgen_fwd(const void* f, int f_ld, int f_coff, const voi
                                   void* map, float* colstat, float* workspace, int B, int64_t N, int K, int C,
                                   int dtype, void* stream) {
   if (!f || !wl || !map || !colstat || !workspace || B <= 0 || N <= 0 || K <= 0 || C <= 0 || !ok_dtype(dtype)) return B200SEG_EINVAL;
-  if (K > MG_K) return B200SEG_EUNSUPPORTED;
+  if (K > MG_KCAP) return B200SEG_EUNSUPPORTED;
   MgArgs a; memset(&a, 0, sizeof(a));
   a.f = f; a.f_ld = f_ld; a.f_coff = f_coff; a.wl = wl; a.w_ld = w_ld; a.w_coff = w_coff; a.map = map; a.map_ld = C;
   a.colstat = colstat; a.partial = workspace; a.B = B; a.N = N; a.K = K; a.C = C;
   const int nblk = (int)((N + MG_T - 1) / MG_T);
   cudaStream_t st = as_stream(stream);
-  DISPATCH_T(dtype, mapgen_fwd_kernel<T><<<dim3(nblk, B), MG_T, 0, st>>>(a); mapgen_merge_kernel<T><<<dim3(K, B), 128, 0, st>>>(a, nblk));
+  const int KC = K <= 32 ? 32 : 64;
+  const size_t fsm = sizeof(float) * ((size_t)MG_T * (KC + 1) + MG_T * (MG_CC + 1) + 5 * KC);
+#define B200_MAPGEN_FWD(TT, KK)                                                                                \
+  do {                                                                                                         \
+    B200_CUDA(cudaFuncSetAttribute(mapgen_fwd_kernel<TT, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm)); \
+    mapgen_fwd_kernel<TT, KK><<<dim3(nblk, B), MG_T, fsm, st>>>(a);                                            \
+    mapgen_merge_kernel<TT><<<dim3(K, B), 128, 0, st>>>(a, nblk);                                              \
+  } while (0)
+  if (dtype == B200SEG_F16) { if (KC == 32) B200_MAPGEN_FWD(__half, 32); else B200_MAPGEN_FWD(__half, 64); }
+  else { if (KC == 32) B200_MAPGEN_FWD(float, 32); else B200_MAPGEN_FWD(float, 64); }
+#undef B200_MAPGEN_FWD
   B200_CHECK_LAUNCH("mapgen_fwd");
   return B200SEG_OK;
 }
@@ -487,7 +520,7 @@ extern "C" int b200seg_mapgen_bwd(const void* f, int f_ld, int f_coff, const voi
                                   void* df, int df_ld, int df_coff, void* dwl, int dw_ld, int dw_coff, int dw_pad,
                                   int B, int64_t N, int K, int C, int dtype, void* stream) {
   if (!f || !wl || !map || !colstat || !dmap || !df || !dwl || B <= 0 || N <= 0 || !ok_dtype(dtype)) return B200SEG_EINVAL;
-  if (K > MG_K || dw_pad > MG_K || dw_pad < K || C % 8 || f_ld % 8 || f_coff % 8 || df_ld % 8 || df_coff % 8) return B200SEG_EUNSUPPORTED;
+  if (K > MG_KCAP || dw_pad > MG_KCAP || dw_pad < K || C % 8 || f_ld % 8 || f_coff % 8 || df_ld % 8 || df_coff % 8) return B200SEG_EUNSUPPORTED;
   const size_t smem = sizeof(float) * ((size_t)K * C + 3 * K);
   if (smem > 200 * 1024) return B200SEG_EUNSUPPORTED;
   MgArgs a; memset(&a, 0, sizeof(a));
@@ -497,13 +530,15 @@ extern "C" int b200seg_mapgen_bwd(const void* f, int f_ld, int f_coff, const voi
   a.B = B; a.N = N; a.K = K; a.C = C;
   const int nblk = (int)((N + MG_T - 1) / MG_T);
   cudaStream_t st = as_stream(stream);
-  if (dtype == B200SEG_F16) {
-    B200_CUDA(cudaFuncSetAttribute(mapgen_bwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mapgen_bwd_kernel<__half><<<dim3(nblk, B), MG_T, smem, st>>>(a);
-  } else {
-    B200_CUDA(cudaFuncSetAttribute(mapgen_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mapgen_bwd_kernel<float><<<dim3(nblk, B), MG_T, smem, st>>>(a);
-  }
+  const int KC = dw_pad <= 32 ? 32 : 64;
+#define B200_MAPGEN_BWD(TT, KK)                                                                                \
+  do {                                                                                                         \
+    B200_CUDA(cudaFuncSetAttribute(mapgen_bwd_kernel<TT, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mapgen_bwd_kernel<TT, KK><<<dim3(nblk, B), MG_T, smem, st>>>(a);                                           \
+  } while (0)
+  if (dtype == B200SEG_F16) { if (KC == 32) B200_MAPGEN_BWD(__half, 32); else B200_MAPGEN_BWD(__half, 64); }
+  else { if (KC == 32) B200_MAPGEN_BWD(float, 32); else B200_MAPGEN_BWD(float, 64); }
+#undef B200_MAPGEN_BWD
   B200_CHECK_LAUNCH("mapgen_bwd");
   return B200SEG_OK;
 }
@@ -588,8 +623,8 @@ extern "C" int b200seg_mhsa(const void* qkv, const void* dout, void* out, void* 
                             float scale, int dtype, void* stream) {
   if (!qkv || B <= 0 || L <= 0 || heads <= 0 || !ok_dtype(dtype)) return B200SEG_EINVAL;
   if ((dout == nullptr) == (out == nullptr) || (dout && !dqkv)) return B200SEG_EINVAL;
-  if (dim_head != MH_D || L > 128) return B200SEG_EUNSUPPORTED;
-  const size_t smem = sizeof(float) * ((size_t)4 * L * (MH_D + 1) + (size_t)L * (L + 1));
+  if (dim_head != MH_D || L > 192) return B200SEG_EUNSUPPORTED;
+  const size_t smem = sizeof(float) * ((size_t)(dout ? 6 : 3) * L * (MH_D + 1) + (size_t)MH_RT * (L + 1));
   if (dtype == B200SEG_F16) {
     B200_CUDA(cudaFuncSetAttribute(mhsa_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mhsa_kernel<__half><<<dim3(heads, B), 256, smem, as_stream(stream)>>>((const __half*)qkv, (const __half*)dout, (__half*)out, (__half*)dqkv, L, heads, scale);

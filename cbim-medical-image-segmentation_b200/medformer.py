@@ -5,7 +5,7 @@ Same constructor arguments, the same module tree / parameter registration order,
 (SURVEY.md §8b).  The forward is written against libb200seg only: dense convs on the tcgen05 path, depthwise convs,
 B-MHA, map generation, SE, the token transformer — each a torch.autograd.Function from medformer_ops.py / ops.py.
 Supported configuration = what every reference MedFormer YAML uses: norm 'in', act 'relu', conv_block
-'BasicBlock', proj_type 'depthwise', dropout 0, dim_head 32 on attention levels, <= 32 map tokens.
+'BasicBlock', proj_type 'depthwise', dropout 0, dim_head 32 on attention levels, <= 64 map tokens.
 """
 import torch
 import torch.nn as nn
@@ -198,8 +198,8 @@ class SemanticMapGeneration(nn.Module):
         self.map_size = tuple(map_size)
         self.map_dim = map_dim
         self.map_code_num = map_size[0] * map_size[1] * map_size[2]
-        if self.map_code_num > 32:
-            raise ValueError("the B200 map kernels handle at most 32 map tokens, got map_size=%s" % (map_size,))
+        if self.map_code_num > 64:
+            raise ValueError("the B200 map kernels handle at most 64 map tokens, got map_size=%s" % (map_size,))
         self.base_proj = nn.Conv3d(feat_dim, map_dim, kernel_size=3, padding=1, bias=False)
         self.semantic_proj = nn.Conv3d(feat_dim, self.map_code_num, kernel_size=3, padding=1, bias=False)
         self._pack = PackedWeights()

@@ -231,7 +231,7 @@ int b200seg_copy_channels(const void* x, int x_dtype, int x_ld, int x_coff,
 /* ---------------------------------------------------------------------------
  * MedFormer bidirectional attention core (B-MHA), medformer_utils.py:63-97
  * (BidirectionAttention.forward between the q/v projections and the output
- * projections).  N = D*H*W feature voxels, M <= 32 semantic-map tokens,
+ * projections).  N = D*H*W feature voxels, M <= 64 semantic-map tokens,
  * dim_head must be 32 (every BASELINE MedFormer level).  All tensors are
  * channels-last with channel index  c = d*heads + h  inside the `inner` block
  * (rearrange1, :43-51):
@@ -282,7 +282,7 @@ int b200seg_dwconv3d_wgrad(const void* x, int x_ld, int x_coff, const double* x_
  *   y[b,d,h,w,q*C+c] = x[b,d*sd+i,h*sh+j,w*sw+k,c], q=(i*sh+j)*sw+k; reverse!=0
  *   scatters y back into x (the gradient).  Do/Ho/Wo are the OUTPUT extents.
  * mapgen: SemanticMapGeneration medformer_utils.py:221-226,
- *   map[b,k,c] = sum_j softmax_j(wl[b,j,k]) * f[b,j,c]   (K <= 32 map codes),
+ *   map[b,k,c] = sum_j softmax_j(wl[b,j,k]) * f[b,j,c]   (K <= 64 map codes),
  *   colstat float[B][K][2]; bwd writes df and dwl (dw_pad >= K logits channels,
  *   the padding gets zeros) into the gradient of the fused projection output.
  * se_gate: SEBlock conv_layers.py:159-174 on the channel means taken from IN
@@ -293,7 +293,7 @@ int b200seg_dwconv3d_wgrad(const void* x, int x_ld, int x_coff, const double* x_
  * layernorm: nn.LayerNorm(C, eps) trans_layers.py:36-41 over rows [R][C];
  *   mean_rstd float[R][2]; bwd accumulates (+=) dgamma/dbeta.
  * gelu: exact erf GELU trans_layers.py:22; dy==NULL -> forward, else out=dy*gelu'(x).
- * mhsa: Attention core trans_layers.py:84-93 for L<=128 tokens, dim_head 32;
+ * mhsa: Attention core trans_layers.py:84-93 for L<=192 tokens, dim_head 32;
  *   qkv [B][L][3*inner] ('(heads dim_head)' order), out [B][L][inner];
  *   forward when dout==NULL, otherwise writes dqkv.
  * ------------------------------------------------------------------------- */

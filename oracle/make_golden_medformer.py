@@ -16,6 +16,7 @@ from oracle.make_golden import import_reference          # noqa: E402
 from oracle import medformer_ops as mops                 # noqa: E402
 
 BIATTN = {  # name: (B, heads, feat spatial, map spatial, feat_dim, map_dim, seed)
+    "biattn_d": (1, 2, (3, 5, 9), (4, 4, 4), 16, 24, 24),
     "biattn_a": (2, 2, (4, 6, 5), (3, 3, 3), 24, 16, 21),
     "biattn_b": (1, 4, (5, 6, 7), (3, 3, 3), 32, 32, 22),
     "biattn_c": (1, 1, (2, 3, 67), (2, 2, 2), 8, 8, 23),
@@ -26,8 +27,9 @@ MODELS = {   # name: (ctor kwargs, classes, input BxDxHxW)
                            num_heads=[1, 4, 8, 10, 8, 4, 1, 1], fusion_depth=2, fusion_dim=320, fusion_heads=10,
                            kernel_size=[[1, 3, 3], [1, 3, 3], [3, 3, 3], [3, 3, 3], [3, 3, 3]],
                            scale=[[1, 2, 2], [1, 2, 2], [2, 2, 2], [2, 2, 2]], aux_loss=True), 14, (1, 16, 32, 32)),
-    # a variant: conv blocks on attention levels, 18 map tokens, isotropic scales, no aux head, batch 2
-    "medformer_var": (dict(map_size=[2, 3, 3], conv_num=[1, 1, 0, 0, 0, 1, 1, 1], trans_num=[0, 1, 2, 1, 1, 1, 0, 0],
+    # a variant: conv blocks on attention levels, 64 map tokens (the 4x4x4 maps of the AMOS / KiTS YAMLs -> 192 fused
+    # tokens), isotropic scales, no aux head, batch 2
+    "medformer_var": (dict(map_size=[4, 4, 4], conv_num=[1, 1, 0, 0, 0, 1, 1, 1], trans_num=[0, 1, 2, 1, 1, 1, 0, 0],
                            num_heads=[1, 4, 8, 10, 8, 4, 1, 1], fusion_depth=1, fusion_dim=128, fusion_heads=4,
                            kernel_size=[[3, 3, 3]] * 5, scale=[[2, 2, 2]] * 4, aux_loss=False), 4, (2, 16, 32, 32)),
 }

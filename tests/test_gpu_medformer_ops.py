@@ -38,7 +38,7 @@ def _run_biattn(ops, fqv, mqv, heads, dfo, dmo, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
-@pytest.mark.parametrize("name", ["biattn_a", "biattn_b", "biattn_c"])
+@pytest.mark.parametrize("name", ["biattn_a", "biattn_b", "biattn_c", "biattn_d"])
 def test_biattn_golden(ops, name, dtype):
     g = load_golden(name)
     fo, mo, dfqv, dmqv = _run_biattn(ops, g["fqv"], g["mqv"], g["heads"], g["dfo"], g["dmo"], dtype)
@@ -50,7 +50,9 @@ def test_biattn_golden(ops, name, dtype):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
 @pytest.mark.parametrize("B,heads,fs,ms", [(2, 4, (12, 12, 12), (3, 3, 3)),      # BCV level shape, several blocks
                                             (1, 1, (3, 5, 131), (1, 1, 1)),        # single token, ragged block
-                                            (1, 10, (6, 6, 6), (2, 4, 4))])        # 320-channel level, M = 32
+                                            (1, 10, (6, 6, 6), (2, 4, 4)),         # 320-channel level, M = 32
+                                            (2, 4, (10, 12, 12), (4, 4, 4)),       # 64 tokens (AMOS / KiTS map size)
+                                            (1, 8, (3, 3, 5), (3, 4, 4))])         # 48 tokens in the 64-row build
 def test_biattn_vs_oracle(ops, dtype, B, heads, fs, ms):
     torch.manual_seed(5)
     inner = 32 * heads
@@ -73,9 +75,9 @@ def test_biattn_rejects_unsupported(ops):
     with pytest.raises(ops._lib.B200SegError):
         ops.biattn_fwd(f, m, 1, dim_head=64)                       # dim_head != 32 -> loud, no fallback
     f = torch.zeros(1, 2, 2, 2, 64, device="cuda")
-    m = torch.zeros(1, 4, 4, 4, 64, device="cuda")
+    m = torch.zeros(1, 2, 6, 6, 64, device="cuda")
     with pytest.raises(ops._lib.B200SegError):
-        ops.biattn_fwd(f, m, 1)                                    # 64 map tokens > 32
+        ops.biattn_fwd(f, m, 1)                                    # 72 map tokens (ACDC YAML) > 64
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])

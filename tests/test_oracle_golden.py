@@ -59,7 +59,7 @@ def test_dice_alpha_is_differentiable():
     assert abs(fd.item() - ga.view(-1)[17].item()) < 5e-3 * abs(fd.item()) + 1e-9
 
 
-@pytest.mark.parametrize("name", ["biattn_a", "biattn_b", "biattn_c"])
+@pytest.mark.parametrize("name", ["biattn_a", "biattn_b", "biattn_c", "biattn_d"])
 def test_biattn_oracle_matches_reference_fixture(name):
     """fixtures captured at the projection boundaries of the unmodified BidirectionAttention module."""
     from oracle import medformer_ops as mops
