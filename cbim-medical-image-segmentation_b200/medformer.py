@@ -21,9 +21,11 @@ EPS_BLOCK = 1e-4      # ConvNormAct's norm(in_ch, eps=1e-4), conv_layers.py:40
 EPS_PLAIN = 1e-5      # bare norm(dim): PatchMerging.norm :158, BidirectionAttentionBlock.norm1/2 :107-108
 
 
-def _conv(pack, x, stats, weights, ksize, act=ACT_NONE, bias=None, residual=None, co_pad=0, eps=EPS_BLOCK):
+def _conv(pack, x, stats, weights, ksize, act=ACT_NONE, bias=None, residual=None, co_pad=0, eps=EPS_BLOCK,
+          want_stats=False):
+    """want_stats: produce the IN sums of the output (only when its consumer normalises it)."""
     packs = pack.get(list(weights), x.dtype, x.shape[0], co_pad)
-    return ConvFn.apply(x, stats, residual, bias, packs, tuple(ksize), act, co_pad, eps, *weights)
+    return ConvFn.apply(x, stats, residual, bias, packs, tuple(ksize), act, co_pad, eps, want_stats, *weights)
 
 
 def _need_in(norm, act):
@@ -45,10 +47,10 @@ class DepthwiseSeparableConv(nn.Module):
         self.pointwise = nn.Conv3d(in_ch, out_ch, kernel_size=1, bias=False)
         self._pack = PackedWeights()
 
-    def forward(self, x, stats, eps, residual=None):
+    def forward(self, x, stats, eps, residual=None, want_stats=False):
         """pointwise(depthwise(IN(x))) (+residual); stats=None means the input is used raw."""
-        y, _ = DwConvFn.apply(x, stats, self.depthwise.weight, ACT_NONE, eps)
-        return _conv(self._pack, y, None, [self.pointwise.weight], (1, 1, 1), residual=residual)
+        y, _ = DwConvFn.apply(x, stats, self.depthwise.weight, ACT_NONE, eps, False)
+        return _conv(self._pack, y, None, [self.pointwise.weight], (1, 1, 1), residual=residual, want_stats=want_stats)
 
 
 class BidirectionAttention(nn.Module):
@@ -76,7 +78,7 @@ class BidirectionAttention(nn.Module):
         m_stats = ops.instnorm_stats(smap, 0, smap.shape[-1])                              # norm2, :127
         mqv, _ = _conv(self._pack_mqv, smap, m_stats, [self.map_qv.weight], (1, 1, 1), eps=EPS_PLAIN)   # :68
         fo, mo = BiAttnFn.apply(fqv, mqv, self.heads, self.dim_head)                        # :70-91
-        out, out_stats = self.feat_out(fo, None, EPS_PLAIN, residual=feat_residual)         # :95 (+ :131)
+        out, out_stats = self.feat_out(fo, None, EPS_PLAIN, residual=feat_residual, want_stats=True)   # :95 (+ :131)
         if isinstance(self.map_out, nn.Identity):
             mapp = AddFn.apply(mo, map_residual)
         else:
@@ -119,10 +121,11 @@ class MBConv(nn.Module):
         self._pack_p = PackedWeights()
 
     def forward(self, x, stats):
-        e, e_st = _conv(self._pack_e, x, stats, [self.expand_proj.conv.weight], (1, 1, 1), act=ACT_RELU)     # :225
-        d, d_st = DwConvFn.apply(e, e_st, self.depthwise.conv.weight, ACT_RELU, EPS_BLOCK)                    # :226
+        e, e_st = _conv(self._pack_e, x, stats, [self.expand_proj.conv.weight], (1, 1, 1), act=ACT_RELU, want_stats=True)  # :225
+        d, d_st = DwConvFn.apply(e, e_st, self.depthwise.conv.weight, ACT_RELU, EPS_BLOCK, True)              # :226
         s, s_st = self.se(d, d_st)                                                                            # :228
-        return _conv(self._pack_p, s, s_st, [self.pointwise.conv.weight], (1, 1, 1), act=ACT_NONE, residual=x)  # :230-234
+        return _conv(self._pack_p, s, s_st, [self.pointwise.conv.weight], (1, 1, 1), act=ACT_NONE, residual=x,
+                     want_stats=True)                                                                     # :230-234
 
 
 class BidirectionAttentionBlock(nn.Module):
@@ -165,7 +168,7 @@ class PatchMerging(nn.Module):
 
     def forward(self, x):
         y, y_st = SpaceToDepthFn.apply(x, self.down_scale)            # :164-172
-        return self.reduction(y, y_st, EPS_PLAIN)                     # :173-174
+        return self.reduction(y, y_st, EPS_PLAIN, want_stats=True)    # :173-174
 
 
 class BasicLayer(nn.Module):

@@ -16,10 +16,11 @@ from .ops import (IN_EPS, _dt, _need_cuda, _p, _stream, conv3d_fwd, conv3d_wgrad
 class ConvFn(torch.autograd.Function):
     """y = conv(act(IN(x))) (+bias) (+residual), `ConvNormAct(preact=True)` conv_layers.py:46-53 with any of
     norm/act switched off; several weights sharing the input run as one GEMM (outputs concatenated).  `co_pad`
-    zero output channels are appended by the packer.  Returns (y, IN sums of y)."""
+    zero output channels are appended by the packer.  Returns (y, IN sums of y or None when the consumer does not
+    normalise y: the statistics butterfly is a large part of the conv epilogue)."""
 
     @staticmethod
-    def forward(ctx, x, x_stats, residual, bias, packs, ksize, act, co_pad, eps, *weights):
+    def forward(ctx, x, x_stats, residual, bias, packs, ksize, act, co_pad, eps, want_stats, *weights):
         _need_cuda(x)
         Cin = weights[0].shape[1]
         couts = [w.shape[0] for w in weights]
@@ -30,11 +31,13 @@ class ConvFn(torch.autograd.Function):
             bias_k[:Cout - co_pad] = bias.detach().float()
         else:
             bias_k = None if bias is None else bias.detach().float().contiguous()
-        y, y_stats = conv3d_fwd(x, 0, Cin, x_stats, act, w_fwd, Cout, ksize, bias=bias_k, residual=residual, eps=eps)
+        y, y_stats = conv3d_fwd(x, 0, Cin, x_stats, act, w_fwd, Cout, ksize, bias=bias_k, residual=residual, eps=eps,
+                                want_stats=want_stats)
         ctx.save_for_backward(x, x_stats, w_bwd[0])
         ctx.meta = (Cin, Cout, couts, tuple(ksize), act, w_bwd[1], bias is not None, residual is not None,
                     ctx.needs_input_grad[0], eps)
-        ctx.mark_non_differentiable(y_stats)
+        if y_stats is not None:
+            ctx.mark_non_differentiable(y_stats)
         return y, y_stats
 
     @staticmethod
@@ -57,7 +60,7 @@ class ConvFn(torch.autograd.Function):
                 dx, _ = conv3d_fwd(dy, 0, Cout, None, ACT_NONE, (w_bwd, algo_b), Cin, ksize, want_stats=False)
         if has_bias:
             db = db[:off]
-        return (dx, None, dy if has_res else None, db if has_bias else None, None, None, None, None, None, *dws)
+        return (dx, None, dy if has_res else None, db if has_bias else None, None, None, None, None, None, None, *dws)
 
 
 class DwConvFn(torch.autograd.Function):
@@ -66,14 +69,15 @@ class DwConvFn(torch.autograd.Function):
     groups == channels, conv_layers.py:208)."""
 
     @staticmethod
-    def forward(ctx, x, x_stats, weight, act, eps):
+    def forward(ctx, x, x_stats, weight, act, eps, want_stats=True):
         ks = tuple(weight.shape[2:])
         wt = weight.detach().reshape(weight.shape[0], -1).t().contiguous().float()
         x = x.contiguous()
-        y, y_stats = dwconv3d(x, wt, ks, x_stats=x_stats, act=act, want_stats=True, eps=eps)
+        y, y_stats = dwconv3d(x, wt, ks, x_stats=x_stats, act=act, want_stats=want_stats, eps=eps)
         ctx.save_for_backward(x, x_stats, wt)
         ctx.meta = (ks, act, weight.dtype, eps)
-        ctx.mark_non_differentiable(y_stats)
+        if y_stats is not None:
+            ctx.mark_non_differentiable(y_stats)
         return y, y_stats
 
     @staticmethod
@@ -89,7 +93,7 @@ class DwConvFn(torch.autograd.Function):
             dx = in_bwd_apply(g2, x, 0, C, x_stats, bst, eps=eps)
         else:
             dx = g
-        return dx, None, dw.t().reshape(C, 1, *ks).to(wdtype), None, None
+        return dx, None, dw.t().reshape(C, 1, *ks).to(wdtype), None, None, None
 
 
 class SpaceToDepthFn(torch.autograd.Function):
