@@ -44,7 +44,6 @@ struct WgParams {
   int tiles_h, tiles_w, nvt;
   int tmem_cols;
   int smem_bar_off;
-  int swap_lbo_sbo;                        // debug knob (B200SEG_WGRAD_SWAP)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -261,7 +260,6 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
       const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NTC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       uint32_t dy_lbo = 128u, dy_sbo = (uint32_t)p.dy_plane;
       uint32_t a_lbo = (uint32_t)p.HALO_W * 16u, a_sbo = (uint32_t)p.a_plane;
-      if (p.swap_lbo_sbo) { uint32_t t1 = dy_lbo; dy_lbo = dy_sbo; dy_sbo = t1; t1 = a_lbo; a_lbo = a_sbo; a_sbo = t1; }
       // lean issue loop (this one thread feeds the tensor core): descriptor templates + constant adds
       const uint64_t dy_tmpl = make_desc(0, dy_lbo, dy_sbo), a_tmpl = make_desc(0, a_lbo, a_sbo);
       const uint32_t a_kstep = (2u * (uint32_t)p.HALO_W * 16u) >> 4;    // two voxel rows per K=16 step
@@ -397,8 +395,6 @@ bool fill_params(const WgradArgs& a, WgParams& p) {
   if (pow2 > 512) return false;
   p.tmem_cols = pow2;
   p.smem_bar_off = p.NS * p.stage_bytes;
-  const char* sw = getenv("B200SEG_WGRAD_SWAP");
-  p.swap_lbo_sbo = (sw && sw[0] == '1') ? 1 : 0;
   return true;
 }
 

@@ -64,3 +64,25 @@ def test_same_seed_same_init_as_holder_modules():
     torch.manual_seed(3)
     b = b200seg.get_model(_args())
     assert all(torch.equal(p, q) for p, q in zip(a.parameters(), b.parameters()))
+
+
+def test_get_model_dispatches_medformer_with_reference_argument_list():
+    """model/utils.py:95 — the MedFormer branch of the factory, driven by a config namespace like the BCV YAML."""
+    import types
+    import b200seg
+    args = types.SimpleNamespace(
+        dimension='3d', model='medformer', in_chan=1, classes=14, base_chan=32, map_size=[3, 3, 3],
+        conv_block='BasicBlock', conv_num=[2, 0, 0, 0, 0, 0, 2, 2], trans_num=[0, 2, 4, 6, 4, 2, 0, 0],
+        num_heads=[1, 4, 8, 10, 8, 4, 1, 1], fusion_depth=2, fusion_dim=320, fusion_heads=10, expansion=4, attn_drop=0.,
+        proj_drop=0., proj_type='depthwise', norm='in', act='relu',
+        kernel_size=[[1, 3, 3], [1, 3, 3], [3, 3, 3], [3, 3, 3], [3, 3, 3]],
+        down_scale=[[1, 2, 2], [1, 2, 2], [2, 2, 2], [2, 2, 2]], aux_loss=True)
+    net = b200seg.get_model(args)
+    assert isinstance(net, b200seg.MedFormer) and len(net.state_dict()) == 300
+    import pytest
+    args.map_size = [2, 6, 6]                      # ACDC YAML: 72 tokens -> loud, not silent
+    with pytest.raises(ValueError):
+        b200seg.get_model(args)
+    args.map_size, args.act = [3, 3, 3], 'gelu'
+    with pytest.raises(ValueError):
+        b200seg.get_model(args)

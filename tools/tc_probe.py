@@ -62,7 +62,7 @@ def run_wprobe(i):
     a, b = out[_lib.ALGO_TC], out[_lib.ALGO_DIRECT]
     err = ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
     ok = err < 2e-3
-    print("wprobe %2d %-32s swap=%s dw_rel_err %.3e %s" % (i, name, os.environ.get("B200SEG_WGRAD_SWAP", "0"), err, "OK" if ok else "FAIL"), flush=True)
+    print("wprobe %2d %-32s dw_rel_err %.3e %s" % (i, name, err, "OK" if ok else "FAIL"), flush=True)
     if not ok:
         e = (a - b).abs()
         print("   tc absmax %.4f direct absmax %.4f nonfinite=%d" % (a.abs().max(), b.abs().max(), (~torch.isfinite(a)).sum()))
