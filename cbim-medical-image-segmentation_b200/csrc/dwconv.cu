@@ -38,7 +38,7 @@ __host__ __device__ inline Tile make_tile(int rb, int D, int H, int Wn) {
 template <typename T> struct Raw;
 template <> struct Raw<__half> {
   uint4 u; bool ok;
-  __device__ __forceinline__ void load(const __half* p, bool valid) { ok = valid; u = valid ? *reinterpret_cast<const uint4*>(p) : make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void load(const __half* p, bool valid) { ok = valid; if (valid) u = *reinterpret_cast<const uint4*>(p); }
   __device__ __forceinline__ void get(float (&v)[8]) const {
     const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -49,16 +49,19 @@ template <> struct Raw<float> {
   float4 a, b; bool ok;
   __device__ __forceinline__ void load(const float* p, bool valid) {
     ok = valid;
-    a = valid ? *reinterpret_cast<const float4*>(p) : make_float4(0, 0, 0, 0);
-    b = valid ? *reinterpret_cast<const float4*>(p + 4) : make_float4(0, 0, 0, 0);
+    if (valid) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
   }
   __device__ __forceinline__ void get(float (&v)[8]) const { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
 };
 
-template <typename T>
+// KD/KH/KW > 0 fix the filter extents at compile time (3x3x3 and 1x3x3 cover every reference config: the tap loops
+// unroll and the index arithmetic folds); 0 = run-time extents.  NR: 0 raw input, 1 IN, 2 IN+ReLU, 3 run-time flags.
+template <typename T, int KD, int KH, int KW, int NR>
 __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
   extern __shared__ float sm[];
-  const int C = a.C, taps = a.kd * a.kh * a.kw;
+  const int kd = KD > 0 ? KD : a.kd, kh = KH > 0 ? KH : a.kh, kw = KW > 0 ? KW : a.kw;
+  const int D = a.D, H = a.H, W = a.W, x_ld = a.x_ld, y_ld = a.y_ld;
+  const int C = a.C, taps = kd * kh * kw;
   float* s_w = sm;                         // [taps][C]
   float* s_scale = s_w + taps * C;         // [C]
   float* s_shift = s_scale + C;            // [C]
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
   float* s_sq = s_sum + C;                 // [C]
   const int b = blockIdx.y, tid = threadIdx.x;
   const int c0 = blockIdx.z * C;            // this block's channel slice [c0, c0 + C) of the Ctot-channel layer
-  const double nvox = (double)a.D * a.H * a.W;
+  const double nvox = (double)D * H * W;
   for (int o = tid; o < taps * C; o += blockDim.x) {
     const int t = o / C, c = o % C;
     // [tap][half][cg][4]: a warp's float4 reads (lane = channel group) are contiguous -> no bank conflicts
@@ -80,52 +83,54 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
     s_sum[c] = 0.f; s_sq[c] = 0.f;
   }
   __syncthreads();
-  const int ncg = C >> 3, WR = (a.W + RUN - 1) / RUN;
+  const int ncg = C >> 3, WR = (W + RUN - 1) / RUN;
   const int cg = tid % ncg;                // blockDim.x and the grid stride are multiples of ncg
-  const int pd = a.kd >> 1, ph = a.kh >> 1, pw = a.kw >> 1;
-  const bool norm = a.x_stats != nullptr, relu = a.act == 1;
+  const int pd = kd >> 1, ph = kh >> 1, pw = kw >> 1;
+  const bool norm = NR == 3 ? a.x_stats != nullptr : NR != 0, relu = NR == 3 ? a.act == 1 : NR == 2;
   const float* sc = s_scale + cg;          // element c at sc[c * ncg]; read at the use site (keeps 16 registers free)
   const float* sh = s_shift + cg;
   float tsum[8], tsq[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) { tsum[c] = 0.f; tsq[c] = 0.f; }
-  const T* xb = (const T*)a.x + (int64_t)b * a.D * a.H * a.W * a.x_ld + a.x_coff + c0 + cg * 8;
-  T* yb = (T*)a.y + (int64_t)b * a.D * a.H * a.W * a.y_ld + a.y_coff + c0 + cg * 8;
+  const T* xb = (const T*)a.x + (int64_t)b * D * H * W * x_ld + a.x_coff + c0 + cg * 8;
+  T* yb = (T*)a.y + (int64_t)b * D * H * W * y_ld + a.y_coff + c0 + cg * 8;
   // a block pass covers a compact 2(d) x 4(h) x TWR(w-runs) tile so the 3x3x3 neighbourhoods of its threads
   // overlap in L1 instead of each being fetched from L2
-  const Tile tl = make_tile(blockDim.x / ncg, a.D, a.H, WR);
+  const Tile tl = make_tile(blockDim.x / ncg, D, H, WR);
   const int rl = tid / ncg, lw = rl % tl.tw, lh = (rl / tl.tw) % tl.th, ldp = rl / (tl.tw * tl.th);
   for (int64_t tile = blockIdx.x; tile < tl.ntiles; tile += gridDim.x) {
     const int wr = (int)(tile % tl.nw) * tl.tw + lw;
     const int h = (int)((tile / tl.nw) % tl.nh) * tl.th + lh;
     const int d = (int)(tile / ((int64_t)tl.nw * tl.nh)) * tl.td + ldp;
-    if (wr >= WR || h >= a.H || d >= a.D) continue;
+    if (wr >= WR || h >= H || d >= D) continue;
     const int w0 = wr * RUN;
     float acc[RUN][8];
 #pragma unroll
     for (int o = 0; o < RUN; ++o)
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[o][c] = 0.f;
-    for (int zd = 0; zd < a.kd; ++zd) {
+#pragma unroll
+    for (int zd = 0; zd < (KD > 0 ? KD : MAXK); ++zd) {
       const int id = d + zd - pd;
-      if (id < 0 || id >= a.D) continue;
-      for (int zh = 0; zh < a.kh; ++zh) {
+      if (zd >= kd || (unsigned)id >= (unsigned)D) continue;
+#pragma unroll
+      for (int zh = 0; zh < (KH > 0 ? KH : MAXK); ++zh) {
         const int ih = h + zh - ph;
-        if (ih < 0 || ih >= a.H) continue;
-        const T* row = xb + ((int64_t)id * a.H + ih) * a.W * a.x_ld;
-        const float* wrow = s_w + (zd * a.kh + zh) * a.kw * C + cg * 4;
+        if (zh >= kh || (unsigned)ih >= (unsigned)H) continue;
+        const T* row = xb + ((int64_t)id * H + ih) * W * x_ld;
+        const float* wrow = s_w + (zd * kh + zh) * kw * C + cg * 4;
         // all loads of the row first (independent, in flight together), then the arithmetic
         Raw<T> raw[RUN + MAXK - 1];
 #pragma unroll
         for (int j = 0; j < RUN + MAXK - 1; ++j) {            // input column w0 - pw + j
           const int iw = w0 - pw + j;
-          const bool ok = (j < RUN + a.kw - 1) && iw >= 0 && iw < a.W;
-          raw[j].load(row + (int64_t)(ok ? iw : w0) * a.x_ld, ok);
+          const bool ok = (j < RUN + kw - 1) && (unsigned)iw < (unsigned)W;
+          raw[j].load(row + iw * x_ld, ok);
         }
         float wt[MAXK][8];
 #pragma unroll
         for (int k = 0; k < MAXK; ++k) {
-          if (k < a.kw) {
+          if (k < kw) {
             const float4 w0v = *reinterpret_cast<const float4*>(wrow + k * C), w1v = *reinterpret_cast<const float4*>(wrow + k * C + ncg * 4);
             wt[k][0] = w0v.x; wt[k][1] = w0v.y; wt[k][2] = w0v.z; wt[k][3] = w0v.w;
             wt[k][4] = w1v.x; wt[k][5] = w1v.y; wt[k][6] = w1v.z; wt[k][7] = w1v.w;
@@ -157,11 +162,11 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
         }
       }
     }
-    T* yrow = yb + (((int64_t)d * a.H + h) * a.W + w0) * a.y_ld;
+    T* yrow = yb + (((int64_t)d * H + h) * W + w0) * y_ld;
 #pragma unroll
     for (int o = 0; o < RUN; ++o) {
-      if (w0 + o < a.W) {
-        st8<T>(yrow + (int64_t)o * a.y_ld, acc[o]);
+      if (w0 + o < W) {
+        st8<T>(yrow + o * y_ld, acc[o]);
         if (a.y_stats) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) { const float r2 = Elem<T>::round(acc[o][c]); tsum[c] += r2; tsq[c] = fmaf(r2, r2, tsq[c]); }
@@ -181,17 +186,20 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
 }
 
 // dw[tap][c] += sum_{b,voxel} dy[voxel][c] * a[voxel + tap][c];  grid.y = B * kd (one depth tap per block row)
-template <typename T>
+// KHW: 3 = in-plane extent 3x3 fixed at compile time (every reference config), 0 = run-time extents
+template <typename T, int KHW>
 __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
   extern __shared__ float sm[];
+  const int kh = KHW > 0 ? KHW : a.kh, kw = KHW > 0 ? KHW : a.kw;
+  const int D = a.D, H = a.H, W = a.W, x_ld = a.x_ld, dy_ld = a.dy_ld;
   const int C = a.C;
   float* s_scale = sm;                     // [C]
   float* s_shift = s_scale + C;
   float* s_acc = s_shift + C;              // [kh*kw][C]
   const int b = blockIdx.y / a.kd, zd = blockIdx.y % a.kd, tid = threadIdx.x;
   const int c0 = blockIdx.z * C;
-  const int thw = a.kh * a.kw;
-  const double nvox = (double)a.D * a.H * a.W;
+  const int thw = kh * kw;
+  const double nvox = (double)D * H * W;
   for (int c = tid; c < C; c += blockDim.x) {
     float mean = 0.f, rstd = 1.f;
     if (a.x_stats) stats_to_mean_rstd(a.x_stats + ((int64_t)b * a.Ctot + c0 + c) * 2, nvox, a.eps, mean, rstd);
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
   for (int o = tid; o < thw * C; o += blockDim.x) s_acc[o] = 0.f;
   __syncthreads();
   const int ncg = C >> 3, cg = tid % ncg;
-  const int pd = a.kd >> 1, ph = a.kh >> 1, pw = a.kw >> 1;
+  const int pd = a.kd >> 1, ph = kh >> 1, pw = kw >> 1;
   const bool norm = a.x_stats != nullptr, relu = a.act == 1;
   const float* sc = s_scale + cg;
   const float* sh = s_shift + cg;
@@ -209,9 +217,9 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
   for (int t = 0; t < MAXK * MAXK; ++t)
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
-  const T* xb = (const T*)a.x + (int64_t)b * a.D * a.H * a.W * a.x_ld + a.x_coff + c0 + cg * 8;
-  const T* gb = (const T*)a.dy + (int64_t)b * a.D * a.H * a.W * a.dy_ld + a.dy_coff + c0 + cg * 8;
-  const Tile tl = make_tile(blockDim.x / ncg, a.D, a.H, a.W);
+  const T* xb = (const T*)a.x + (int64_t)b * D * H * W * x_ld + a.x_coff + c0 + cg * 8;
+  const T* gb = (const T*)a.dy + (int64_t)b * D * H * W * dy_ld + a.dy_coff + c0 + cg * 8;
+  const Tile tl = make_tile(blockDim.x / ncg, D, H, W);
   const int rl = tid / ncg, lw = rl % tl.tw, lh = (rl / tl.tw) % tl.th, ldp = rl / (tl.tw * tl.th);
   for (int64_t tile = blockIdx.x; tile < tl.ntiles; tile += gridDim.x) {
     // input-stationary: the thread owns one INPUT vector (normalised once) and meets the 9 output gradients
@@ -220,16 +228,17 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
     const int ih = (int)((tile / tl.nw) % tl.nh) * tl.th + lh;
     const int id = (int)(tile / ((int64_t)tl.nw * tl.nh)) * tl.td + ldp;
     const int d = id - zd + pd;
-    if (iw >= a.W || ih >= a.H || id >= a.D || d < 0 || d >= a.D) continue;
+    if (iw >= W || ih >= H || id >= D || (unsigned)d >= (unsigned)D) continue;
     Raw<T> rx, rg[MAXK * MAXK];
-    rx.load(xb + (((int64_t)id * a.H + ih) * a.W + iw) * a.x_ld, true);
+    rx.load(xb + (((int64_t)id * H + ih) * W + iw) * x_ld, true);
+    const T* gc = gb + (((int64_t)d * H + ih) * W + iw) * dy_ld;      // the centre output voxel; neighbours by 32-bit offsets
 #pragma unroll
     for (int zh = 0; zh < MAXK; ++zh) {
 #pragma unroll
       for (int zw = 0; zw < MAXK; ++zw) {
         const int h = ih - zh + ph, w = iw - zw + pw;
-        const bool ok = zh < a.kh && zw < a.kw && h >= 0 && h < a.H && w >= 0 && w < a.W;
-        rg[zh * MAXK + zw].load(gb + (((int64_t)d * a.H + (ok ? h : ih)) * a.W + (ok ? w : iw)) * a.dy_ld, ok);
+        const bool ok = zh < kh && zw < kw && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W;
+        rg[zh * MAXK + zw].load(gc + ((ph - zh) * W + (pw - zw)) * dy_ld, ok);
       }
     }
     float v[8];
@@ -254,9 +263,9 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
   for (int zh = 0; zh < MAXK; ++zh)
 #pragma unroll
     for (int zw = 0; zw < MAXK; ++zw)
-      if (zh < a.kh && zw < a.kw) {
+      if (zh < kh && zw < kw) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) atomicAdd(&s_acc[(zh * a.kw + zw) * C + cg * 8 + c], acc[zh * MAXK + zw][c]);
+        for (int c = 0; c < 8; ++c) atomicAdd(&s_acc[(zh * kw + zw) * C + cg * 8 + c], acc[zh * MAXK + zw][c]);
       }
   __syncthreads();
   for (int o = tid; o < thw * C; o += blockDim.x)
@@ -303,11 +312,24 @@ extern "C" int b200seg_dwconv3d_fwd(const void* x, int x_ld, int x_coff, const d
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
   const size_t sm = sizeof(float) * ((size_t)taps * chunk + 4 * chunk);
-  if (dtype == B200SEG_F16) {
-    dwconv_fwd_kernel<__half><<<dim3(gx, B, nchunk), threads, sm, st>>>(a);
-  } else {
-    dwconv_fwd_kernel<float><<<dim3(gx, B, nchunk), threads, sm, st>>>(a);
-  }
+  const int nr = !x_stats ? (act ? 3 : 0) : (act == 1 ? 2 : 1);
+  const dim3 grid(gx, B, nchunk);
+#define B200_DW_FWD(TT, A, Bk, Ck, NRk) dwconv_fwd_kernel<TT, A, Bk, Ck, NRk><<<grid, threads, sm, st>>>(a)
+#define B200_DW_FWD_NR(TT, A, Bk, Ck)                                                          \
+  do {                                                                                          \
+    if (nr == 0) B200_DW_FWD(TT, A, Bk, Ck, 0); else if (nr == 1) B200_DW_FWD(TT, A, Bk, Ck, 1); \
+    else if (nr == 2) B200_DW_FWD(TT, A, Bk, Ck, 2); else B200_DW_FWD(TT, A, Bk, Ck, 3);        \
+  } while (0)
+#define B200_DW_FWD_K(TT)                                                                       \
+  do {                                                                                          \
+    if (kd == 3 && kh == 3 && kw == 3) B200_DW_FWD_NR(TT, 3, 3, 3);                             \
+    else if (kd == 1 && kh == 3 && kw == 3) B200_DW_FWD_NR(TT, 1, 3, 3);                        \
+    else B200_DW_FWD(TT, 0, 0, 0, 3);                                                           \
+  } while (0)
+  if (dtype == B200SEG_F16) B200_DW_FWD_K(__half); else B200_DW_FWD_K(float);
+#undef B200_DW_FWD_K
+#undef B200_DW_FWD_NR
+#undef B200_DW_FWD
   B200_CHECK_LAUNCH("dwconv3d_fwd");
   return B200SEG_OK;
 }
@@ -333,9 +355,11 @@ extern "C" int b200seg_dwconv3d_wgrad(const void* x, int x_ld, int x_coff, const
   const size_t sm = sizeof(float) * ((size_t)kh * kw * chunk + 2 * chunk);
   cudaStream_t st = as_stream(stream);
   if (dtype == B200SEG_F16) {
-    dwconv_wgrad_kernel<__half><<<dim3(gx, B * kd, nchunk), threads, sm, st>>>(a);
+    if (kh == 3 && kw == 3) dwconv_wgrad_kernel<__half, 3><<<dim3(gx, B * kd, nchunk), threads, sm, st>>>(a);
+    else dwconv_wgrad_kernel<__half, 0><<<dim3(gx, B * kd, nchunk), threads, sm, st>>>(a);
   } else {
-    dwconv_wgrad_kernel<float><<<dim3(gx, B * kd, nchunk), threads, sm, st>>>(a);
+    if (kh == 3 && kw == 3) dwconv_wgrad_kernel<float, 3><<<dim3(gx, B * kd, nchunk), threads, sm, st>>>(a);
+    else dwconv_wgrad_kernel<float, 0><<<dim3(gx, B * kd, nchunk), threads, sm, st>>>(a);
   }
   B200_CHECK_LAUNCH("dwconv3d_wgrad");
   return B200SEG_OK;
