@@ -98,10 +98,13 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
   // overlap in L1 instead of each being fetched from L2
   const Tile tl = make_tile(blockDim.x / ncg, D, H, WR);
   const int rl = tid / ncg, lw = rl % tl.tw, lh = (rl / tl.tw) % tl.th, ldp = rl / (tl.tw * tl.th);
-  for (int64_t tile = blockIdx.x; tile < tl.ntiles; tile += gridDim.x) {
-    const int wr = (int)(tile % tl.nw) * tl.tw + lw;
-    const int h = (int)((tile / tl.nw) % tl.nh) * tl.th + lh;
-    const int d = (int)(tile / ((int64_t)tl.nw * tl.nh)) * tl.td + ldp;
+  // 32-bit tile arithmetic: 64-bit div/mod here cost several hundred instructions per item (ncu, round 1)
+  const unsigned ntiles = (unsigned)tl.ntiles, nwh = (unsigned)(tl.nw * tl.nh);
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const unsigned td_ = tile / nwh, rem = tile - td_ * nwh, th_ = rem / (unsigned)tl.nw, tw_ = rem - th_ * (unsigned)tl.nw;
+    const int wr = (int)tw_ * tl.tw + lw;
+    const int h = (int)th_ * tl.th + lh;
+    const int d = (int)td_ * tl.td + ldp;
     if (wr >= WR || h >= H || d >= D) continue;
     const int w0 = wr * RUN;
     float acc[RUN][8];
@@ -221,12 +224,14 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
   const T* gb = (const T*)a.dy + (int64_t)b * D * H * W * dy_ld + a.dy_coff + c0 + cg * 8;
   const Tile tl = make_tile(blockDim.x / ncg, D, H, W);
   const int rl = tid / ncg, lw = rl % tl.tw, lh = (rl / tl.tw) % tl.th, ldp = rl / (tl.tw * tl.th);
-  for (int64_t tile = blockIdx.x; tile < tl.ntiles; tile += gridDim.x) {
+  const unsigned ntiles = (unsigned)tl.ntiles, nwh = (unsigned)(tl.nw * tl.nh);
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // input-stationary: the thread owns one INPUT vector (normalised once) and meets the 9 output gradients
     // of this depth tap that it contributes to:  dw[zd][zh][zw] += dy[id-zd+pd, ih-zh+ph, iw-zw+pw] * a[id,ih,iw]
-    const int iw = (int)(tile % tl.nw) * tl.tw + lw;
-    const int ih = (int)((tile / tl.nw) % tl.nh) * tl.th + lh;
-    const int id = (int)(tile / ((int64_t)tl.nw * tl.nh)) * tl.td + ldp;
+    const unsigned td_ = tile / nwh, rem = tile - td_ * nwh, th_ = rem / (unsigned)tl.nw, tw_ = rem - th_ * (unsigned)tl.nw;
+    const int iw = (int)tw_ * tl.tw + lw;
+    const int ih = (int)th_ * tl.th + lh;
+    const int id = (int)td_ * tl.td + ldp;
     const int d = id - zd + pd;
     if (iw >= W || ih >= H || id >= D || (unsigned)d >= (unsigned)D) continue;
     Raw<T> rx, rg[MAXK * MAXK];
@@ -307,6 +312,7 @@ extern "C" int b200seg_dwconv3d_fwd(const void* x, int x_ld, int x_coff, const d
   a.Ctot = C; a.C = chunk; a.c0 = 0;
   const int nchunk = C / chunk, ncg = chunk / 8, threads = pick_threads(ncg);
   const Tile tl = make_tile(threads / ncg, D, H, (W + RUN - 1) / RUN);
+  if (tl.ntiles >= (1LL << 31)) return B200SEG_EUNSUPPORTED;
   int gx = (int)(tl.ntiles < (1 << 30) ? tl.ntiles : (1 << 30));
   int cap = (B200SEG_NUM_SMS * 8 + B * nchunk - 1) / (B * nchunk);
   if (cap < 1) cap = 1;
@@ -348,6 +354,7 @@ extern "C" int b200seg_dwconv3d_wgrad(const void* x, int x_ld, int x_coff, const
   a.Ctot = C; a.C = chunk; a.c0 = 0;
   const int ncg = chunk / 8, threads = pick_threads(ncg);
   const Tile tl = make_tile(threads / ncg, D, H, W);
+  if (tl.ntiles >= (1LL << 31)) return B200SEG_EUNSUPPORTED;
   int gx = (int)(tl.ntiles < (1 << 30) ? tl.ntiles : (1 << 30));
   int cap = (B200SEG_NUM_SMS * 4 + B * kd * nchunk - 1) / (B * kd * nchunk);
   if (cap < 1) cap = 1;
