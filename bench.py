@@ -452,7 +452,10 @@ def biattn_roofline(torch, ops, _lib, dev, B):
         pass
     peak = peaks.get("hbm_gbs", 7700.0)
     ach = nbytes / (kms / 1e3) / 1e9
-    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum of biattn_fwd_kernel at this shape from the committed ncu --set full
+    # capture (profiles/r1_ncu_full_medformer_ops.txt: 31.22 MB read + 2.84 MB written per launch, B = 1)
+    traffic = 34.06e6 if B == 1 else None
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 7.7 TB/s",
             "kernel": "biattn_fwd N=%d heads=%d dim_head=32 M=27 (B-MHA core, both softmax directions)" % (N, heads),
             "ms": kms}
