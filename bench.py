@@ -271,8 +271,8 @@ def run_b200(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the ONE JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION/INFO
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200SEG_NCCL_DEBUG", "WARN")
+        # keep stdout to the ONE JSON line: NCCL prints its version banner (and any NCCL_DEBUG output) there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/b200seg_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
     assert _lib.load().b200seg_check_device() == 0, "not an sm_100 device"
 
