@@ -159,6 +159,23 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class quiet_stdout:
+    """Temporarily point the process-level stdout (fd 1) at /dev/null — for native libraries that print banners."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.null)
+
+
 def usable_cores():
     """Host threads this process can really use: CPU affinity capped by the cgroup CPU quota (a container that
     sees 128 logical CPUs but owns a 16-CPU quota thrashes with 128 threads)."""
@@ -271,9 +288,11 @@ def run_b200(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the ONE JSON line: NCCL prints its version banner (and any NCCL_DEBUG output) there
+        # keep stdout to the ONE JSON line: communicator creation prints an "NCCL version ..." banner on fd 1
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/b200seg_nccl.%h.%p.log")
-        dist.init_process_group("nccl", device_id=dev)
+        with quiet_stdout():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
     assert _lib.load().b200seg_check_device() == 0, "not an sm_100 device"
 
     def make_net():
