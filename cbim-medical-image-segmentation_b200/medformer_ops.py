@@ -8,9 +8,9 @@ their own backward (in_bwd_reduce / in_bwd_apply).
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, call
-from .ops import (IN_EPS, _dt, _need_cuda, _p, _stream, conv3d_fwd, conv3d_wgrad, copy_channels, dwconv3d,
-                  dwconv3d_wgrad, in_bwd_apply, in_bwd_reduce, instnorm_stats, new_stats)
+from ._lib import ACT_NONE, call
+from .ops import (_dt, _need_cuda, _stream, conv3d_fwd, conv3d_wgrad, copy_channels, dwconv3d, dwconv3d_wgrad,
+                  in_bwd_apply, in_bwd_reduce, instnorm_stats)
 
 
 class ConvFn(torch.autograd.Function):
