@@ -125,3 +125,49 @@ def test_medformer_state_dict_contract():
         b200seg.MedFormer(1, 14, 32, norm="bn")
     with pytest.raises(b200seg.B200SegError):
         net(torch.zeros(1, 1, 16, 32, 32))          # CPU tensor: loud failure, no fallback
+
+
+def _req(d):
+    return {k: v.clone().requires_grad_(True) for k, v in d.items()}
+
+
+@pytest.mark.parametrize("name", ["swin_attn_a", "swin_attn_b", "swin_attn_c"])
+def test_swin_window_attention_oracle_matches_reference_fixture(name):
+    """WindowAttention.forward of the vendored swin_unetr.py (rel-pos bias, shift mask) — rows a15 of SURVEY §8."""
+    from oracle import swin_ops as so
+    g = load_golden(name)
+    cfg = g["cfg"]
+    mask = None if g["mask_cross"] is None else g["mask_cross"].float() * -100.0
+    x, p = g["x"].clone().requires_grad_(True), _req(g["params"])
+    y = so.window_attention(x, p, cfg["heads"], so.relative_position_index(cfg["window"]), mask)
+    y.backward(g["gy"])
+    assert rel_err(y, g["y"]) < 1e-5 and rel_err(x.grad, g["dx"]) < 1e-4
+    for k in p:
+        assert rel_err(p[k].grad, g["dparams"][k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("name", ["swin_block_a", "swin_block_b", "swin_block_c"])
+def test_swin_block_part1_oracle_matches_reference_fixture(name):
+    """LayerNorm + pad + cyclic shift + window partition + attention + reverse (SwinTransformerBlock.forward_part1)."""
+    from oracle import swin_ops as so
+    g = load_golden(name)
+    cfg = g["cfg"]
+    ws, ss = so.get_window_size(cfg["dhw"], cfg["window"], cfg["shift"])
+    pdims = [-(-cfg["dhw"][i] // ws[i]) * ws[i] for i in range(3)]
+    mask = so.compute_mask(pdims, ws, ss) if any(ss) else None
+    x, p = g["x"].clone().requires_grad_(True), _req(g["params"])
+    y = so.swin_block_part1(x, p, cfg["heads"], cfg["window"], cfg["shift"], mask)
+    y.backward(g["gy"])
+    assert rel_err(y, g["y"]) < 1e-5 and rel_err(x.grad, g["dx"]) < 1e-4
+    for k in p:
+        assert rel_err(p[k].grad, g["dparams"][k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("name,fn", [("swin_merge_a", "patch_merging"), ("swin_merge_b", "patch_merging_v2")])
+def test_swin_patch_merging_oracle_matches_reference_fixture(name, fn):
+    from oracle import swin_ops as so
+    g = load_golden(name)
+    x = g["x"].clone().requires_grad_(True)
+    y = getattr(so, fn)(x, g["norm_w"], g["norm_b"], g["red_w"])
+    y.backward(g["gy"])
+    assert rel_err(y, g["y"]) < 1e-5 and rel_err(x.grad, g["dx"]) < 1e-5
