@@ -15,7 +15,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, kind="unet"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -29,17 +29,30 @@ def _worker(rank, world, port, q):
     class MP:
         def setattr(self, obj, name, val):
             setattr(obj, name, val)
-    emu_ops.install(MP())
     torch.Tensor.is_cuda = property(lambda self: True)
     torch.manual_seed(0)
     scale, kernel = [[1, 2, 2], [1, 2, 2], [2, 2, 2], [1, 1, 1]], [[1, 3, 3], [1, 3, 3], [3, 3, 3], [3, 3, 3], [3, 3, 3]]
-    net = b200seg.UNet(1, 4, scale=scale, kernel_size=kernel, num_classes=3, block="BasicBlock", norm="in")
-    shapes = ounet.unet_param_shapes(1, 4, 3, kernel, "BasicBlock")
+    if kind == "unet":
+        emu_ops.install(MP())
+        net = b200seg.UNet(1, 4, scale=scale, kernel_size=kernel, num_classes=3, block="BasicBlock", norm="in")
+        shapes = ounet.unet_param_shapes(1, 4, 3, kernel, "BasicBlock")
+        img, lab = make_volume(1, 4, 16, 16, 3, seed=100 + rank)                  # each rank its own patch
+    else:                                                                         # a narrow MedFormer, deep supervision on
+        import emu_medformer
+        emu_medformer.install(MP())
+        net = b200seg.MedFormer(1, 3, 16, map_size=[2, 2, 2], conv_num=[1, 0, 0, 0, 0, 0, 1, 1], trans_num=[0, 1, 1, 1, 1, 1, 0, 0],
+                                chan_num=[32, 32, 64, 64, 64, 32, 32, 16], num_heads=[1, 1, 2, 2, 2, 1, 1, 1], fusion_depth=1,
+                                fusion_dim=64, fusion_heads=2, kernel_size=kernel, scale=[[1, 2, 2], [1, 2, 2], [2, 2, 2], [2, 2, 2]],
+                                aux_loss=True)
+        shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        img, lab = make_volume(1, 8, 32, 32, 3, seed=100 + rank)
     net.load_state_dict(ounet.make_state_dict(shapes, seed=3))
     net = torch.nn.SyncBatchNorm.convert_sync_batchnorm(net)                      # no-op: InstanceNorm only
     ddp = torch.nn.parallel.DistributedDataParallel(net, find_unused_parameters=True)
-    img, lab = make_volume(1, 4, 16, 16, 3, seed=100 + rank)                      # each rank its own patch
-    crit = b200seg.DiceCELoss(weight=torch.tensor([0.5, 1.0, 2.0]))
+    ce_dice = b200seg.DiceCELoss(weight=torch.tensor([0.5, 1.0, 2.0]))
+
+    def crit(res, lab):                                                           # train_ddp.py:186-191
+        return sum(0.5 * ce_dice(r, lab) for r in res) if isinstance(res, (list, tuple)) else ce_dice(res, lab)
     # local (un-reduced) gradient of this rank, through the bare module
     net.zero_grad()
     crit(net(img), lab).backward()
@@ -61,11 +74,12 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_ddp_world2_gloo_gradient_is_rank_mean():
+@pytest.mark.parametrize("kind", ["unet", "medformer"])
+def test_ddp_world2_gloo_gradient_is_rank_mean(kind):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (7 if kind == "medformer" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, kind)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
