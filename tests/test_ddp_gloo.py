@@ -1,6 +1,7 @@
 """CPU, world_size=2 over gloo: the N>1 path of the drop-in.  The module is wrapped exactly like
 train_ddp.py:352-358 (SyncBatchNorm.convert + DistributedDataParallel(find_unused_parameters=True)), with the
-C-ABI ops emulated in PyTorch (tests/emu_ops.py); checks that
+C-ABI ops emulated in PyTorch (tests/emu_ops.py, tests/emu_medformer.py), for the UNet and for a narrow MedFormer
+with its deep-supervision head; checks that
   * custom autograd Functions keep every parameter reachable (DDP's unused-parameter walk finds none),
   * the all-reduced gradient is the MEAN of the per-rank gradients (Dice / CE normalisers are per-rank, §8e),
   * parameters stay bit-identical across ranks after an optimiser step."""
