@@ -32,6 +32,12 @@ MODELS = {   # name: (ctor kwargs, classes, input BxDxHxW)
     "medformer_var": (dict(map_size=[4, 4, 4], conv_num=[1, 1, 0, 0, 0, 1, 1, 1], trans_num=[0, 1, 2, 1, 1, 1, 0, 0],
                            num_heads=[1, 4, 8, 10, 8, 4, 1, 1], fusion_depth=1, fusion_dim=128, fusion_heads=4,
                            kernel_size=[[3, 3, 3]] * 5, scale=[[2, 2, 2]] * 4, aux_loss=False), 4, (2, 16, 32, 32)),
+    # the ACDC YAML (config/acdc/medformer_3d.yaml:9-28): 2x6x6 = 72 map tokens, 4 heads per level -> dim_head 32/64/80,
+    # fusion_dim 256.  Oracle-only for now: the B200 kernels do not cover dim_head != 32 / 72 tokens yet.
+    "medformer_acdc": (dict(map_size=[2, 6, 6], conv_num=[2, 0, 0, 0, 0, 0, 2, 2], trans_num=[0, 2, 2, 2, 2, 2, 0, 0],
+                            num_heads=[1, 4, 4, 4, 4, 4, 1, 1], fusion_depth=2, fusion_dim=256, fusion_heads=4,
+                            kernel_size=[[1, 3, 3], [1, 3, 3], [3, 3, 3], [3, 3, 3], [3, 3, 3]],
+                            scale=[[1, 2, 2], [1, 2, 2], [2, 2, 2], [2, 2, 2]], aux_loss=True), 4, (1, 8, 32, 32)),
 }
 DWCONV = {"dwconv_a": (2, 16, (5, 6, 7), [3, 3, 3], 31), "dwconv_b": (1, 24, (4, 9, 8), [1, 3, 3], 32)}
 

@@ -83,7 +83,7 @@ def test_dwconv_oracle_matches_reference_fixture(name):
     assert rel_err(y, g["y"]) < 1e-6 and rel_err(x.grad, g["dx"]) < 1e-5 and rel_err(w.grad, g["dw"]) < 1e-5
 
 
-@pytest.mark.parametrize("name", ["medformer_bcv", "medformer_var"])
+@pytest.mark.parametrize("name", ["medformer_bcv", "medformer_var", "medformer_acdc"])
 def test_medformer_oracle_matches_reference_fixture(name):
     from oracle import medformer as omed
     from oracle.unet3d import make_state_dict
