@@ -229,28 +229,47 @@ conv_wgrad_direct_kernel(WgradArgs a) {
     atomicAdd(&a.dbias[co0 + threadIdx.x], bacc);
 }
 
+// packed position of element i of a [Cout][Cin][taps] fp32 parameter (see b200seg_pack_weight)
+__device__ __forceinline__ int64_t pack_index(int64_t i, int Cout, int Cin, int taps, int transpose_flip, int co_off,
+                                              int co_total, int layout_tc) {
+  // virtual packed tensor [taps][R][Cc]: fwd: R = co_total rows (cout), Cc = Cin cols; dgrad operand: R = Cin, Cc = co_total
+  const int R = transpose_flip ? Cin : co_total, Cc = transpose_flip ? co_total : Cin;
+  const int tap = (int)(i % taps); const int64_t t = i / taps; const int ci = (int)(t % Cin); const int co = (int)(t / Cin);
+  const int tp = transpose_flip ? taps - 1 - tap : tap;
+  const int row = transpose_flip ? ci : co_off + co;
+  const int col = transpose_flip ? co_off + co : ci;
+  if (!layout_tc) return ((int64_t)tp * R + row) * Cc + col;
+  const int NT = tc_pick_nt(R), KC = tc_pick_kc(Cc), NKC = Cc / KC;
+  const int ntile = row / NT, nn = row % NT, kc = col / KC, kk = col % KC, k8 = kk >> 3, e = kk & 7;
+  return ((((int64_t)(ntile * taps + tp) * NKC + kc) * (KC / 8) + k8) * NT + nn) * 8 + e;
+}
+
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, T* __restrict__ wp,
                                    int transpose_flip, int co_off, int co_total, int layout_tc) {
   int64_t n = (int64_t)Cout * Cin * taps;
-  // virtual packed tensor [taps][R][Cc]: fwd: R = co_total rows (cout), Cc = Cin cols; dgrad operand: R = Cin, Cc = co_total
-  const int R = transpose_flip ? Cin : co_total, Cc = transpose_flip ? co_total : Cin;
-  const int NT = layout_tc ? tc_pick_nt(R) : 1, KC = layout_tc ? tc_pick_kc(Cc) : 1;
-  const int NKC = layout_tc ? Cc / KC : 1;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int tap = (int)(i % taps); int64_t t = i / taps; int ci = (int)(t % Cin); int co = (int)(t / Cin);
-    float v = w[i];
-    const int tp = transpose_flip ? taps - 1 - tap : tap;
-    const int row = transpose_flip ? ci : co_off + co;
-    const int col = transpose_flip ? co_off + co : ci;
-    int64_t o;
-    if (!layout_tc) {
-      o = ((int64_t)tp * R + row) * Cc + col;
-    } else {
-      const int ntile = row / NT, nn = row % NT, kc = col / KC, kk = col % KC, k8 = kk >> 3, e = kk & 7;
-      o = ((((int64_t)(ntile * taps + tp) * NKC + kc) * (KC / 8) + k8) * NT + nn) * 8 + e;
-    }
-    Elem<T>::st(wp + o, v);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    Elem<T>::st(wp + pack_index(i, Cout, Cin, taps, transpose_flip, co_off, co_total, layout_tc), w[i]);
+}
+
+// Multi-tensor variant: every conv weight of a model is re-packed by ONE launch per forward (the per-weight
+// launches were ~90 x 12 us per step).  jobs[j] = {w, out, Cout, Cin, taps, dtype, transpose_flip, co_off, co_total,
+// layout_tc}; chunks[c] = {job, first element}: one block per chunk of kPackChunk elements.
+constexpr int kPackChunk = 4096;
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const int64_t* __restrict__ jobs, const int64_t* __restrict__ chunks) {
+  const int64_t* c = chunks + 2 * (int64_t)blockIdx.x;
+  const int64_t* j = jobs + 10 * c[0];
+  const float* w = reinterpret_cast<const float*>(j[0]);
+  const int Cout = (int)j[2], Cin = (int)j[3], taps = (int)j[4], dtype = (int)j[5], tf = (int)j[6], co_off = (int)j[7],
+            co_total = (int)j[8], tc = (int)j[9];
+  const int64_t n = (int64_t)Cout * Cin * taps, i0 = c[1];
+  const int64_t i1 = i0 + kPackChunk < n ? i0 + kPackChunk : n;
+  if (dtype == B200SEG_F16) {
+    __half* o = reinterpret_cast<__half*>(j[1]);
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) o[pack_index(i, Cout, Cin, taps, tf, co_off, co_total, tc)] = __float2half_rn(w[i]);
+  } else {
+    float* o = reinterpret_cast<float*>(j[1]);
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) o[pack_index(i, Cout, Cin, taps, tf, co_off, co_total, tc)] = w[i];
   }
 }
 
@@ -315,5 +334,15 @@ extern "C" int b200seg_pack_weight(const float* w, int Cout, int Cin, int taps, 
   else if (dtype == B200SEG_F32) pack_weight_kernel<float><<<grid, 256, 0, st>>>(w, Cout, Cin, taps, (float*)w_packed, transpose_flip, co_off, co_total, tc);
   else return B200SEG_EINVAL;
   B200_CHECK_LAUNCH("pack_weight_kernel");
+  return B200SEG_OK;
+}
+
+extern "C" int b200seg_pack_chunk_elems(void) { return kPackChunk; }
+
+extern "C" int b200seg_pack_weights_multi(const int64_t* jobs_dev, const int64_t* chunks_dev, int nchunks, void* stream) {
+  if (nchunks == 0) return B200SEG_OK;
+  if (!jobs_dev || !chunks_dev || nchunks < 0) return B200SEG_EINVAL;
+  pack_weights_multi_kernel<<<nchunks, 256, 0, as_stream(stream)>>>(jobs_dev, chunks_dev);
+  B200_CHECK_LAUNCH("pack_weights_multi_kernel");
   return B200SEG_OK;
 }

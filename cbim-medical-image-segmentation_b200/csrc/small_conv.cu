@@ -8,172 +8,222 @@
 namespace {
 
 constexpr int kWarpsPerBlock = 8;
+constexpr int kSmallGridPerSM = 2;        // persistent blocks per SM (register accumulators live for the whole kernel)
 
-// ---- stem: dW[co][tap] = sum_v dy[v][co] * x[v + tap],  Cin == 1, Cout <= 64, taps <= 27
-template <typename T, int KD, int KH, int KW>
+// ---- stem: dW[co][tap] = sum_v dy[v][co] * x[v + tap],  Cin == 1, Cout <= 64, taps <= 27.
+// HBM-bound (reads dy once: Cout*s bytes per voxel).  Persistent blocks walk (b, d, 8-row h-groups); the single-channel
+// input halo of the group sits zero-padded in shared memory as fp32, so the inner loop has no bounds checks:
+// warp = one h row, lane = output channel, per voxel 1 coalesced load of dy + KD*KH broadcast LDS (sliding 3-wide
+// window along w kept in registers) + taps FFMA.  One atomicAdd per (block, co, tap) at the very end.
+template <typename T, int KD, int KH, int KW, bool TWO>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-wgrad_cin1_kernel(WgradArgs a, int64_t vox_per_warp) {
-  constexpr int MAXT = KD * KH * KW;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_id = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  const int64_t V = (int64_t)a.D * a.H * a.W, total = (int64_t)a.B * V;
+wgrad_cin1_kernel(WgradArgs a) {
+  constexpr int TAPS = KD * KH * KW, ROWS = kWarpsPerBlock, HR = ROWS + KH - 1, WMAX = 256;
   constexpr int pd = KD / 2, ph = KH / 2, pw = KW / 2;
+  // the halo tile (main loop) and the reduction scratch (after it) share one buffer
+  constexpr int XW = WMAX + 4, kXFloats = KD * HR * XW, kRFloats = kWarpsPerBlock * 32 * (TAPS + 1);
+  __shared__ float s_raw[kXFloats > kRFloats ? kXFloats : kRFloats];
+  float (*s_x)[HR][XW] = reinterpret_cast<float (*)[HR][XW]>(s_raw);
+  float (*s_red)[32][TAPS + 1] = reinterpret_cast<float (*)[32][TAPS + 1]>(s_raw);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const T* x = (const T*)a.x; const T* dy = (const T*)a.dy;
-  float acc0[MAXT], acc1[MAXT];
+  float acc0[TAPS], acc1[TWO ? TAPS : 1];
 #pragma unroll
-  for (int t = 0; t < MAXT; ++t) { acc0[t] = 0.f; acc1[t] = 0.f; }
-  const bool two = a.Cout > 32;
-  int64_t v0 = warp_id * vox_per_warp, v1 = v0 + vox_per_warp; if (v1 > total) v1 = total;
-  for (int64_t gv = v0; gv < v1; ++gv) {
-    const int64_t b = gv / V, v = gv - b * V;
-    const int w = (int)(v % a.W); const int64_t t2 = v / a.W; const int h = (int)(t2 % a.H); const int d = (int)(t2 / a.H);
-    const float g0 = lane < a.Cout ? Elem<T>::ld(dy + gv * a.dy_ld + a.dy_coff + lane) : 0.f;
-    const float g1 = (two && lane + 32 < a.Cout) ? Elem<T>::ld(dy + gv * a.dy_ld + a.dy_coff + lane + 32) : 0.f;
-    const T* xb = x + b * V * a.x_ld + a.x_coff;
+  for (int t = 0; t < TAPS; ++t) acc0[t] = 0.f;
 #pragma unroll
-    for (int zd = 0; zd < KD; ++zd) {
-      const int dd = d + zd - pd;
+  for (int t = 0; t < (TWO ? TAPS : 1); ++t) acc1[t] = 0.f;
+  const int hgroups = (a.H + ROWS - 1) / ROWS;
+  const int wchunks = (a.W + WMAX - 1) / WMAX;
+  const int64_t njobs = (int64_t)a.B * a.D * hgroups * wchunks;
+  const bool c0ok = lane < a.Cout, c1ok = TWO && (lane + 32 < a.Cout);
+  for (int64_t job = blockIdx.x; job < njobs; job += gridDim.x) {
+    int64_t q = job;
+    const int wc = (int)(q % wchunks); q /= wchunks;
+    const int hg = (int)(q % hgroups); q /= hgroups;
+    const int d = (int)(q % a.D); const int b = (int)(q / a.D);
+    const int h0 = hg * ROWS, w0 = wc * WMAX;
+    const int wn = min(WMAX, a.W - w0);
+    __syncthreads();                       // previous job's readers are done with s_x
+    for (int i = threadIdx.x; i < KD * HR * (wn + 2 * pw); i += kWarpsPerBlock * 32) {
+      const int wi = i % (wn + 2 * pw); int r = i / (wn + 2 * pw);
+      const int hi = r % HR, zi = r / HR;
+      const int dd = d + zi - pd, hh = h0 + hi - ph, ww = w0 + wi - pw;
+      float v = 0.f;
+      if ((unsigned)dd < (unsigned)a.D && (unsigned)hh < (unsigned)a.H && (unsigned)ww < (unsigned)a.W)
+        v = Elem<T>::ld(x + ((((int64_t)b * a.D + dd) * a.H + hh) * a.W + ww) * a.x_ld + a.x_coff);
+      s_x[zi][hi][wi] = v;
+    }
+    __syncthreads();
+    const int h = h0 + wid;
+    if (h < a.H) {
+      const T* dyrow = dy + ((((int64_t)b * a.D + d) * a.H + h) * a.W + w0) * a.dy_ld + a.dy_coff + lane;
+      float win[KD][KH][KW];               // x[.., w-1], x[.., w], x[.., w+1] per (zd, zh) row
 #pragma unroll
-      for (int zh = 0; zh < KH; ++zh) {
-        const int hh = h + zh - ph;
+      for (int zd = 0; zd < KD; ++zd)
 #pragma unroll
-        for (int zw = 0; zw < KW; ++zw) {
-          const int ww = w + zw - pw;
-          float xv = 0.f;          // warp-uniform address: one broadcast transaction
-          if ((unsigned)dd < (unsigned)a.D && (unsigned)hh < (unsigned)a.H && (unsigned)ww < (unsigned)a.W)
-            xv = Elem<T>::ld(xb + (((int64_t)dd * a.H + hh) * a.W + ww) * a.x_ld);
-          constexpr int dummy = 0; (void)dummy;
-          const int t = (zd * KH + zh) * KW + zw;
-          acc0[t] = fmaf(g0, xv, acc0[t]);
-          acc1[t] = fmaf(g1, xv, acc1[t]);
+        for (int zh = 0; zh < KH; ++zh)
+#pragma unroll
+          for (int zw = 0; zw < KW - 1; ++zw) win[zd][zh][zw + 1] = s_x[zd][wid + zh][zw];
+      constexpr int U = 4;
+      for (int wb = 0; wb < wn; wb += U) {
+        float g0[U], g1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool in = wb + u < wn;
+          g0[u] = (in && c0ok) ? Elem<T>::ld(dyrow + (int64_t)(wb + u) * a.dy_ld) : 0.f;
+          g1[u] = (in && c1ok) ? Elem<T>::ld(dyrow + (int64_t)(wb + u) * a.dy_ld + 32) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (wb + u >= wn) break;
+#pragma unroll
+          for (int zd = 0; zd < KD; ++zd)
+#pragma unroll
+            for (int zh = 0; zh < KH; ++zh) {
+#pragma unroll
+              for (int zw = 0; zw < KW - 1; ++zw) win[zd][zh][zw] = win[zd][zh][zw + 1];
+              win[zd][zh][KW - 1] = s_x[zd][wid + zh][wb + u + KW - 1];
+#pragma unroll
+              for (int zw = 0; zw < KW; ++zw) {
+                const int t = (zd * KH + zh) * KW + zw;
+                acc0[t] = fmaf(g0[u], win[zd][zh][zw], acc0[t]);
+                if (TWO) acc1[t] = fmaf(g1[u], win[zd][zh][zw], acc1[t]);
+              }
+            }
         }
       }
     }
   }
-  // block-level reduction first: thousands of warps hammering the same few hundred addresses with atomics
-  // serialise in L2 (measured ~1 ms); one atomic per (block, output) instead
-  __shared__ float s_acc[kWarpsPerBlock][32][MAXT];
-  const int wid = threadIdx.x >> 5;
-  for (int half = 0; half < (two ? 2 : 1); ++half) {
+  // block-level reduction, then one atomic per (block, output)
+  for (int half = 0; half < (TWO ? 2 : 1); ++half) {
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < MAXT; ++q) s_acc[wid][lane][q] = half ? acc1[q] : acc0[q];
+    for (int t = 0; t < TAPS; ++t) s_red[wid][lane][t] = (half && TWO) ? acc1[TWO ? t : 0] : acc0[t];
     __syncthreads();
     const int nco = min(32, a.Cout - 32 * half);
-    for (int o = threadIdx.x; o < nco * MAXT; o += kWarpsPerBlock * 32) {
-      const int co = o / MAXT, q = o % MAXT;
+    for (int o = threadIdx.x; o < nco * TAPS; o += kWarpsPerBlock * 32) {
+      const int co = o / TAPS, t = o % TAPS;
       float sum = 0.f;
 #pragma unroll
-      for (int w = 0; w < kWarpsPerBlock; ++w) sum += s_acc[w][co][q];
-      atomicAdd(&a.dw[(int64_t)(co + 32 * half) * MAXT + q], sum);
+      for (int w = 0; w < kWarpsPerBlock; ++w) sum += s_red[w][co][t];
+      atomicAdd(&a.dw[(int64_t)(co + 32 * half) * TAPS + t], sum);
     }
   }
 }
 
-// ---- head: dW[co][ci] = sum_v dy[v][co] * a[v][ci], 1x1x1, Cout <= 16, Cin <= 128; dbias[co] = sum_v dy[v][co]
-template <typename T, int MAXCO>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-wgrad_head_kernel(WgradArgs a, int64_t vox_per_warp) {
-  __shared__ float s_mean_all[kWarpsPerBlock][128], s_rstd_all[kWarpsPerBlock][128];   // per warp: runs may sit in different samples
-  float* s_mean = s_mean_all[threadIdx.x >> 5];
-  float* s_rstd = s_rstd_all[threadIdx.x >> 5];
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_id = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  const int64_t V = (int64_t)a.D * a.H * a.W, total = (int64_t)a.B * V;
+// ---- head: dW[co][ci] = sum_v dy[v][co] * a[v][ci], 1x1x1, Cout <= 16, Cin <= 128 (multiple of 8);
+// dbias[co] = sum_v dy[v][co].  HBM-bound: one 16-byte (fp16) load of 8 input channels per thread per voxel, the
+// voxel's Cout gradients as one vector load, CPT x MAXCO FFMA into registers; persistent blocks, smem tree reduction,
+// one atomicAdd per (block, output).
+template <typename T, int MAXCO, int CPT>
+__global__ void __launch_bounds__(256)
+wgrad_head_kernel(WgradArgs a) {
+  constexpr int U = MAXCO <= 4 ? 4 : 2;
+  __shared__ float s_red[256][CPT * MAXCO / 4 + 1][4];       // padded rows: conflict-light float4-free layout
+  const int64_t V = (int64_t)a.D * a.H * a.W;
   const T* x = (const T*)a.x; const T* dy = (const T*)a.dy;
-  const int nci = (a.Cin + 31) / 32;        // channels per lane: lane, lane+32, ...
-  float acc[4][MAXCO];
-  float bacc[MAXCO];
+  const int ngrp = a.Cin / CPT;                   // threads per voxel
+  const int vpi = 256 / ngrp;                     // voxels per block iteration
+  const int cg = threadIdx.x % ngrp, vl = threadIdx.x / ngrp;
+  const bool active = vl < vpi;
+  // the voxel's 4 gradients as one vector load when the layout allows it (the UNet head: dy is [V][4])
+  const bool gvec = MAXCO == 4 && a.Cout == 4 && a.dy_ld % 4 == 0 && a.dy_coff % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(a.dy) % (4 * sizeof(T))) == 0;
+  float acc[CPT][MAXCO], bacc[MAXCO];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < CPT; ++k)
 #pragma unroll
     for (int c = 0; c < MAXCO; ++c) acc[k][c] = 0.f;
 #pragma unroll
   for (int c = 0; c < MAXCO; ++c) bacc[c] = 0.f;
-  int64_t v0 = warp_id * vox_per_warp, v1 = v0 + vox_per_warp; if (v1 > total) v1 = total;
-  int64_t cur_b = -1;
-  constexpr int U = 4;                         // voxels in flight per warp iteration (memory-level parallelism)
-  for (int64_t gv0 = v0; gv0 < v1; gv0 += U) {
-    const int64_t b = gv0 / V;
-    if (a.x_stats && (b != cur_b || (gv0 + U - 1) / V != b)) {
-      // (re)load the sample's mean / rstd; a batch that straddles two samples is processed voxel by voxel below
-      __syncwarp();
-      for (int c = lane; c < a.Cin; c += 32) stats_to_mean_rstd(a.x_stats + (b * a.Cin + c) * 2, (double)V, a.eps, s_mean[c], s_rstd[c]);
-      __syncwarp();
-      cur_b = b;
+  for (int b = 0; b < a.B; ++b) {
+    float mean[CPT], rstd[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      mean[k] = 0.f; rstd[k] = 1.f;
+      if (a.x_stats) stats_to_mean_rstd(a.x_stats + ((int64_t)b * a.Cin + cg * CPT + k) * 2, (double)V, a.eps, mean[k], rstd[k]);
     }
-    const bool straddle = a.x_stats && ((gv0 + U - 1) / V != b) && (gv0 + U - 1 < v1);
-    float g[U][MAXCO], xr[U][4];
+    const T* xb = x + (int64_t)b * V * a.x_ld + a.x_coff + cg * CPT;
+    const T* db = dy + (int64_t)b * V * a.dy_ld + a.dy_coff;
+    for (int64_t v0 = (int64_t)blockIdx.x * vpi * U + vl; active && v0 < V; v0 += (int64_t)gridDim.x * vpi * U) {
+      float xv[U][CPT], g[U][MAXCO];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t gv = gv0 + u;
-      const bool in = gv < v1;
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = v0 + (int64_t)u * vpi;
+        const bool in = v < V;
+        if (in) {
+          if constexpr (CPT == 8) ld8<T>(xb + v * a.x_ld, xv[u]);
+          else {
 #pragma unroll
-      for (int c = 0; c < MAXCO; ++c) g[u][c] = (in && c < a.Cout) ? Elem<T>::ld(dy + gv * a.dy_ld + a.dy_coff + c) : 0.f;
+            for (int k = 0; k < CPT; ++k) xv[u][k] = Elem<T>::ld(xb + v * a.x_ld + k);
+          }
+          if (MAXCO == 4 && gvec) {
+            if constexpr (sizeof(T) == 2) {
+              const uint2 q = *reinterpret_cast<const uint2*>(db + v * a.dy_ld);
+              const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+              g[u][0] = f0.x; g[u][1] = f0.y; g[u][2] = f1.x; g[u][3] = f1.y;
+            } else {
+              const float4 q = *reinterpret_cast<const float4*>(db + v * a.dy_ld);
+              g[u][0] = q.x; g[u][1] = q.y; g[u][2] = q.z; g[u][3] = q.w;
+            }
+          } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int ci = lane + 32 * k;
-        xr[u][k] = (in && k < nci && ci < a.Cin) ? Elem<T>::ld(x + gv * a.x_ld + a.x_coff + ci) : 0.f;
-      }
-    }
+            for (int c = 0; c < MAXCO; ++c) g[u][c] = c < a.Cout ? Elem<T>::ld(db + v * a.dy_ld + c) : 0.f;
+          }
+        } else {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t gv = gv0 + u;
-      if (gv >= v1) break;
-      if (straddle && gv / V != cur_b) {
-        const int64_t b2 = gv / V;
-        __syncwarp();
-        for (int c = lane; c < a.Cin; c += 32) stats_to_mean_rstd(a.x_stats + (b2 * a.Cin + c) * 2, (double)V, a.eps, s_mean[c], s_rstd[c]);
-        __syncwarp();
-        cur_b = b2;
-      }
+          for (int k = 0; k < CPT; ++k) xv[u][k] = 0.f;
 #pragma unroll
-      for (int c = 0; c < MAXCO; ++c) bacc[c] += g[u][c];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k >= nci) break;
-        const int ci = lane + 32 * k;
-        float xv = 0.f;
-        if (ci < a.Cin) {
-          xv = xr[u][k];
-          if (a.x_stats) xv = (xv - s_mean[ci]) * s_rstd[ci];
-          if (a.act == B200SEG_ACT_RELU) xv = fmaxf(xv, 0.f);
-          xv = Elem<T>::round(xv);
+          for (int c = 0; c < MAXCO; ++c) g[u][c] = 0.f;
         }
+      }
 #pragma unroll
-        for (int c = 0; c < MAXCO; ++c) acc[k][c] = fmaf(g[u][c], xv, acc[k][c]);
+      for (int u = 0; u < U; ++u) {
+        const bool in = v0 + (int64_t)u * vpi < V;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+          float t = xv[u][k];
+          if (a.x_stats) t = (t - mean[k]) * rstd[k];
+          if (a.act == B200SEG_ACT_RELU) t = fmaxf(t, 0.f);
+          t = in ? Elem<T>::round(t) : 0.f;
+#pragma unroll
+          for (int c = 0; c < MAXCO; ++c) acc[k][c] = fmaf(g[u][c], t, acc[k][c]);
+        }
+        if (cg == 0) {
+#pragma unroll
+          for (int c = 0; c < MAXCO; ++c) bacc[c] += g[u][c];
+        }
       }
     }
   }
-  __shared__ float s_acc[kWarpsPerBlock][32][MAXCO];
-  __shared__ float s_bacc[kWarpsPerBlock][MAXCO];
-  const int wid = threadIdx.x >> 5;
-  if (lane == 0) {
+  // reduce over the voxel lanes that share a channel group: tree in shared memory
+  constexpr int NV = CPT * MAXCO;
+  float* mine = &s_red[threadIdx.x][0][0];
 #pragma unroll
-    for (int c = 0; c < MAXCO; ++c) s_bacc[wid][c] = bacc[c];
-  }
+  for (int k = 0; k < CPT; ++k)
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (k >= nci) break;
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < MAXCO; ++c) s_acc[wid][lane][c] = acc[k][c];
-    __syncthreads();
-    const int nch = min(32, a.Cin - 32 * k);
-    for (int o = threadIdx.x; o < nch * a.Cout; o += kWarpsPerBlock * 32) {
-      const int c = o / nch, cl = o % nch;
-      float sum = 0.f;
-#pragma unroll
-      for (int w = 0; w < kWarpsPerBlock; ++w) sum += s_acc[w][cl][c];
-      atomicAdd(&a.dw[(int64_t)c * a.Cin + 32 * k + cl], sum);
-    }
-  }
+    for (int c = 0; c < MAXCO; ++c) mine[k * MAXCO + c] = acc[k][c];
   __syncthreads();
-  if (a.dbias && threadIdx.x < a.Cout) {
+  constexpr int RS = (CPT * MAXCO / 4 + 1) * 4;       // row stride in floats
+  for (int o = threadIdx.x; o < ngrp * NV; o += 256) {
+    const int g2 = o / NV, e = o % NV;
     float sum = 0.f;
+    for (int l = 0; l < vpi; ++l) sum += (&s_red[0][0][0])[(l * ngrp + g2) * RS + e];
+    const int k = e / MAXCO, c = e % MAXCO;
+    if (c < a.Cout) atomicAdd(&a.dw[(int64_t)c * a.Cin + g2 * CPT + k], sum);
+  }
+  if (a.dbias) {
+    __syncthreads();
+    if (cg == 0 && active) {
 #pragma unroll
-    for (int w = 0; w < kWarpsPerBlock; ++w) sum += s_bacc[w][threadIdx.x];
-    atomicAdd(&a.dbias[threadIdx.x], sum);
+      for (int c = 0; c < MAXCO; ++c) mine[c] = bacc[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < a.Cout) {
+      float sum = 0.f;
+      for (int l = 0; l < vpi; ++l) sum += (&s_red[0][0][0])[(l * ngrp) * RS + threadIdx.x];
+      atomicAdd(&a.dbias[threadIdx.x], sum);
+    }
   }
 }
 
@@ -182,31 +232,27 @@ wgrad_head_kernel(WgradArgs a, int64_t vox_per_warp) {
 // returns B200SEG_EUNSUPPORTED when the shape is not one of the special cases
 int conv3d_wgrad_small(const WgradArgs& a, int dtype, cudaStream_t st) {
   const int taps = a.kd * a.kh * a.kw;
-  const int64_t total = (int64_t)a.B * a.D * a.H * a.W;
-  const int nwarps_target = B200SEG_NUM_SMS * kWarpsPerBlock * 4;
-  int64_t vpw = (total + nwarps_target - 1) / nwarps_target; if (vpw < 64) vpw = 64;
-  const int64_t nwarps = (total + vpw - 1) / vpw;
-  const int grid = (int)((nwarps + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const int grid = B200SEG_NUM_SMS * kSmallGridPerSM;
   const bool k133 = (a.kd == 1 && a.kh == 3 && a.kw == 3), k333 = (a.kd == 3 && a.kh == 3 && a.kw == 3);
   if (a.Cin == 1 && a.Cout <= 64 && (k133 || k333) && !a.x_stats && !a.act && !a.dbias) {
     const int th = kWarpsPerBlock * 32;
-    if (dtype == B200SEG_F16) {
-      if (k133) wgrad_cin1_kernel<__half, 1, 3, 3><<<grid, th, 0, st>>>(a, vpw);
-      else wgrad_cin1_kernel<__half, 3, 3, 3><<<grid, th, 0, st>>>(a, vpw);
-    } else {
-      if (k133) wgrad_cin1_kernel<float, 1, 3, 3><<<grid, th, 0, st>>>(a, vpw);
-      else wgrad_cin1_kernel<float, 3, 3, 3><<<grid, th, 0, st>>>(a, vpw);
-    }
+#define CIN1(TT, KDD, TWO_) wgrad_cin1_kernel<TT, KDD, 3, 3, TWO_><<<grid, th, 0, st>>>(a)
+#define CIN1_T(TT) do { if (a.Cout > 32) { if (k133) CIN1(TT, 1, true); else CIN1(TT, 3, true); } \
+                        else { if (k133) CIN1(TT, 1, false); else CIN1(TT, 3, false); } } while (0)
+    if (dtype == B200SEG_F16) CIN1_T(__half); else CIN1_T(float);
+#undef CIN1_T
+#undef CIN1
     B200_CHECK_LAUNCH("wgrad_cin1_kernel");
     return B200SEG_OK;
   }
-  if (taps == 1 && a.Cout <= 16 && a.Cin <= 128) {
+  if (taps == 1 && a.Cout <= 16 && a.Cin <= 128 && a.Cin % 8 == 0 && a.x_ld % 8 == 0 && a.x_coff % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(a.x) & 15) == 0) {
     if (dtype == B200SEG_F16) {
-      if (a.Cout <= 4) wgrad_head_kernel<__half, 4><<<grid, kWarpsPerBlock * 32, 0, st>>>(a, vpw);
-      else wgrad_head_kernel<__half, 16><<<grid, kWarpsPerBlock * 32, 0, st>>>(a, vpw);
+      if (a.Cout <= 4) wgrad_head_kernel<__half, 4, 8><<<grid, 256, 0, st>>>(a);
+      else wgrad_head_kernel<__half, 16, 2><<<grid, 256, 0, st>>>(a);
     } else {
-      if (a.Cout <= 4) wgrad_head_kernel<float, 4><<<grid, kWarpsPerBlock * 32, 0, st>>>(a, vpw);
-      else wgrad_head_kernel<float, 16><<<grid, kWarpsPerBlock * 32, 0, st>>>(a, vpw);
+      if (a.Cout <= 4) wgrad_head_kernel<float, 4, 8><<<grid, 256, 0, st>>>(a);
+      else wgrad_head_kernel<float, 16, 2><<<grid, 256, 0, st>>>(a);
     }
     B200_CHECK_LAUNCH("wgrad_head_kernel");
     return B200SEG_OK;

@@ -35,7 +35,15 @@ class DiceLoss(nn.Module):
         self.beta = beta
 
     def forward(self, preds, targets):
-        return DiceCEFn.apply(preds, targets, None, 0.0, 1.0)
+        loss = DiceCEFn.apply(preds, targets, None, 0.0, 1.0)
+        # the reference overwrites self.alpha / self.beta with the per-class tensors it just computed
+        # (training/losses.py:38-41); the kernel leaves alpha_c in its stats buffer (dice_ce.cu: out[4+2C+c])
+        st = getattr(DiceCEFn, "last_stats", None)
+        if st is not None:
+            C = preds.shape[1]
+            self.alpha = st[4 + 2 * C:4 + 3 * C].detach().clone()
+            self.beta = 1.0 - self.alpha
+        return loss
 
 
 class CrossEntropyLoss(nn.Module):

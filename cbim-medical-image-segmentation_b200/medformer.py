@@ -436,11 +436,17 @@ class MedFormer(nn.Module):
         self.outc = nn.Conv3d(chan_num[7], num_classes, kernel_size=1)
         self.num_classes = num_classes
         self._pack_out, self._pack_aux = PackedWeights(), PackedWeights()
+        self._packs = ops.PackRegistry(self)
 
     def forward(self, x):
         if not x.is_cuda:
             raise ops._lib.B200SegError("b200seg.MedFormer runs on a B200 only — there is no CPU fallback")
+        with ops.on_device(x):
+            return self._forward(x)
+
+    def _forward(self, x):
         dt = ops.compute_dtype()
+        self._packs.refresh()           # every packed weight image is rebuilt from the live parameters (one launch)
         xin = x.permute(0, 2, 3, 4, 1).to(dt).contiguous()
         x0 = self.inc(xin)
         x1, _ = self.down1(x0)

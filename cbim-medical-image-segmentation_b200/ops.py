@@ -32,14 +32,34 @@ def _stream():
 
 
 def _need_cuda(t):
+    """Kernels launch on the CURRENT device and stream: a tensor that lives elsewhere would be an illegal address
+    or a cross-stream race, so it is an error (models switch device themselves, see `on_device`)."""
     if not t.is_cuda:
         raise _lib.B200SegError("b200seg ops need CUDA tensors on a B200 — there is no CPU fallback")
+    if t.device.type == "cuda" and t.device.index != torch.cuda.current_device():
+        raise _lib.B200SegError("tensor lives on %s but the current CUDA device is cuda:%d — wrap the call in "
+                                "torch.cuda.device(tensor.device)" % (t.device, torch.cuda.current_device()))
+
+
+def on_device(t):
+    """Context manager making t's device current (model.forward uses it, so DDP ranks / multi-device processes
+    launch on the right GPU and the right current stream)."""
+    if t.device.type != "cuda":         # CPU-emulated host-logic tests; real ops reject such tensors in _need_cuda
+        import contextlib
+        return contextlib.nullcontext()
+    return torch.cuda.device(t.device)
 
 
 def compute_dtype():
     """fp16 storage/tensor-core operands under torch.autocast (the reference's --amp path,
     train_ddp.py:181), fp32 otherwise."""
-    return torch.float16 if torch.is_autocast_enabled() else torch.float32
+    if not torch.is_autocast_enabled():
+        return torch.float32
+    adt = torch.get_autocast_dtype("cuda")
+    if adt != torch.float16:
+        raise _lib.B200SegError("b200seg implements fp16 autocast (the reference's --amp path); autocast dtype %s is "
+                                "not supported — use torch.autocast('cuda', dtype=torch.float16)" % adt)
+    return torch.float16
 
 
 def new_stats(B, C, device):
@@ -160,19 +180,35 @@ def instnorm_stats(x, x_coff, C):
 
 # ----------------------------------------------------------------------------- weight cache
 class PackedWeights:
-    """Per-module cache of packed (fwd and dgrad) weights, keyed on the parameters' version counters so a
-    repack happens once per optimiser step, not once per use (SURVEY.md §8b "Ownership")."""
+    """Per-module holder of the packed (fwd and dgrad) images of one (possibly fused) conv weight.
+
+    Staleness rule: an in-place write through ``.data`` — the reference's own
+    ``update_ema_variables`` (training/utils.py:99-102) — does not bump ``Tensor._version``, so version counters
+    cannot prove an image fresh.  Instead the images are simply rebuilt on EVERY forward:
+      * a holder attached to a ``PackRegistry`` (every b200seg model attaches its holders) is refreshed by the
+        registry's single multi-tensor launch at the top of ``model.forward`` (≈60 us for 40 M parameters);
+      * a free-standing holder (unit tests driving one block) re-packs inside ``get`` with per-weight launches.
+    What IS cached is the allocation and the job description, keyed on (dtype, B, co_pad, data_ptrs, shapes)."""
 
     def __init__(self):
-        self._key = None
+        self._sig = None
         self._fwd = None
         self._bwd = None
+        self._jobs = []           # [(weight, out tensor, transpose_flip, co_off, co_total, layout)]
+        self._registry = None
+        self._epoch = -1
+
+    def _signature(self, weights, dtype, B, co_pad):
+        return (dtype, B, co_pad) + tuple((w.data_ptr(), tuple(w.shape)) for w in weights)
 
     def get(self, weights, dtype, B=1, co_pad=0):
         """co_pad extra all-zero output channels are appended (Cout not a multiple of 8/16, e.g. the 27 map codes
         or 14 classes of MedFormer) so the wide-tile kernels and 16-byte stores apply; callers ignore them."""
-        key = (dtype, B, co_pad) + tuple((w.data_ptr(), w._version) for w in weights)
-        if key != self._key:
+        sig = self._signature(weights, dtype, B, co_pad)
+        reg = self._registry
+        if sig == self._sig and reg is not None and self._epoch == reg.epoch:
+            return self._fwd, self._bwd           # refreshed by the registry's launch of this forward
+        if sig != self._sig:
             co_total = sum(w.shape[0] for w in weights) + co_pad
             Cin = weights[0].shape[1]
             ks = tuple(weights[0].shape[2:])
@@ -183,13 +219,66 @@ class PackedWeights:
             alloc = torch.zeros if co_pad else torch.empty
             fwd = alloc(taps * co_total * Cin, dtype=dtype, device=dev)
             bwd = alloc(taps * co_total * Cin, dtype=dtype, device=dev)
-            off = 0
+            jobs, off = [], 0
             for w in weights:
-                pack_weight(w, dtype, False, fwd, off, co_total, algo_f)
-                pack_weight(w, dtype, True, bwd, off, co_total, algo_b)
+                jobs.append((w, fwd, False, off, co_total, algo_f))
+                jobs.append((w, bwd, True, off, co_total, algo_b))
                 off += w.shape[0]
-            self._key, self._fwd, self._bwd = key, (fwd, algo_f), (bwd, algo_b)
+            self._sig, self._fwd, self._bwd, self._jobs = sig, (fwd, algo_f), (bwd, algo_b), jobs
+            if reg is not None:
+                reg.dirty = True
+        for w, out, flip, off, co_total, layout in self._jobs:
+            pack_weight(w, out.dtype, flip, out, off, co_total, layout)
+        if reg is not None:
+            self._epoch = reg.epoch
         return self._fwd, self._bwd
+
+
+class PackRegistry:
+    """All PackedWeights holders of one model; ``refresh()`` re-packs every known weight with one launch."""
+
+    def __init__(self, model):
+        self.holders = []
+        for m in model.modules():
+            for v in vars(m).values():
+                for h in (v if isinstance(v, (list, tuple)) else (v,)):
+                    if isinstance(h, PackedWeights) and h._registry is None:
+                        h._registry = self
+                        self.holders.append(h)
+        self.epoch = 0
+        self.dirty = True
+        self._tables = None
+        self._table_sig = None
+
+    def refresh(self):
+        """Start a new forward: every holder that already knows its jobs is refreshed here in one launch; holders
+        seen for the first time (or whose dtype/batch changed) fall back to per-weight launches inside get()."""
+        self.epoch += 1
+        live = [h for h in self.holders if h._jobs]
+        if not live or live[0]._jobs[0][0].device.type != "cuda":
+            return                      # nothing known yet (first forward): get() packs lazily
+        tsig = tuple(h._sig for h in live)
+        if self.dirty or tsig != self._table_sig:
+            chunk = _lib.load().b200seg_pack_chunk_elems()
+            jobs, chunks = [], []
+            for h in live:
+                for w, out, flip, off, co_total, layout in h._jobs:
+                    if w.dtype != torch.float32 or not w.is_contiguous():
+                        raise _lib.B200SegError("conv weights must be contiguous fp32 parameters")
+                    taps = w[0, 0].numel()
+                    j = len(jobs)
+                    jobs.append([w.data_ptr(), out.data_ptr(), w.shape[0], w.shape[1], taps, _dt(out),
+                                 1 if flip else 0, off, co_total, 1 if layout == ALGO_TC else 0])
+                    chunks.extend([j, e] for e in range(0, w.numel(), chunk))
+            dev = live[0]._jobs[0][0].device
+            self._tables = (torch.tensor(jobs, dtype=torch.int64).to(dev), torch.tensor(chunks, dtype=torch.int64).to(dev),
+                            len(chunks))
+            self._table_sig, self.dirty = tsig, False
+        jt, ct, n = self._tables
+        with torch.cuda.device(jt.device):
+            call("b200seg_pack_weights_multi", jt.data_ptr(), ct.data_ptr(), n, _stream())
+        for h in live:
+            h._epoch = self.epoch
 
 
 # ----------------------------------------------------------------------------- autograd Functions
@@ -404,6 +493,8 @@ class DiceCEFn(torch.autograd.Function):
     """ce_scale*CrossEntropy(weight) + dice_scale*DiceLoss in one pass each way
     (training/losses.py:18-58, train_ddp.py:93,186-191)."""
 
+    last_stats = None     # the kernel's stats buffer of the most recent forward ({loss, ce, dice, wsum}, dTP, dSP, alpha_c, dice_c)
+
     @staticmethod
     def forward(ctx, logits, labels, weight, ce_scale, dice_scale):
         _need_cuda(logits)
@@ -441,6 +532,7 @@ class DiceCEFn(torch.autograd.Function):
              B, V, C, float(ce_scale), float(dice_scale), partial.data_ptr(), out.data_ptr(), _stream())
         ctx.save_for_backward(lg, labels, out, wt if wt is not None else torch.empty(0, device=dev))
         ctx.meta = (B, V, C, sb, sv, sc, lb, float(ce_scale), float(dice_scale), wt is not None, logits.shape)
+        DiceCEFn.last_stats = out
         return out[0].clone()
 
     @staticmethod

@@ -38,6 +38,9 @@ class TrainStep:
 
     def _loss(self, result, label):
         if isinstance(result, (tuple, list)):
+            if self.aux_weight is None or len(self.aux_weight) < len(result):
+                raise ValueError("the model returned %d outputs (deep supervision, train_ddp.py:186-189): pass "
+                                 "aux_weight with one weight per output" % len(result))
             return sum(self.aux_weight[j] * self.criterion(r, label) for j, r in enumerate(result))
         return self.criterion(result, label)
 

@@ -185,11 +185,17 @@ class UNet(nn.Module):
         self.up4 = up_block(2 * base_ch, base_ch, num_block, blk, kernel_size[0], scale[0])
         self.outc = nn.Conv3d(base_ch, num_classes, kernel_size=1)
         self._pack_out = PackedWeights()
+        self._packs = ops.PackRegistry(self)
 
     def forward(self, x):
         if not x.is_cuda:
             raise ops._lib.B200SegError("b200seg.UNet runs on a B200 only — there is no CPU fallback")
+        with ops.on_device(x):
+            return self._forward(x)
+
+    def _forward(self, x):
         dt = ops.compute_dtype()
+        self._packs.refresh()           # every packed weight image is rebuilt from the live parameters (one launch)
         # boundary: NCDHW-shaped input -> NDHWC working layout (free when in_ch == 1)
         xin = x.permute(0, 2, 3, 4, 1)
         xin = xin.to(dt).contiguous()

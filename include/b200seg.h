@@ -143,6 +143,17 @@ int b200seg_pack_weight(const float* w, int Cout, int Cin, int taps,
                         void* w_packed, int dtype, int transpose_flip,
                         int co_off, int co_total, int layout, void* stream);
 
+/* Multi-tensor form of b200seg_pack_weight: one launch re-packs every weight of a
+ * model (called once per forward, so an in-place `.data` update of a parameter —
+ * the reference's EMA, training/utils.py:99-102 — can never leave a stale image).
+ *   jobs_dev  : int64 [njobs][10] = {w ptr, out ptr, Cout, Cin, taps, dtype,
+ *               transpose_flip, co_off, co_total, layout==TC}
+ *   chunks_dev: int64 [nchunks][2] = {job index, first element}; every chunk
+ *               covers b200seg_pack_chunk_elems() consecutive elements of w. */
+int b200seg_pack_chunk_elems(void);
+int b200seg_pack_weights_multi(const int64_t* jobs_dev, const int64_t* chunks_dev,
+                               int nchunks, void* stream);
+
 /* Which algorithm (B200SEG_ALGO_TC or _DIRECT) serves a conv of this shape.  The
  * packed-weight layout is per algorithm (`layout` above = this value):
  *   DIRECT: [tap][Cout][Cin];
