@@ -42,8 +42,6 @@ _PROTOS = {
     "b200seg_maxpool3d_bwd": [P, I, I, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "b200seg_upsample_trilinear_fwd": [P, I, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P],
     "b200seg_upsample_trilinear_bwd": [P, I, I, P, I, I, I, I, I, I, I, I, I, I, I, I, P],
-    "b200seg_debug_tc_timers": [P],
-    "b200seg_debug_tc_trace": [P],
     "b200seg_copy_channels": [P, I, I, I, P, I, I, I, I, L, I, P],
     "b200seg_dwconv3d_fwd": [P, I, I, P, F, I, P, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P],
     "b200seg_dwconv3d_wgrad": [P, I, I, P, F, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P],
@@ -105,7 +103,7 @@ def check(rc, what):
 
 
 # kernels launched per entry point (dice fwd = reduce + finalize; its memset is not ours)
-_KERNELS = {"b200seg_dice_ce_fwd": 2, "b200seg_conv3d_wgrad": 3, "b200seg_biattn_fwd": 2, "b200seg_biattn_bwd": 2,
+_KERNELS = {"b200seg_dice_ce_fwd": 2, "b200seg_biattn_fwd": 2, "b200seg_biattn_bwd": 2,
             "b200seg_mapgen_fwd": 2}
 launch_count = 0
 

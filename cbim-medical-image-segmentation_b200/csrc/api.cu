@@ -102,8 +102,7 @@ extern "C" int b200seg_conv3d_wgrad(const void* x, int x_ld, int x_coff, const d
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if (algo == B200SEG_ALGO_TC) return conv3d_wgrad_tc(a, dtype, workspace, ws_bytes, st);
-  if (algo == B200SEG_ALGO_AUTO && conv3d_wgrad_tc_supported(a, dtype) && workspace &&
-      ws_bytes >= conv3d_wgrad_tc_workspace(a))
+  if (algo == B200SEG_ALGO_AUTO && conv3d_wgrad_tc_supported(a, dtype))
     return conv3d_wgrad_tc(a, dtype, workspace, ws_bytes, st);
   if (algo != B200SEG_ALGO_AUTO && algo != B200SEG_ALGO_DIRECT) return B200SEG_EINVAL;
   if (algo == B200SEG_ALGO_AUTO) {

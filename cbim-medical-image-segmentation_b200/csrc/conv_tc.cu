@@ -10,39 +10,51 @@
 //     once in shared memory as [KC/8][halo voxel][8 ch] (UMMA K-major, no-swizzle core matrices:
 //     8 consecutive w-voxels x 16 B).  Every (kh,kw) tap reads the SAME staged tile through a shifted
 //     matrix descriptor (start += (zh*HALO_W + zw)*16 B, SBO = HALO_W*16 B) — im2col is never formed.
-//     The loader warps apply InstanceNorm-normalise + ReLU while staging (the normalised activation
-//     tensor never exists in HBM) and zero-fill padding / ragged-tile voxels.
+//   * Staging (round 2): the loader warps no longer hold the tile in registers across the global-memory
+//     latency.  They issue 16-byte cp.async copies (LDGSTS, zero-fill for padding / ragged tiles) for up to three
+//     stages AHEAD, and when a stage has landed apply InstanceNorm-normalise + ReLU IN PLACE in shared memory
+//     (skipped for raw inputs: every data-gradient launch), then publish it to the tensor core.  The normalised
+//     activation tensor never exists in HBM.
 //   * B operand = weights pre-packed on device into the exact shared-memory image per (ntile,tap,kchunk)
-//     ([KC/8][NT][8] fp16), streamed by 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) through an mbarrier ring.
-//   * D lives in TMEM (double-buffered when 2*NT <= 512 columns); 4 epilogue warps drain it with
-//     tcgen05.ld while the MMA warp already works on the next tile.
-// Warp roles (448 threads, 1 CTA/SM, persistent over tiles):
-//   warps 0-3  epilogue (TMEM lane quadrant == warp id): bias / residual / dgrad ReLU-mask, fp16 store,
-//              InstanceNorm sums (or IN-backward sums) of what was stored
-//   warps 4-11 A loaders, two groups of 4 warps working on alternating stages
+//     ([KC/8][NT][8] fp16): resident for the CTA's lifetime when the layer's weights fit (<=112 KB), else streamed
+//     by 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) through an mbarrier ring.
+//   * D lives in TMEM (double-buffered when 2*NT <= 512 columns); EIGHT epilogue warps (two per TMEM lane
+//     quadrant, alternating 16-column chunks) drain it with tcgen05.ld while the MMA warp works on the next tile.
+//     InstanceNorm sums of the stored tile: for NT <= 64 per-thread register accumulators carried across all the
+//     tiles of the persistent CTA (2 FP ops per value instead of a 16-shuffle butterfly per chunk) and reduced
+//     once at the end; for wider tiles the butterfly (the MMA time hides it there).
+// Warp roles (512 threads = 4 warpgroups, 1 CTA/SM, persistent over tiles; `setmaxnreg` moves registers from the
+// loader / MMA warpgroups to the two epilogue warpgroups, whose statistics accumulators need them):
+//   warps 0-7  epilogue (TMEM lane quadrant == warp id & 3): bias / residual / dgrad ReLU-mask, fp16 store, IN sums
+//   warps 8-11 A loaders (cp.async prefetch + in-place transform)
 //   warp  12   weight producer (bulk TMA)
 //   warp  13   TMEM alloc + tcgen05.mma issue (highest warp id = highest issue priority)
 // Roofline: tensor pipe (dense fp16) for NT>=128; for NT<128 the MMA is bound by the shared-memory read of
-// A (SS mode), see DESIGN.md.
+// A (SS mode: 4 KB per 128xNTx16 instruction, ~52 cycles), see DESIGN.md.
 #include "common.cuh"
 #include "conv_args.h"
+#include "tc_common.cuh"
 #include <string.h>
-#include <stdio.h>
 #include <stdlib.h>
 
 namespace {
 
+using namespace tc;
+
 constexpr int TH = 16, TW = 8;            // output tile (h, w); M = 128
-constexpr int kEpiWarps = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kStatCopies = 4;            // per TMEM lane quadrant (the two warps of a quadrant own disjoint columns)
 // The SM arbitrates highest-warp-id-first inside a sub-partition (B300_MICROARCH.md): the single MMA-issuing warp
 // must never queue behind ALU-heavy loader / epilogue warps, so it gets the highest id (measured: 4-5x faster issue).
-constexpr int kLoadWarp0 = 4;
+constexpr int kLoadWarp0 = 8;
+constexpr int kLoadThreads = 128;
 constexpr int kWgtWarp = 12;
 constexpr int kMmaWarp = 13;
-constexpr int kLoadGroups = 2;
-constexpr int kLoadGroupThreads = 128;
-constexpr int kThreads = 14 * 32;   // 448
-constexpr uint32_t kSpinLimit = 1u << 24;
+constexpr int kThreads = 16 * 32;   // 512: four complete warpgroups (setmaxnreg is a warpgroup-wide instruction);
+                                    // warps 14-15 only take part in the block-wide barriers
+// registers per thread after the role dispatch (launch allotment: 65536 / 512 = 128 each):
+//   2 epilogue warpgroups x 184 + loader warpgroup x 72 + {weights, MMA, 2 idle} x 72  == 65536
+constexpr int kRegsEpi = 184, kRegsLoad = 72, kRegsMma = 72;
 
 struct TcParams {
   ConvArgs a;
@@ -53,114 +65,9 @@ struct TcParams {
   int tiles_h, tiles_w, n_tiles;
   int tmem_cols, acc_stages;
   int w_resident;          // all weights of the layer live in shared memory for the CTA's lifetime (no B ring)
+  int prefetch;            // A stages the loaders keep in flight (1..3, < SA)
   int smem_a_off, smem_b_off, smem_bar_off, smem_norm_off, smem_gnorm_off, smem_stat_off;
-  int* err_flag;
-  int debug;
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.  The diagnostics
-// live out of line so the polling loop stays a handful of instructions (the single MMA-issuing thread runs it
-// once per weight tile).
-__device__ __noinline__ void mbar_timeout(int* err_flag, int code, uint32_t parity) {
-  if (err_flag) atomicExch(err_flag, code);
-  printf("b200seg conv_tc: mbarrier timeout code=%d block=%d thread=%d parity=%u\n", code, blockIdx.x, threadIdx.x, parity);
-  __trap();
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > kSpinLimit) mbar_timeout(err_flag, code, parity);
-  }
-}
-// The MMA warp's variant: NO function call on the slow path.  A call inside the issue loop makes the compiler keep
-// the loop-carried descriptors in vector registers, and every tcgen05.mma then needs five R2UR.BROADCASTs
-// (~250 cycles per MMA measured); with the inline trap the whole loop runs on the uniform datapath.
-__device__ __forceinline__ void mbar_wait_nocall(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > kSpinLimit) __trap();
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], fp16 x fp16 -> fp32
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory matrix descriptor, SWIZZLE_NONE (cute::UMMA::SmemDescriptor, version 1 = sm_100)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;      // descriptor version (Blackwell)
-  return d;                    // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
-}
-
-// optional cycle accounting of block 0 (B200SEG_TC_DEBUG=1): where each warp role spends its time
-__device__ long long g_tc_dbg[32];
-__device__ long long g_tc_trace[4][256];   // [role][event] raw clock64 stamps of block 0 (roles: 0 mma, 1 loader g0, 2 loader g1, 3 epilogue)
-#define TRACE(role, idx) do { const int _i = (idx); if (dbg && _i < 256) g_tc_trace[role][_i] = clock64(); } while (0)
-#define DBG_ADD(slot, val) do { if (dbg) atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_dbg[slot]), (unsigned long long)(val)); } while (0)
-
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred;
-}
 
 // Straight-line issue of one staged halo tile against RESIDENT weights: every tap and K step unrolled, descriptor low
 // words are `base + compile-time-shaped offsets`, high words constant.  ~5 uniform instructions per tcgen05.mma
@@ -186,65 +93,338 @@ __device__ __forceinline__ void issue_stage_resident(uint32_t tmem_d, uint64_t d
   }
 }
 
-struct Ring {
-  int idx; uint32_t phase; int n;
-  __device__ __forceinline__ void init(int n_) { idx = 0; phase = 0; n = n_; }
-  __device__ __forceinline__ void advance() { if (++idx == n) { idx = 0; phase ^= 1; } }
-};
-
-// sum over the 32 lanes of v[j] for every j in 0..15; lane L returns column
-// ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1)   (v is clobbered)
-__device__ __forceinline__ float column_sum16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float send = (lane & 16) ? v[i] : v[i + 8], keep = (lane & 16) ? v[i + 8] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float send = (lane & 8) ? v[i] : v[i + 4], keep = (lane & 8) ? v[i + 4] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float send = (lane & 4) ? v[i] : v[i + 2], keep = (lane & 4) ? v[i + 2] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  {
-    const float send = (lane & 2) ? v[0] : v[1], keep = (lane & 2) ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
 struct TileCoord { int b, d, h0, w0, ntile; };
 // Persistent tile walk t = blockIdx.x, +gridDim.x, ... as a mixed-radix counter (ntile, w-tile, h-tile, d, b):
 // one set of divisions per kernel instead of four per tile per warp role (~1000 cycles/tile measured).
-struct TileIter {
-  int ntile, wi, hi, d, b;          // current digits
+// TileWalk = the constants of the walk (radices, digits of the stride); TileIter = one position on it.
+struct TileWalk {
   int s0, s1, s2, s3, s4;           // digits of the stride
   int r0, r1, r2, r3;               // radices
-  int t, n_tiles, stride;
+  int n_tiles, stride;
   __device__ __forceinline__ void init(const TcParams& p) {
     r0 = p.NTILES; r1 = p.tiles_w; r2 = p.tiles_h; r3 = p.a.D;
-    n_tiles = p.n_tiles; stride = gridDim.x; t = blockIdx.x;
-    int x = t;
-    ntile = x % r0; x /= r0; wi = x % r1; x /= r1; hi = x % r2; x /= r2; d = x % r3; b = x / r3;
-    x = stride;
+    n_tiles = p.n_tiles; stride = gridDim.x;
+    int x = stride;
     s0 = x % r0; x /= r0; s1 = x % r1; x /= r1; s2 = x % r2; x /= r2; s3 = x % r3; s4 = x / r3;
   }
-  __device__ __forceinline__ bool valid() const { return t < n_tiles; }
+};
+struct TileIter {
+  int ntile, wi, hi, d, b, t;       // current digits, linear index
+  __device__ __forceinline__ void init(const TileWalk& k) {
+    t = blockIdx.x;
+    int x = t;
+    ntile = x % k.r0; x /= k.r0; wi = x % k.r1; x /= k.r1; hi = x % k.r2; x /= k.r2; d = x % k.r3; b = x / k.r3;
+  }
+  __device__ __forceinline__ bool valid(const TileWalk& k) const { return t < k.n_tiles; }
   __device__ __forceinline__ TileCoord coord() const { TileCoord c; c.b = b; c.d = d; c.h0 = hi * TH; c.w0 = wi * TW; c.ntile = ntile; return c; }
-  __device__ __forceinline__ void next() {
-    t += stride;
+  __device__ __forceinline__ void next(const TileWalk& k) {
+    t += k.stride;
     int c;
-    ntile += s0; c = ntile >= r0; if (c) ntile -= r0;
-    wi += s1 + c; c = wi >= r1; if (c) wi -= r1;
-    hi += s2 + c; c = hi >= r2; if (c) hi -= r2;
-    d += s3 + c; c = d >= r3; if (c) d -= r3;
-    b += s4 + c;
+    ntile += k.s0; c = ntile >= k.r0; if (c) ntile -= k.r0;
+    wi += k.s1 + c; c = wi >= k.r1; if (c) wi -= k.r1;
+    hi += k.s2 + c; c = hi >= k.r2; if (c) hi -= k.r2;
+    d += k.s3 + c; c = d >= k.r3; if (c) d -= k.r3;
+    b += k.s4 + c;
   }
 };
+
+// One A stage = (tile, K chunk, depth tap) with an in-volume input slice; the loaders walk them in exactly the order
+// the MMA warp consumes them: for tile { for kc { for zd { skip if din outside the volume } } }.
+struct StageCursor {
+  TileIter ti; int kc, zd, din;
+  __device__ __forceinline__ void init(const TileWalk& k, const TcParams& p) {
+    ti.init(k); kc = 0; zd = -1;
+    if (ti.valid(k)) next(k, p);
+  }
+  __device__ __forceinline__ bool valid(const TileWalk& k) const { return ti.valid(k); }
+  __device__ __forceinline__ void next(const TileWalk& k, const TcParams& p) {
+    for (;;) {
+      if (++zd == p.a.kd) { zd = 0; if (++kc == p.NKC) { kc = 0; ti.next(k); if (!ti.valid(k)) return; } }
+      din = ti.d + zd - p.a.kd / 2;
+      if ((unsigned)din < (unsigned)p.a.D) return;
+    }
+  }
+};
+
+// ------------------------------------------------------------------ A loaders
+// cp.async (LDGSTS) prefetch of P stages + in-place InstanceNorm/ReLU once a stage has landed.  Each thread owns ONE
+// 8-channel plane and a fixed set of halo voxels of it, copies exactly those chunks and later transforms exactly
+// those chunks, so no cross-thread synchronisation is needed between the copy and the transform.
+template <int P>
+__device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, const float2* s_norm, uint32_t bar0) {
+  const ConvArgs& a = p.a;
+  const int lt = threadIdx.x - kLoadWarp0 * 32;
+  const int cpv = p.KC / 8;
+  const int vstep = kLoadThreads / cpv;
+  const bool active = lt < vstep * cpv;
+  const int c8 = lt % cpv, v0 = lt / cpv;
+  const int sh = vstep / p.HALO_W, sw = vstep % p.HALO_W;
+  const int hh0 = v0 / p.HALO_W, ww0 = v0 % p.HALO_W;
+  const int ph = a.kh / 2, pw = a.kw / 2;
+  const bool xform = (a.x_stats != nullptr) || (a.act != 0);
+  const __half* xbase = reinterpret_cast<const __half*>(a.x);
+  const uint32_t smem_a = smem_u32(smem + p.smem_a_off) + (uint32_t)(c8 * p.plane_stride);
+  uint8_t* smem_a_gen = smem + p.smem_a_off + c8 * p.plane_stride;
+  auto A_FULL = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  auto A_EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(p.SA + i); };
+
+  TileWalk tw; tw.init(p);
+  StageCursor ci, cd;
+  ci.init(tw, p); cd.init(tw, p);
+  Ring ri, rd; ri.init(p.SA); rd.init(p.SA);
+
+  auto issue = [&]() {
+    mbar_wait(A_EMPTY(ri.idx), ri.phase ^ 1, 1);
+    if (active) {
+      const uint32_t dst = smem_a + (uint32_t)(ri.idx * p.a_stage_bytes);
+      const __half* xs = xbase + ((int64_t)(ci.ti.b * a.D + ci.din) * a.H * a.W) * a.x_ld + a.x_coff + ci.kc * p.KC + c8 * 8;
+      const int hb = ci.ti.hi * TH - ph, wb = ci.ti.wi * TW - pw;
+      int hh = hh0, ww = ww0;
+#pragma unroll 4
+      for (int v = v0; v < p.nvox_h; v += vstep) {
+        const int h = hb + hh, w = wb + ww;
+        const bool ok = ((unsigned)h < (unsigned)a.H) && ((unsigned)w < (unsigned)a.W);
+        cp_async16(dst + (uint32_t)v * 16u, ok ? (const void*)(xs + ((int64_t)h * a.W + w) * a.x_ld) : (const void*)xbase, ok ? 16u : 0u);
+        hh += sh; ww += sw;
+        if (ww >= p.HALO_W) { ww -= p.HALO_W; ++hh; }
+      }
+    }
+    ri.advance(); ci.next(tw, p);
+  };
+
+#pragma unroll
+  for (int i = 0; i < P; ++i) { if (ci.valid(tw)) issue(); cp_async_commit(); }
+  while (cd.valid(tw)) {
+    cp_async_wait<P - 1>();                       // this thread's copies of the oldest stage have landed
+    if (xform && active) {
+      uint8_t* sp = smem_a_gen + rd.idx * p.a_stage_bytes;
+      float sc[8], sf[8];                          // x*sc + sf == (x - mean) * rstd
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 mr = s_norm[cd.ti.b * a.Cin + cd.kc * p.KC + c8 * 8 + j];
+        sc[j] = mr.y; sf[j] = -mr.x * mr.y;
+      }
+      const int hb = cd.ti.hi * TH - ph, wb = cd.ti.wi * TW - pw;
+      int hh = hh0, ww = ww0;
+      const bool relu = a.act == B200SEG_ACT_RELU;
+#pragma unroll 2
+      for (int v = v0; v < p.nvox_h; v += vstep) {
+        const int h = hb + hh, w = wb + ww;
+        // zero-filled padding voxels must stay zero: the conv pads the NORMALISED activation
+        if (((unsigned)h < (unsigned)a.H) && ((unsigned)w < (unsigned)a.W)) {
+          uint4 raw = *reinterpret_cast<const uint4*>(sp + v * 16);
+          __half2* hv = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f = __half22float2(hv[j]);
+            f.x = fmaf(f.x, sc[2 * j], sf[2 * j]); f.y = fmaf(f.y, sc[2 * j + 1], sf[2 * j + 1]);
+            if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+            hv[j] = __floats2half2_rn(f.x, f.y);
+          }
+          *reinterpret_cast<uint4*>(sp + v * 16) = raw;
+        }
+        hh += sh; ww += sw;
+        if (ww >= p.HALO_W) { ww -= p.HALO_W; ++hh; }
+      }
+    }
+    fence_proxy_async();            // generic-proxy / cp.async writes -> visible to the tensor core (async proxy)
+    mbar_arrive(A_FULL(rd.idx));
+    rd.advance(); cd.next(tw, p);
+    if (ci.valid(tw)) issue();
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------ epilogue
+// One 16-column chunk of one accumulator row: bias / residual / dgrad mask, fp16 rounding, store.  On return r[] holds
+// the STORED values (0 for rows outside the volume) and s2[] the second statistics operand (r^2, or g*xhat for dgrad).
+__device__ __forceinline__ void epi_chunk(const ConvArgs& a, bool valid, bool dgrad, const uint32_t (&v)[16], const uint4& cur0,
+                                          const uint4& cur1, bool has_side, bool is_res, const float2* gnorm, const float* bias,
+                                          __half* yout, float (&r)[16], float (&s2)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) r[j] = __uint_as_float(v[j]);
+  if (!valid) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { r[j] = 0.f; s2[j] = 0.f; }
+    return;
+  }
+  if (bias) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] += bias[j];
+  }
+  float sv[16];
+  if (has_side) {
+    const __half2* h0 = reinterpret_cast<const __half2*>(&cur0);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&cur1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f0 = __half22float2(h0[j]), f1 = __half22float2(h1[j]);
+      sv[2 * j] = f0.x; sv[2 * j + 1] = f0.y; sv[8 + 2 * j] = f1.x; sv[8 + 2 * j + 1] = f1.y;
+    }
+  }
+  if (dgrad) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float2 mr = gnorm[j];
+      const float hx = (sv[j] - mr.x) * mr.y;
+      float g = (a.g_act == B200SEG_ACT_RELU && !(hx > 0.f)) ? 0.f : r[j];
+      g = __half2float(__float2half_rn(g));
+      r[j] = g; s2[j] = g * hx;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = __half2float(__float2half_rn(r[j]));
+    if (is_res) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = __half2float(__float2half_rn(r[j] + sv[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s2[j] = r[j] * r[j];
+  }
+  st8<__half>(yout, reinterpret_cast<const float(&)[8]>(r[0]));
+  st8<__half>(yout + 8, reinterpret_cast<const float(&)[8]>(r[8]));
+}
+
+// REGSTATS: NT <= 64 (at most two chunks per warp); the InstanceNorm sums live in registers across all tiles.
+struct EpiCtx {
+  const TcParams* p; int q, half, lane, nchunks; bool dgrad, want_stats;
+  float* s_stat; const float2* s_gnorm;
+};
+
+// flush one chunk's register accumulators into the quadrant's shared partial sums (once per CTA, or on a batch change)
+__device__ __forceinline__ void flush_chunk(const EpiCtx& e, int c, int b, float (&as)[16], float (&aq)[16]) {
+  if (c >= e.nchunks) return;
+  const float u = column_sum16(as, e.lane), q2 = column_sum16(aq, e.lane);
+  if ((e.lane & 1) == 0) {
+    float* ws = e.s_stat + ((e.q * e.p->a.B + b) * e.p->a.Cout + 16 * c + column_of_lane16(e.lane)) * 2;
+    ws[0] += u; ws[1] += q2;
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { as[j] = 0.f; aq[j] = 0.f; }
+}
+
+// one chunk of one tile on the register-statistics path
+__device__ __forceinline__ void reg_chunk(const EpiCtx& e, int c, uint32_t trow, uint32_t t_empty, bool valid, const uint4& sd0,
+                                          const uint4& sd1, bool has_side, const float2* gn, const float* bias, __half* yp,
+                                          float (&as)[16], float (&aq)[16]) {
+  if (c >= e.nchunks) return;
+  uint32_t v[16];
+  tmem_ld16(trow + (uint32_t)(16 * c), v);
+  tmem_ld_wait();
+  if (c + 2 >= e.nchunks) {       // last chunk of this warp is in registers: hand the TMEM buffer back now
+    tc_fence_before();
+    mbar_arrive(t_empty);
+  }
+  float r[16], s2[16];
+  epi_chunk(e.p->a, valid, e.dgrad, v, sd0, sd1, has_side, !e.dgrad && has_side, gn + 16 * c, bias ? bias + 16 * c : nullptr,
+            yp + 16 * c, r, s2);
+  if (e.want_stats) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { as[j] += r[j]; aq[j] += s2[j]; }
+  }
+}
+
+template <bool REGSTATS>
+__device__ __forceinline__ void epilogue_role(const TcParams& p, int warp, int lane, uint32_t tmem_base, uint32_t bar0,
+                                              const float2* s_gnorm, float* s_stat) {
+  const ConvArgs& a = p.a;
+  auto T_FULL = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.SA + 2 * p.SB + i); };
+  auto T_EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.SA + 2 * p.SB + 2 + i); };
+  EpiCtx e;
+  e.p = &p; e.q = warp & 3; e.half = warp >> 2; e.lane = lane; e.nchunks = p.NT >> 4;
+  e.dgrad = a.gx != nullptr; e.want_stats = a.y_stats != nullptr; e.s_stat = s_stat; e.s_gnorm = s_gnorm;
+  const int q = e.q, half = e.half;           // TMEM lane quadrant; which alternate 16-column chunks this warp owns
+  const int row = q * 32 + lane;              // GEMM row = hl*8 + wl
+  const int hl = row >> 3, wl = row & 7;
+  const bool dgrad = e.dgrad, want_stats = e.want_stats;
+  const int nchunks = e.nchunks;
+  float as0[16], aq0[16], as1[16], aq1[16];
+  int acc_b = -1;
+  if (REGSTATS) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { as0[j] = 0.f; aq0[j] = 0.f; as1[j] = 0.f; aq1[j] = 0.f; }
+  }
+  int it = 0;
+  TileWalk tw; tw.init(p); TileIter ti; ti.init(tw);
+  for (; ti.valid(tw); ti.next(tw), ++it) {
+    const TileCoord tc = ti.coord();
+    const int acc = (p.acc_stages == 2) ? (it & 1) : 0;
+    const uint32_t acc_phase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
+    const int h = tc.h0 + hl, w = tc.w0 + wl;
+    const bool valid = (h < a.H) && (w < a.W);
+    const int64_t vox = ((int64_t)(tc.b * a.D + tc.d) * a.H + h) * a.W + w;
+    const int co_base = tc.ntile * p.NT;
+    __half* yp = reinterpret_cast<__half*>(a.y) + vox * a.y_ld + a.y_coff + co_base;
+    // side input of the epilogue: the residual, or x for the dgrad ReLU mask
+    const __half* side = dgrad ? reinterpret_cast<const __half*>(a.gx) + vox * a.gx_ld + a.gx_coff + co_base
+                               : (a.res ? reinterpret_cast<const __half*>(a.res) + vox * a.r_ld + a.r_coff + co_base : nullptr);
+    const bool has_side = side != nullptr;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
+    const float2* gn = s_gnorm + tc.b * a.Cout + co_base;
+    const float* bias = a.bias ? a.bias + co_base : nullptr;
+    if (REGSTATS) {
+      if (want_stats && tc.b != acc_b) {
+        if (acc_b >= 0) { flush_chunk(e, half, acc_b, as0, aq0); flush_chunk(e, half + 2, acc_b, as1, aq1); }
+        acc_b = tc.b;
+      }
+      // both chunks' side inputs are requested BEFORE waiting for the accumulator: their latency hides behind the MMA
+      uint4 sd00 = make_uint4(0, 0, 0, 0), sd01 = sd00, sd10 = sd00, sd11 = sd00;
+      if (has_side && valid) {
+        if (half < nchunks) {
+          sd00 = __ldg(reinterpret_cast<const uint4*>(side + 16 * half));
+          sd01 = __ldg(reinterpret_cast<const uint4*>(side + 16 * half + 8));
+        }
+        if (half + 2 < nchunks) {
+          sd10 = __ldg(reinterpret_cast<const uint4*>(side + 16 * half + 32));
+          sd11 = __ldg(reinterpret_cast<const uint4*>(side + 16 * half + 40));
+        }
+      }
+      mbar_wait(T_FULL(acc), acc_phase, 6);
+      tc_fence_after();
+      reg_chunk(e, half, trow, T_EMPTY(acc), valid, sd00, sd01, has_side, gn, bias, yp, as0, aq0);
+      reg_chunk(e, half + 2, trow, T_EMPTY(acc), valid, sd10, sd11, has_side, gn, bias, yp, as1, aq1);
+      if (half >= nchunks) {            // a warp that owns no chunk of this tile (NT == 16) still has to release it
+        tc_fence_before();
+        mbar_arrive(T_EMPTY(acc));
+      }
+    } else {
+      float* wstat = s_stat + ((q * a.B + tc.b) * a.Cout + co_base) * 2;
+      uint4 nx0 = make_uint4(0, 0, 0, 0), nx1 = make_uint4(0, 0, 0, 0);
+      if (has_side && valid && half < nchunks) {
+        nx0 = __ldg(reinterpret_cast<const uint4*>(side + 16 * half));
+        nx1 = __ldg(reinterpret_cast<const uint4*>(side + 16 * half + 8));
+      }
+      mbar_wait(T_FULL(acc), acc_phase, 6);
+      tc_fence_after();
+      for (int c = half; c < nchunks; c += 2) {
+        const int n0 = 16 * c;
+        uint32_t v[16];
+        tmem_ld16(trow + (uint32_t)n0, v);
+        const uint4 cur0 = nx0, cur1 = nx1;
+        if (has_side && valid && c + 2 < nchunks) {        // one chunk AHEAD
+          nx0 = __ldg(reinterpret_cast<const uint4*>(side + n0 + 32));
+          nx1 = __ldg(reinterpret_cast<const uint4*>(side + n0 + 40));
+        }
+        tmem_ld_wait();
+        float r[16], s2[16];
+        epi_chunk(a, valid, dgrad, v, cur0, cur1, has_side, !dgrad && has_side, gn + n0, bias ? bias + n0 : nullptr, yp + n0, r, s2);
+        if (want_stats) {
+          // column sums over the warp's 32 rows with a halving butterfly: 16 shuffles per quantity
+          const float u = column_sum16(r, lane), q2 = column_sum16(s2, lane);
+          if ((lane & 1) == 0) {
+            const int col = column_of_lane16(lane);
+            wstat[(n0 + col) * 2] += u;
+            wstat[(n0 + col) * 2 + 1] += q2;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(T_EMPTY(acc));
+    }
+  }
+  if (REGSTATS && want_stats && acc_b >= 0) { flush_chunk(e, half, acc_b, as0, aq0); flush_chunk(e, half + 2, acc_b, as1, aq1); }
+}
 
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(kThreads, 1)
@@ -255,7 +435,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   // branches and the MMA warp's loop compiles to the uniform datapath (UIADD3 + UTCHMMA, no R2UR per operand)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int taps_hw = a.kh * a.kw;
-  const int pd = a.kd / 2, ph = a.kh / 2, pw = a.kw / 2;
+  const int pd = a.kd / 2;
 
   // barrier block layout (uint64 each): a_full[SA] a_empty[SA] b_full[SB] b_empty[SB] t_full[2] t_empty[2]; then tmem ptr
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.smem_bar_off);
@@ -270,13 +450,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 
   float2* s_norm = reinterpret_cast<float2*>(smem + p.smem_norm_off);   // [B][Cin] {mean, rstd}
   float2* s_gnorm = reinterpret_cast<float2*>(smem + p.smem_gnorm_off); // [B][Cout] {mean, rstd} of dgrad_x
-  float* s_stat = reinterpret_cast<float*>(smem + p.smem_stat_off);     // [4 warps][B][Cout][2]
+  float* s_stat = reinterpret_cast<float*>(smem + p.smem_stat_off);     // [4 quadrants][B][Cout][2]
   const uint32_t smem_a = smem_u32(smem + p.smem_a_off);
   const uint32_t smem_b = smem_u32(smem + p.smem_b_off);
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.SA; ++i) { mbar_init(A_FULL(i), kLoadGroupThreads); mbar_init(A_EMPTY(i), 1); }
+    for (int i = 0; i < p.SA; ++i) { mbar_init(A_FULL(i), kLoadThreads); mbar_init(A_EMPTY(i), 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(B_FULL(i), 1); mbar_init(B_EMPTY(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(T_FULL(i), 1); mbar_init(T_EMPTY(i), kEpiWarps * 32); }
     fence_barrier_init();
@@ -296,7 +476,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         s_gnorm[i] = make_float2(m, r);
       }
     }
-    const int nstat = kEpiWarps * a.B * a.Cout * 2;
+    const int nstat = kStatCopies * a.B * a.Cout * 2;
     for (int i = threadIdx.x; i < nstat; i += kThreads) s_stat[i] = 0.f;
   }
   tc_fence_before();
@@ -305,96 +485,16 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int ksteps = p.KC / 16;
-  const bool dbg = p.debug && blockIdx.x == 0;
 
   if (warp >= kLoadWarp0 && warp < kWgtWarp) {
     // =========================== A LOADERS ===========================
-    // Compact code on purpose: 14 warps run 4 different programs on this SM, and a loader body unrolled over its
-    // 12 chunks (~25 KB of SASS) evicted the MMA warp's tiny issue loop from the instruction cache on every
-    // iteration (measured ~300 cycles per tcgen05.mma instead of ~50).  Each thread owns ONE 8-channel plane
-    // (its InstanceNorm scale/shift live in registers for the whole stage) and walks the halo voxels in steps.
-    const int grp = (warp - kLoadWarp0) >> 2;
-    const int lt = threadIdx.x - (kLoadWarp0 * 32 + grp * kLoadGroupThreads);
-    const int cpv = p.KC / 8;
-    const int act_thr = (kLoadGroupThreads / cpv) * cpv;
-    const int vstep = kLoadGroupThreads / cpv;
-    const int c8 = lt % cpv, v0 = lt / cpv;
-    const int sh = vstep / p.HALO_W, sw = vstep % p.HALO_W;
-    const bool xform = (a.x_stats != nullptr) || (a.act != 0);
-    const __half* xbase = reinterpret_cast<const __half*>(a.x);
-    Ring ring; ring.init(p.SA);
-    int stage_no = 0, tr_l = 0;
-    TileIter ti; ti.init(p);
-    for (; ti.valid(); ti.next()) {
-      const TileCoord tc = ti.coord();
-      for (int kc = 0; kc < p.NKC; ++kc) {
-        for (int zd = 0; zd < a.kd; ++zd) {
-          const int din = tc.d + zd - pd;
-          if ((unsigned)din >= (unsigned)a.D) continue;
-          if ((stage_no & 1) == grp) {
-            const bool dl = dbg && grp == 0 && lt == 0;
-            long long q0 = 0, q1 = 0;
-            if (dl) q0 = clock64();
-            if (lt == 0) TRACE(1 + grp, tr_l++);                   // stage start (before A_EMPTY wait)
-            mbar_wait(A_EMPTY(ring.idx), ring.phase ^ 1, p.err_flag, 1);
-            if (lt == 0) TRACE(1 + grp, tr_l++);                   // slot free
-            if (dl) q1 = clock64();
-            if (lt < act_thr && !(p.debug & 2)) {
-              uint8_t* sdst = smem + p.smem_a_off + ring.idx * p.a_stage_bytes + c8 * p.plane_stride;
-              const __half* xs = xbase + ((int64_t)(tc.b * a.D + din) * a.H * a.W) * a.x_ld + a.x_coff + kc * p.KC + c8 * 8;
-              float sc[8], sf[8];          // x*sc + sf == (x - mean) * rstd
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 mr = s_norm[tc.b * a.Cin + kc * p.KC + c8 * 8 + j];
-                sc[j] = mr.y; sf[j] = -mr.x * mr.y;
-              }
-              int hh = v0 / p.HALO_W, ww = v0 % p.HALO_W;
-#pragma unroll 1
-              for (int v = v0; v < p.nvox_h; v += 6 * vstep) {
-                uint4 raw[6]; int vv[6]; bool ok[6];
-#pragma unroll
-                for (int u = 0; u < 6; ++u) {
-                  vv[u] = hh * p.HALO_W + ww;
-                  const int h = tc.h0 - ph + hh, w = tc.w0 - pw + ww;
-                  ok[u] = (vv[u] < p.nvox_h) && ((unsigned)h < (unsigned)a.H) && ((unsigned)w < (unsigned)a.W);
-                  raw[u] = make_uint4(0, 0, 0, 0);
-                  if (ok[u]) raw[u] = __ldg(reinterpret_cast<const uint4*>(xs + ((int64_t)h * a.W + w) * a.x_ld));
-                  hh += sh; ww += sw;
-                  if (ww >= p.HALO_W) { ww -= p.HALO_W; ++hh; }
-                }
-#pragma unroll
-                for (int u = 0; u < 6; ++u) {
-                  if (vv[u] >= p.nvox_h) continue;
-                  uint4 o = raw[u];
-                  if (ok[u] && xform) {
-                    const __half2* hv = reinterpret_cast<const __half2*>(&raw[u]);
-                    __half2* ov = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      float2 f = __half22float2(hv[j]);
-                      f.x = fmaf(f.x, sc[2 * j], sf[2 * j]); f.y = fmaf(f.y, sc[2 * j + 1], sf[2 * j + 1]);
-                      if (a.act == B200SEG_ACT_RELU) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
-                      ov[j] = __floats2half2_rn(f.x, f.y);
-                    }
-                  }
-                  *reinterpret_cast<uint4*>(sdst + vv[u] * 16) = o;
-                }
-              }
-            }
-            long long q3 = 0;
-            if (dl) q3 = clock64();
-            if (lt == 0) TRACE(1 + grp, tr_l++);                   // stored
-            fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
-            mbar_arrive(A_FULL(ring.idx));
-            if (lt == 0) TRACE(1 + grp, tr_l++);                   // published
-            if (dl) { DBG_ADD(0, q1 - q0); DBG_ADD(2, q3 - q1); DBG_ADD(3, clock64() - q3); DBG_ADD(4, 1); }
-          }
-          ring.advance();
-          ++stage_no;
-        }
-      }
-    }
-  } else if (warp == kWgtWarp) {
+    setmaxnreg_dec<kRegsLoad>();
+    if (p.prefetch >= 3) loader_role<3>(p, smem, s_norm, bar0);
+    else if (p.prefetch == 2) loader_role<2>(p, smem, s_norm, bar0);
+    else loader_role<1>(p, smem, s_norm, bar0);
+  } else if (warp >= kWgtWarp) {
+    setmaxnreg_dec<kRegsMma>();
+   if (warp == kWgtWarp) {
     // =========================== WEIGHT PRODUCER (bulk TMA) ===========================
     if (lane == 0) {
       const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.wimg);
@@ -407,8 +507,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           bulk_g2s(smem_b + i * p.b_stage_bytes, wimg + (int64_t)i * p.b_stage_bytes, (uint32_t)p.b_stage_bytes, B_FULL(0));
       } else {
         Ring ring; ring.init(p.SB);
-        TileIter ti; ti.init(p);
-        for (; ti.valid(); ti.next()) {
+        TileWalk tw; tw.init(p); TileIter ti; ti.init(tw);
+        for (; ti.valid(tw); ti.next(tw)) {
           const TileCoord tc = ti.coord();
           for (int kc = 0; kc < p.NKC; ++kc) {
             for (int zd = 0; zd < a.kd; ++zd) {
@@ -416,7 +516,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               if ((unsigned)din >= (unsigned)a.D) continue;
               for (int thw = 0; thw < taps_hw; ++thw) {
                 const int tap = zd * taps_hw + thw;
-                mbar_wait(B_EMPTY(ring.idx), ring.phase ^ 1, p.err_flag, 2);
+                mbar_wait(B_EMPTY(ring.idx), ring.phase ^ 1, 2);
                 mbar_arrive_expect_tx(B_FULL(ring.idx), (uint32_t)p.b_stage_bytes);
                 const uint8_t* src = wimg + ((int64_t)(tc.ntile * taps + tap) * p.NKC + kc) * p.b_stage_bytes;
                 bulk_g2s(smem_b + ring.idx * p.b_stage_bytes, src, (uint32_t)p.b_stage_bytes, B_FULL(ring.idx));
@@ -427,13 +527,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+   } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
     // Production pattern: the WHOLE warp runs this loop with warp-uniform values (everything is derived from
     // kernel parameters, blockIdx and shuffled broadcasts), and one elected lane issues the tcgen05 instructions.
     // Uniform values live in uniform registers, so a tcgen05.mma costs a couple of UIADDs instead of an
-    // elect / R2UR.BROADCAST sequence per operand (measured: 134 -> see profiles/ cycles per MMA), and the loop
-    // bounds are copied to locals so no constant-bank load sits on the issue path.
+    // elect / R2UR.BROADCAST sequence per operand, and the loop bounds are copied to locals so no constant-bank
+    // load sits on the issue path.
     {
       const uint32_t elected = elect_one();
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -445,20 +545,17 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
       const uint32_t smem_a16 = smem_a >> 4, smem_b16 = smem_b >> 4;
       const int kd = a.kd, kh = a.kh, kw = a.kw, NKC = p.NKC, D = a.D, NT = p.NT, HALO_W = p.HALO_W;
-      const int resident = p.w_resident, n_tiles = p.n_tiles, acc_stages = p.acc_stages;
+      const int resident = p.w_resident, acc_stages = p.acc_stages;
       const int taps_all = kd * taps_hw;
       const uint32_t res_step = (uint32_t)NKC * b_stage16;
-      int it = 0, tr_m = 0;
+      int it = 0;
       if (resident) { mbar_wait_nocall(B_FULL(0), 0); tc_fence_after(); }
-      TileIter ti; ti.init(p);
-      for (; ti.valid(); ti.next(), ++it) {
+      TileWalk tw; tw.init(p); TileIter ti; ti.init(tw);
+      for (; ti.valid(tw); ti.next(tw), ++it) {
         const TileCoord tc = ti.coord();
         const int acc = (acc_stages == 2) ? (it & 1) : 0;
         const uint32_t acc_phase = (acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
-        long long m0 = 0;
-        if (dbg && lane == 0) m0 = clock64();
         mbar_wait_nocall(T_EMPTY(acc), acc_phase ^ 1);
-        if (dbg && lane == 0) DBG_ADD(8, clock64() - m0);
         tc_fence_after();
         const uint32_t tmem_d = tmem_u + (uint32_t)(acc * NT);
         uint32_t accumulate = 0;
@@ -466,11 +563,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           for (int zd = 0; zd < kd; ++zd) {
             const int din = tc.d + zd - pd;
             if ((unsigned)din >= (unsigned)D) continue;
-            if (dbg && lane == 0) m0 = clock64();
-            if (lane == 0) TRACE(0, tr_m++);                       // stage start (before A_FULL wait)
             mbar_wait_nocall(A_FULL(ra.idx), ra.phase);
-            if (lane == 0) TRACE(0, tr_m++);                       // A ready
-            if (dbg && lane == 0) { DBG_ADD(9, clock64() - m0); DBG_ADD(12, 1); m0 = clock64(); }
             tc_fence_after();
             uint64_t da_row = a_tmpl + (uint64_t)(smem_a16 + (uint32_t)ra.idx * a_stage16);
             uint64_t db_res = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)((tc.ntile * taps_all + zd * taps_hw) * NKC + kc) * b_stage16);
@@ -486,148 +579,47 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
               }
             }
             if (!done) {
-            for (int zh = 0; zh < kh; ++zh) {
-              uint64_t da_tap = da_row;
-              for (int zw = 0; zw < kw; ++zw) {
-                uint64_t db;
-                if (resident) {
-                  db = db_res;
-                  db_res += (uint64_t)res_step;
-                } else {
-                  mbar_wait_nocall(B_FULL(rb.idx), rb.phase);
-                  tc_fence_after();
-                  db = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)rb.idx * b_stage16);
-                }
-                uint64_t da = da_tap;
+              for (int zh = 0; zh < kh; ++zh) {
+                uint64_t da_tap = da_row;
+                for (int zw = 0; zw < kw; ++zw) {
+                  uint64_t db;
+                  if (resident) {
+                    db = db_res;
+                    db_res += (uint64_t)res_step;
+                  } else {
+                    mbar_wait_nocall(B_FULL(rb.idx), rb.phase);
+                    tc_fence_after();
+                    db = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)rb.idx * b_stage16);
+                  }
+                  uint64_t da = da_tap;
 #pragma unroll 4
-                for (int j = 0; j < ksteps; ++j) {
-                  if (elected) umma_f16(tmem_d, da, db, idesc, accumulate);
-                  accumulate = 1;
-                  da += a_kstep; db += b_kstep;
+                  for (int j = 0; j < ksteps; ++j) {
+                    if (elected) umma_f16(tmem_d, da, db, idesc, accumulate);
+                    accumulate = 1;
+                    da += a_kstep; db += b_kstep;
+                  }
+                  if (!resident) {
+                    if (elected) umma_commit(B_EMPTY(rb.idx));   // weights slot free once these MMAs retire
+                    rb.advance();
+                  }
+                  da_tap += 1;                      // next tap to the right: 16 B
                 }
-                if (!resident) {
-                  if (elected) umma_commit(B_EMPTY(rb.idx));   // weights slot free once these MMAs retire
-                  rb.advance();
-                }
-                da_tap += 1;                      // next tap to the right: 16 B
+                da_row += (uint64_t)HALO_W;         // next tap row: HALO_W voxels
               }
-              da_row += (uint64_t)HALO_W;         // next tap row: HALO_W voxels
             }
-            }
-            if (lane == 0) TRACE(0, tr_m++);                       // MMAs issued
             if (elected) umma_commit(A_EMPTY(ra.idx));         // halo tile free
             ra.advance();
-            if (lane == 0) TRACE(0, tr_m++);                       // committed
-            if (dbg && lane == 0) DBG_ADD(11, clock64() - m0);      // issue time of one stage (incl. weight waits)
           }
         }
         if (elected) umma_commit(T_FULL(acc));                 // accumulator complete -> epilogue
       }
     }
+   }
   } else {
-    // =========================== EPILOGUE (warps 0-3) ===========================
-    const int q = warp;                         // TMEM lane quadrant
-    const int row = q * 32 + lane;              // GEMM row = hl*8 + wl
-    const int hl = row >> 3, wl = row & 7;
-    const bool dgrad = a.gx != nullptr;
-    int it = 0;
-    TileIter ti; ti.init(p);
-    for (; ti.valid(); ti.next(), ++it) {
-      const TileCoord tc = ti.coord();
-      const int acc = (p.acc_stages == 2) ? (it & 1) : 0;
-      const uint32_t acc_phase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
-      const int h = tc.h0 + hl, w = tc.w0 + wl;
-      const bool valid = (h < a.H) && (w < a.W);
-      const int64_t vox = ((int64_t)(tc.b * a.D + tc.d) * a.H + h) * a.W + w;
-      const int co_base = tc.ntile * p.NT;
-      __half* yp = reinterpret_cast<__half*>(a.y) + vox * a.y_ld + a.y_coff + co_base;
-      const __half* rp = a.res ? reinterpret_cast<const __half*>(a.res) + vox * a.r_ld + a.r_coff + co_base : nullptr;
-      const __half* gp = dgrad ? reinterpret_cast<const __half*>(a.gx) + vox * a.gx_ld + a.gx_coff + co_base : nullptr;
-      float* wstat = s_stat + ((q * a.B + tc.b) * a.Cout + co_base) * 2;
-      // side input of the epilogue (residual, or x for the dgrad ReLU mask): fetched one 16-channel chunk AHEAD so
-      // its global-memory latency overlaps the wait for the accumulator and the previous chunk's work
-      const __half* side = dgrad ? gp : rp;
-      uint4 nx0 = make_uint4(0, 0, 0, 0), nx1 = make_uint4(0, 0, 0, 0);
-      if (side && valid) {
-        nx0 = __ldg(reinterpret_cast<const uint4*>(side));
-        nx1 = __ldg(reinterpret_cast<const uint4*>(side + 8));
-      }
-      long long e0 = 0;
-      const bool de = dbg && threadIdx.x == 0;
-      if (de) e0 = clock64();
-      if (threadIdx.x == 0) TRACE(3, 3 * it);                      // tile start (before T_FULL wait)
-      mbar_wait(T_FULL(acc), acc_phase, p.err_flag, 6);
-      if (threadIdx.x == 0) TRACE(3, 3 * it + 1);                  // accumulator ready
-      if (de) { DBG_ADD(16, clock64() - e0); e0 = clock64(); }
-      tc_fence_after();
-      for (int n0 = 0; n0 < ((p.debug & 4) ? 0 : p.NT); n0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT + n0), v);
-        const uint4 cur0 = nx0, cur1 = nx1;
-        if (side && valid && n0 + 16 < p.NT) {
-          nx0 = __ldg(reinterpret_cast<const uint4*>(side + n0 + 16));
-          nx1 = __ldg(reinterpret_cast<const uint4*>(side + n0 + 24));
-        }
-        tmem_ld_wait();
-        float r[16], s2[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = __uint_as_float(v[j]);
-        if (valid) {
-          if (a.bias) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] += a.bias[co_base + n0 + j];
-          }
-          float sv[16];
-          if (side) {
-            const __half2* h0 = reinterpret_cast<const __half2*>(&cur0);
-            const __half2* h1 = reinterpret_cast<const __half2*>(&cur1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 f0 = __half22float2(h0[j]), f1 = __half22float2(h1[j]);
-              sv[2 * j] = f0.x; sv[2 * j + 1] = f0.y; sv[8 + 2 * j] = f1.x; sv[8 + 2 * j + 1] = f1.y;
-            }
-          }
-          if (dgrad) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 mr = s_gnorm[tc.b * a.Cout + co_base + n0 + j];
-              const float hx = (sv[j] - mr.x) * mr.y;
-              float g = (a.g_act == B200SEG_ACT_RELU && !(hx > 0.f)) ? 0.f : r[j];
-              g = __half2float(__float2half_rn(g));
-              r[j] = g; s2[j] = g * hx;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = __half2float(__float2half_rn(r[j]));
-            if (rp) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) r[j] = __half2float(__float2half_rn(r[j] + sv[j]));
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) s2[j] = r[j] * r[j];
-          }
-          st8<__half>(yp + n0, reinterpret_cast<const float(&)[8]>(r[0]));
-          st8<__half>(yp + n0 + 8, reinterpret_cast<const float(&)[8]>(r[8]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { r[j] = 0.f; s2[j] = 0.f; }
-        }
-        if (a.y_stats) {
-          // column sums over the warp's 32 rows with a halving butterfly: 16 shuffles per quantity instead of 80.
-          // Afterwards lanes 2c and 2c+1 both hold the sum of column col(lane).
-          const float u = column_sum16(r, lane), q2 = column_sum16(s2, lane);
-          if ((lane & 1) == 0) {
-            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            wstat[(n0 + col) * 2] += u;
-            wstat[(n0 + col) * 2 + 1] += q2;
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(T_EMPTY(acc));
-      if (threadIdx.x == 0) TRACE(3, 3 * it + 2);                  // drained
-      if (de) { DBG_ADD(17, clock64() - e0); DBG_ADD(18, 1); }
-    }
+    // =========================== EPILOGUE (warps 0-7) ===========================
+    setmaxnreg_inc<kRegsEpi>();
+    if (p.NT <= 64) epilogue_role<true>(p, warp, lane, tmem_base, bar0, s_gnorm, s_stat);
+    else epilogue_role<false>(p, warp, lane, tmem_base, bar0, s_gnorm, s_stat);
   }
 
   // ---- teardown: flush the per-CTA InstanceNorm partial sums, free TMEM
@@ -639,7 +631,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     for (int i = threadIdx.x; i < n; i += kThreads) {
       double s = 0.0;
 #pragma unroll
-      for (int q = 0; q < kEpiWarps; ++q) s += (double)s_stat[q * n + i];
+      for (int q = 0; q < kStatCopies; ++q) s += (double)s_stat[q * n + i];
       if (s != 0.0) atomicAdd(&a.y_stats[i], s);
     }
   }
@@ -657,9 +649,6 @@ bool conv3d_tc_shape_ok(int Cin, int Cout, int kd, int kh, int kw, int dtype) {
 
 bool conv3d_fwd_tc_supported(const ConvArgs& a, int dtype) {
   if (!conv3d_tc_shape_ok(a.Cin, a.Cout, a.kd, a.kh, a.kw, dtype)) return false;
-  if (dtype != B200SEG_F16) return false;
-  if (tc_pick_nt(a.Cout) == 0 || tc_pick_kc(a.Cin) == 0) return false;
-  if (a.kh > 3 || a.kw > 3 || a.kd > 3) return false;
   if ((a.x_ld % 8) || (a.x_coff % 8) || (a.y_ld % 8) || (a.y_coff % 8)) return false;
   if (a.res && ((a.r_ld % 8) || (a.r_coff % 8))) return false;
   if (a.gx && ((a.gx_ld % 8) || (a.gx_coff % 8))) return false;
@@ -694,14 +683,14 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   p.tmem_cols = pow2;
   // shared memory carve-up
   const int norm_bytes = a.B * a.Cin * 8;
-  const int stat_bytes = kEpiWarps * a.B * a.Cout * 2 * 4;
+  const int stat_bytes = kStatCopies * a.B * a.Cout * 2 * 4;
   const int budget = 227 * 1024 - 1024 - norm_bytes - stat_bytes - a.B * a.Cout * 8 - 512;
   const int64_t w_total = (int64_t)a.kd * a.kh * a.kw * a.Cin * a.Cout * 2;
   int b_region;
   if (w_total <= 112 * 1024 && w_total + 2 * p.a_stage_bytes <= budget) {
     p.w_resident = 1; p.SB = 1;
     b_region = (int)w_total;
-    p.SA = (budget - b_region) / p.a_stage_bytes; if (p.SA > 4) p.SA = 4;
+    p.SA = (budget - b_region) / p.a_stage_bytes; if (p.SA > 6) p.SA = 6;
   } else {
     p.w_resident = 0;
     p.SA = 4;
@@ -710,6 +699,8 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
     if (p.SB < 2) return B200SEG_EUNSUPPORTED;
     b_region = p.SB * p.b_stage_bytes;
   }
+  if (p.SA < 2) return B200SEG_EUNSUPPORTED;
+  p.prefetch = p.SA - 1 < 3 ? p.SA - 1 : 3;
   int off = 0;
   p.smem_a_off = off; off += p.SA * p.a_stage_bytes;
   off = (off + 127) / 128 * 128;
@@ -723,8 +714,6 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   off = (off + 15) / 16 * 16;
   p.smem_stat_off = off; off += stat_bytes;
   const int smem_bytes = off + 1024;       // slack for the 1024-B alignment of the dynamic segment
-  p.err_flag = nullptr;
-  { const char* dv = getenv("B200SEG_TC_DEBUG"); p.debug = dv ? atoi(dv) : 0; }
   int grid = p.n_tiles < B200SEG_NUM_SMS ? p.n_tiles : B200SEG_NUM_SMS;
   static thread_local bool attr_set = false;
   if (!attr_set) {
@@ -733,26 +722,5 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   }
   conv_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(p);
   B200_CHECK_LAUNCH("conv_tc_kernel");
-  return B200SEG_OK;
-}
-
-
-// debug: read-and-clear the cycle counters written by block 0 when B200SEG_TC_DEBUG=1
-extern "C" int b200seg_debug_tc_timers(long long* out32) {
-  cudaError_t e = cudaDeviceSynchronize();
-  if (e != cudaSuccess) return b200seg_record_cuda(e, "sync");
-  e = cudaMemcpyFromSymbol(out32, g_tc_dbg, sizeof(long long) * 32);
-  if (e != cudaSuccess) return b200seg_record_cuda(e, "memcpyFromSymbol");
-  long long z[32] = {0};
-  e = cudaMemcpyToSymbol(g_tc_dbg, z, sizeof(z));
-  if (e != cudaSuccess) return b200seg_record_cuda(e, "memcpyToSymbol");
-  return B200SEG_OK;
-}
-
-extern "C" int b200seg_debug_tc_trace(long long* out1024) {
-  cudaError_t e = cudaDeviceSynchronize();
-  if (e != cudaSuccess) return b200seg_record_cuda(e, "sync");
-  e = cudaMemcpyFromSymbol(out1024, g_tc_trace, sizeof(long long) * 1024);
-  if (e != cudaSuccess) return b200seg_record_cuda(e, "memcpyFromSymbol");
   return B200SEG_OK;
 }

@@ -198,12 +198,6 @@ int b200seg_conv3d_wgrad(const void* x, int x_ld, int x_coff,
                          int kd, int kh, int kw, int dtype, int algo,
                          void* workspace, size_t ws_bytes, void* stream);
 
-/* Debug aid: with B200SEG_TC_DEBUG=1 in the environment, block 0 of the tcgen05 conv kernel accounts the
- * cycles each warp role spends waiting / working; this reads and clears the 32 counters (synchronises). */
-int b200seg_debug_tc_timers(long long* out32);
-/* raw clock64 stamps of block 0's first events per warp role: long long[4][256] */
-int b200seg_debug_tc_trace(long long* out1024);
-
 /* ---------------------------------------------------------------------------
  * MaxPool3d, kernel == stride (unet_utils.py:36), floor mode, + IN sums of the
  * pooled tensor.  idx: uint8[B][Do][Ho][Wo][C] argmax offset inside the window.
