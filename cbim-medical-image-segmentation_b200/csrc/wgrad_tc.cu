@@ -19,7 +19,9 @@
 //   * split-K over voxel tiles fills the machine: grid = jobs x S.  Every CTA adds its partial D tiles straight into
 //     dW with fp32 reductions (red.global.add.f32) — no partial workspace, no second kernel.  The sum order of the S
 //     partials is not fixed, so dW is reproducible to fp32 rounding (~1e-7 relative), like cuDNN's default wgrad.
-// Warp roles (416 threads, 1 CTA/SM): warps 0-3 epilogue, warps 4-11 loaders, warp 12 MMA issue + TMEM alloc.
+//   * narrow layers (Cin tile <= 64) run in TS mode: dy^T is transposed smem -> TMEM once per voxel tile by the four
+//     (otherwise idle) epilogue warps and the MMAs take their A operand from tensor memory.
+// Warp roles (416 threads, 1 CTA/SM): warps 0-3 TS transposers + epilogue, warps 4-11 loaders, warp 12 MMA issue + TMEM alloc.
 #include "common.cuh"
 #include "conv_args.h"
 #include "tc_common.cuh"
@@ -48,6 +50,7 @@ struct WgParams {
   int HALO_H, HALO_W, nvox_h, a_plane, dy_plane, a_bytes, dy_bytes, stage_bytes, NS, prefetch;
   int tiles_h, tiles_w, nvt;
   int tmem_cols;
+  int ts;                                  // A operand (dy^T) is fed from TENSOR MEMORY (narrow Cin: see file header)
   int smem_bar_off, smem_norm_off;
 };
 
@@ -63,22 +66,40 @@ __device__ __forceinline__ Job decode_job(const WgParams& p, int bid) {
   return j;
 }
 
-// voxel tiles this CTA owns: vt = s, s+S, ... ; those whose input depth slice lies outside the volume are skipped
+// voxel tiles this CTA owns: vt = s, s+S, ... ; those whose input depth slice lies outside the volume are skipped.
+// The walk is a mixed-radix counter (w-tile, h-tile, d, b) advanced by the digits of S: no divisions per tile.
+struct VtWalk {
+  int s0, s1, s2, s3;               // digits of the stride S
+  int r0, r1, r2;                   // radices: tiles_w, tiles_h, D
+  __device__ __forceinline__ void init(const WgParams& p) {
+    r0 = p.tiles_w; r1 = p.tiles_h; r2 = p.D;
+    int x = p.S;
+    s0 = x % r0; x /= r0; s1 = x % r1; x /= r1; s2 = x % r2; s3 = x / r2;
+  }
+};
 struct VtCursor {
-  int vt, b, d, h0, w0, din;
-  __device__ __forceinline__ void decode(const WgParams& p, int zoff) {
-    int t = vt;
-    w0 = (t % p.tiles_w) * TW; t /= p.tiles_w;
-    h0 = (t % p.tiles_h) * TH; t /= p.tiles_h;
-    d = t % p.D; b = t / p.D;
-    din = d + zoff;
+  int vt, wi, hi, d, b, din;
+  __device__ __forceinline__ void step(const VtWalk& k, const WgParams& p) {
+    vt += p.S;
+    int c;
+    wi += k.s0; c = wi >= k.r0; if (c) wi -= k.r0;
+    hi += k.s1 + c; c = hi >= k.r1; if (c) hi -= k.r1;
+    d += k.s2 + c; c = d >= k.r2; if (c) d -= k.r2;
+    b += k.s3 + c;
   }
-  __device__ __forceinline__ void seek(const WgParams& p, int zoff) {      // first valid tile at or after vt
-    while (vt < p.nvt) { decode(p, zoff); if ((unsigned)din < (unsigned)p.D) return; vt += p.S; }
+  __device__ __forceinline__ void seek(const VtWalk& k, const WgParams& p, int zoff) {      // first valid tile at or after vt
+    while (vt < p.nvt) { din = d + zoff; if ((unsigned)din < (unsigned)p.D) return; step(k, p); }
   }
-  __device__ __forceinline__ void init(const WgParams& p, int s, int zoff) { vt = s; seek(p, zoff); }
+  __device__ __forceinline__ void init(const VtWalk& k, const WgParams& p, int s, int zoff) {
+    vt = s;
+    int t = s;
+    wi = t % k.r0; t /= k.r0; hi = t % k.r1; t /= k.r1; d = t % k.r2; b = t / k.r2;
+    seek(k, p, zoff);
+  }
   __device__ __forceinline__ bool valid(const WgParams& p) const { return vt < p.nvt; }
-  __device__ __forceinline__ void next(const WgParams& p, int zoff) { vt += p.S; seek(p, zoff); }
+  __device__ __forceinline__ void next(const VtWalk& k, const WgParams& p, int zoff) { step(k, p); seek(k, p, zoff); }
+  __device__ __forceinline__ int h0() const { return hi * TH; }
+  __device__ __forceinline__ int w0() const { return wi * TW; }
 };
 
 template <int P>
@@ -102,8 +123,9 @@ __device__ __forceinline__ void wg_loader(const WgParams& p, const Job& job, uin
   const bool xform = (p.x_stats != nullptr) || (p.act != 0);
   auto FULL = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   auto EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(p.NS + i); };
+  VtWalk vw; vw.init(p);
   VtCursor ci, cd;
-  ci.init(p, job.s, zoff); cd.init(p, job.s, zoff);
+  ci.init(vw, p, job.s, zoff); cd.init(vw, p, job.s, zoff);
   Ring ri, rd; ri.init(p.NS); rd.init(p.NS);
 
   auto issue = [&]() {
@@ -115,7 +137,7 @@ __device__ __forceinline__ void wg_loader(const WgParams& p, const Job& job, uin
       const uint32_t dst = sdy + (uint32_t)(c8_d * p.dy_plane);
 #pragma unroll 4
       for (int v = v0_d; v < TH * TW; v += vstep_d) {
-        const int h = ci.h0 + (v >> 3), w = ci.w0 + (v & 7);
+        const int h = ci.h0() + (v >> 3), w = ci.w0() + (v & 7);
         const bool ok = h < p.H && w < p.W;
         cp_async16(dst + (uint32_t)v * 16u, ok ? (const void*)(src + ((int64_t)h * p.W + w) * p.dy_ld) : (const void*)p.dy, ok ? 16u : 0u);
       }
@@ -126,14 +148,14 @@ __device__ __forceinline__ void wg_loader(const WgParams& p, const Job& job, uin
       int hh = hh0, ww = ww0;
 #pragma unroll 4
       for (int v = v0_a; v < p.nvox_h; v += vstep_a) {
-        const int h = ci.h0 - ph + hh, w = ci.w0 - pw + ww;
+        const int h = ci.h0() - ph + hh, w = ci.w0() - pw + ww;
         const bool ok = (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
         cp_async16(dst + (uint32_t)v * 16u, ok ? (const void*)(src + ((int64_t)h * p.W + w) * p.x_ld) : (const void*)p.x, ok ? 16u : 0u);
         hh += sh_a; ww += sw_a;
         if (ww >= p.HALO_W) { ww -= p.HALO_W; ++hh; }
       }
     }
-    ri.advance(); ci.next(p, zoff);
+    ri.advance(); ci.next(vw, p, zoff);
   };
 
 #pragma unroll
@@ -152,7 +174,7 @@ __device__ __forceinline__ void wg_loader(const WgParams& p, const Job& job, uin
       int hh = hh0, ww = ww0;
 #pragma unroll 2
       for (int v = v0_a; v < p.nvox_h; v += vstep_a) {
-        const int h = cd.h0 - ph + hh, w = cd.w0 - pw + ww;
+        const int h = cd.h0() - ph + hh, w = cd.w0() - pw + ww;
         if ((unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W) {      // padding voxels stay zero
           uint4 raw = *reinterpret_cast<const uint4*>(sp + v * 16);
           __half2* hv = reinterpret_cast<__half2*>(&raw);
@@ -171,7 +193,7 @@ __device__ __forceinline__ void wg_loader(const WgParams& p, const Job& job, uin
     }
     fence_proxy_async();
     mbar_arrive(FULL(rd.idx));
-    rd.advance(); cd.next(p, zoff);
+    rd.advance(); cd.next(vw, p, zoff);
     if (ci.valid(p)) issue();
     cp_async_commit();
   }
@@ -195,12 +217,15 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   auto FULL = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   auto EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(p.NS + i); };
   const uint32_t DONE = bar0 + 8u * (uint32_t)(2 * p.NS);
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(bars + 2 * p.NS + 1);
+  auto A_READY = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.NS + 1 + i); };     // TS mode: dy^T tile i sits in TMEM
+  auto A_FREE = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.NS + 3 + i); };      //          the MMAs reading it retired
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(bars + 2 * p.NS + 5);
   float2* s_norm = reinterpret_cast<float2*>(smem + p.smem_norm_off);     // [B][NTC] {mean, rstd} of this job's channels
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.NS; ++i) { mbar_init(FULL(i), kLoadThreads); mbar_init(EMPTY(i), 1); }
     mbar_init(DONE, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(A_READY(i), kEpiWarps * 32); mbar_init(A_FREE(i), 1); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), (uint32_t)p.tmem_cols);
@@ -239,36 +264,92 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
       const int zh0 = job.tap0 / p.kw, zw0 = job.tap0 % p.kw;
       const int ntaps = job.ntaps, kw = p.kw, HALO_W = p.HALO_W, NTC = p.NTC, NS = p.NS;
       int idx = 0; uint32_t phase = 0; uint32_t accumulate = 0;
-      VtCursor c; c.init(p, job.s, zoff);
-      for (; c.valid(p); c.next(p, zoff)) {
+      VtWalk vw; vw.init(p);
+      VtCursor c; c.init(vw, p, job.s, zoff);
+      const int ts = p.ts;
+      const uint32_t idesc_ts = (1u << 4) | (1u << 16) | ((uint32_t)(p.NTC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const int gmax = p.gbase + (p.grem ? 1 : 0);
+      const uint32_t tmem_a0 = tmem_u + (uint32_t)(gmax * NTC);       // two 64-column dy^T buffers behind the accumulators
+      int it = 0;
+      for (; c.valid(p); c.next(vw, p, zoff), ++it) {
         mbar_wait_nocall(FULL(idx), phase);
+        if (ts) mbar_wait_nocall(A_READY(it & 1), (uint32_t)((it >> 1) & 1));
         tc_fence_after();
         const uint64_t da0 = dy_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16);
         uint64_t db_tap = a_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16 + dy16 + (uint32_t)(zh0 * HALO_W + zw0));
+        const uint32_t ta0 = tmem_a0 + (uint32_t)((it & 1) * 64);
         int zw = zw0;
         uint32_t tmem_d = tmem_u;
         for (int tl = 0; tl < ntaps; ++tl) {
           uint64_t da = da0, db = db_tap;
+          if (ts) {
 #pragma unroll
-          for (int j = 0; j < (TH * TW) / 16; ++j) {
-            if (elected) umma_f16(tmem_d, da, db, idesc, (accumulate | (uint32_t)(j > 0)));
-            da += 16;            // 2 voxel rows of the dy tile = 256 B
-            db += a_kstep;
+            for (int j = 0; j < (TH * TW) / 16; ++j) {
+              if (elected) umma_f16_ts(tmem_d, ta0 + (uint32_t)(j * 8), db, idesc_ts, (accumulate | (uint32_t)(j > 0)));
+              db += a_kstep;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < (TH * TW) / 16; ++j) {
+              if (elected) umma_f16(tmem_d, da, db, idesc, (accumulate | (uint32_t)(j > 0)));
+              da += 16;            // 2 voxel rows of the dy tile = 256 B
+              db += a_kstep;
+            }
           }
           tmem_d += (uint32_t)NTC;
           // next in-plane tap: one voxel to the right, or wrap to the next halo row
           if (++zw == kw) { zw = 0; db_tap += (uint64_t)(HALO_W - (kw - 1)); } else db_tap += 1;
         }
         accumulate = 1;
-        if (elected) umma_commit(EMPTY(idx));
+        if (elected) {
+          umma_commit(EMPTY(idx));
+          if (ts) umma_commit(A_FREE(it & 1));
+        }
         if (++idx == NS) { idx = 0; phase ^= 1; }
       }
       if (elected) umma_commit(DONE);
     }
   } else if (warp < kEpiWarps) {
-    // =========================== EPILOGUE (once) ===========================
-    VtCursor c; c.init(p, job.s, zoff);
+    // =========================== (TS mode: dy^T -> TMEM), then EPILOGUE (once) ===========================
+    VtWalk vw; vw.init(p);
+    VtCursor c; c.init(vw, p, job.s, zoff);
     const bool any = c.valid(p);               // did this CTA process any stage at all?
+    if (p.ts) {
+      // Narrow layers (Cin <= 64) are bound by the tensor core's shared-memory read of the A operand (4 KB per
+      // 128 x N x 16 MMA, ~52 cycles whatever N is).  dy^T does not change between the taps of a tile, so it is
+      // moved into TENSOR MEMORY once per tile — lane = output channel, 32-bit column c = voxels 2c, 2c+1 — and the
+      // tile's ntaps*8 MMAs read A from there (tcgen05.mma with a TMEM A operand) at N/2 cycles each.
+      const int gmax = p.gbase + (p.grem ? 1 : 0);
+      const uint32_t tmem_a0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(gmax * p.NTC);
+      const int col = warp * 32 + lane;         // this thread's GEMM row = output channel within the M tile
+      const bool live = warp * 32 < co_real;     // warp-uniform
+      const uint8_t* lane_base = smem + (col >> 3) * p.dy_plane + (col & 7) * 2;
+      int idx = 0; uint32_t phase = 0; int it = 0;
+      for (; c.valid(p); c.next(vw, p, zoff), ++it) {
+        mbar_wait(FULL(idx), phase, 4);
+        mbar_wait(A_FREE(it & 1), (uint32_t)(((it >> 1) & 1) ^ 1), 5);
+        if (live) {
+          tc_fence_after();
+          const uint8_t* src = lane_base + idx * p.stage_bytes;
+          const uint32_t dst = tmem_a0 + (uint32_t)((it & 1) * 64);
+#pragma unroll 2
+          for (int kb = 0; kb < 8; ++kb) {       // 16 voxels -> 8 columns
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t lo = *reinterpret_cast<const uint16_t*>(src + (16 * kb + 2 * i) * 16);
+              const uint32_t hi = *reinterpret_cast<const uint16_t*>(src + (16 * kb + 2 * i + 1) * 16);
+              w[i] = lo | (hi << 16);
+            }
+            tmem_st8(dst + (uint32_t)(kb * 8), w);
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(A_READY(it & 1));
+        if (++idx == p.NS) { idx = 0; phase ^= 1; }
+      }
+    }
     mbar_wait(DONE, 0, 3);
     tc_fence_after();
     const int row = warp * 32 + lane;
@@ -313,7 +394,9 @@ bool fill_params(const WgradArgs& a, WgParams& p) {
   p.ci_tiles = a.Cin / p.NTC;
   p.co_tiles = (a.Cout + MT - 1) / MT;
   const int taps_hw = a.kh * a.kw;
-  int G = 512 / p.NTC; if (G > taps_hw) G = taps_hw;
+  // TS mode (dy^T in tensor memory) pays when the MMA is bound by the smem read of A: N = Cin tile <= 64
+  p.ts = (p.NTC <= 64 && !getenv("B200SEG_WGRAD_NO_TS")) ? 1 : 0;
+  int G = (p.ts ? 384 : 512) / p.NTC; if (G > taps_hw) G = taps_hw;
   p.ngroups = (taps_hw + G - 1) / G;
   p.gbase = taps_hw / p.ngroups; p.grem = taps_hw % p.ngroups;
   p.HALO_H = TH + a.kh - 1; p.HALO_W = TW + a.kw - 1; p.nvox_h = p.HALO_H * p.HALO_W;
@@ -340,12 +423,12 @@ bool fill_params(const WgradArgs& a, WgParams& p) {
   if (S > p.nvt) S = p.nvt;
   p.S = S;
   const int gmax = p.gbase + (p.grem ? 1 : 0);
-  int cols = gmax * p.NTC, pow2 = 32; while (pow2 < cols) pow2 <<= 1;
+  int cols = gmax * p.NTC + (p.ts ? 128 : 0), pow2 = 32; while (pow2 < cols) pow2 <<= 1;
   if (pow2 > 512) return false;
   p.tmem_cols = pow2;
   int off = p.NS * p.stage_bytes + 16 * p.dy_plane;       // + slack for the 16-plane descriptor footprint
   off = (off + 15) / 16 * 16;
-  p.smem_bar_off = off; off += (2 * p.NS + 2) * 8 + 16;
+  p.smem_bar_off = off; off += (2 * p.NS + 6) * 8 + 16;
   off = (off + 15) / 16 * 16;
   p.smem_norm_off = off;
   return true;
