@@ -36,10 +36,14 @@ WORKLOADS = {
                               kernel_size=[[1, 3, 3], [1, 3, 3], [3, 3, 3], [3, 3, 3], [3, 3, 3]],
                               scale=[[1, 2, 2], [1, 2, 2], [2, 2, 2], [2, 2, 2]], aux_loss=True),
                          None, 14, [0.5] + [1.0] * 13, (1, 96, 96, 96)),
+    # BASELINE.json configs[3]: SwinUNETR([128]*3, 1, 16, feature_size=48) (model/utils.py:111 with base_chan 48 as in
+    # config/{bcv,kits,lits}/swin_unetr_3d.yaml; 16 classes per config/amos_ct/resunet_3d.yaml:3), AMP
+    "swin_unetr_amos_128": ("swin", 48, 16, [0.5] + [1.0] * 15, (1, 128, 128, 128)),
 }
 BASE = 32
 METRIC = "3D-UNet (ResBasicBlock) training voxels/sec, synthetic 128^3"
 METRIC_MEDFORMER = "3D MedFormer training voxels/sec, synthetic 96^3"
+METRIC_SWIN = "SwinUNETR training voxels/sec, synthetic 128^3"
 AUX_WEIGHT = [0.5, 0.5]
 
 
@@ -47,11 +51,17 @@ def is_medformer(wl):
     return isinstance(wl[0], dict)
 
 
+def is_swin(wl):
+    return wl[0] == "swin"
+
+
 def metric_of(wl):
-    return METRIC_MEDFORMER if is_medformer(wl) else METRIC
+    return METRIC_SWIN if is_swin(wl) else (METRIC_MEDFORMER if is_medformer(wl) else METRIC)
 
 
 def model_name(wl):
+    if is_swin(wl):
+        return "SwinUNETR (reference SwinUNETR([128,128,128], 1, 16, feature_size=48), depths (2,2,2,0), window 7^3)"
     if is_medformer(wl):
         return "MedFormer-3D BCV config (reference MedFormer(1,14,32,...,norm='in',act='relu',aux_loss=True))"
     return "ResUNet-3D base32 BasicBlock IN (reference UNet(1,32,...,block='BasicBlock',norm='in'))"
@@ -61,6 +71,13 @@ def oracle_state(wl):
     """Seeded synthetic weights keyed like the reference's state_dict."""
     import torch
     from oracle import unet3d as ounet
+    if is_swin(wl):
+        from oracle import swin_unetr as osw
+        sd = ounet.make_state_dict(osw.swin_unetr_param_shapes(1, wl[2], wl[1]), seed=7)
+        for k in sd:
+            if k.endswith("norm1.weight") or k.endswith("norm2.weight") or k.endswith("norm.weight"):
+                sd[k] = 1.0 + 0.1 * sd[k] / sd[k].abs().max()
+        return sd
     if is_medformer(wl):
         import b200seg
         with torch.device("meta"):      # parameter names / shapes straight from the module tree (no allocation)
@@ -77,6 +94,9 @@ def oracle_state(wl):
 
 def oracle_loss(wl, sd, img, lab, w):
     from oracle import losses as olosses
+    if is_swin(wl):
+        from oracle import swin_unetr as osw
+        return olosses.total_loss(osw.swin_unetr_forward(sd, img), lab, w)
     if is_medformer(wl):
         from oracle import medformer as omed
         return olosses.total_loss(omed.medformer_forward(sd, img, wl[0]), lab, w, AUX_WEIGHT)
@@ -108,6 +128,23 @@ def conv_layers(scale, kernel, classes, B, D, H, W, base=BASE):
         block(ci + co, co, kernel[3 - j], dims[3 - j])
         block(co, co, kernel[3 - j], dims[3 - j])
     L.append((base, classes, [1, 1, 1], dims[0]))
+    return L
+
+
+def swin_conv_layers(fs, classes, D, H, W):
+    """3x3x3 / 1x1x1 conv3d layers of SwinUNETR's monai blocks (call sites swin_unetr.py:129-228) as (Cin, Cout, k, dims)."""
+    L = []
+    k3, k1 = [3, 3, 3], [1, 1, 1]
+
+    def res(ci, co, dm):
+        L.append((ci, co, k3, dm)); L.append((co, co, k3, dm))
+        if ci != co:
+            L.append((ci, co, k1, dm))
+    dims = [(D >> i, H >> i, W >> i) for i in range(6)]
+    res(1, fs, dims[0]); res(fs, fs, dims[1]); res(2 * fs, 2 * fs, dims[2]); res(4 * fs, 4 * fs, dims[3]); res(16 * fs, 16 * fs, dims[5])
+    for i, (ci, co) in enumerate(((16 * fs, 8 * fs), (8 * fs, 4 * fs), (4 * fs, 2 * fs), (2 * fs, fs), (fs, fs))):
+        res(2 * co, co, dims[4 - i])
+    L.append((fs, classes, k1, dims[0]))
     return L
 
 
@@ -236,12 +273,15 @@ def oracle_step_fn(wl):
 def cpu_sample_shape(wl, step):
     """Smallest legal depth-crop of the workload and the measured CPU rate on it (voxels/s)."""
     from oracle.synth import make_volume
-    scale = wl[0]["scale"] if is_medformer(wl) else wl[0]
     classes, (_, _, H, W) = wl[2], wl[4]
-    dmin = 1
-    for s in scale:
-        dmin *= s[0]
-    dmin = max(dmin * 2, 8)
+    if is_swin(wl):
+        dmin = 64                      # img_size % 32 == 0 and >= 2 voxels at the deepest stage
+    else:
+        scale = wl[0]["scale"] if is_medformer(wl) else wl[0]
+        dmin = 1
+        for s in scale:
+            dmin *= s[0]
+        dmin = max(dmin * 2, 8)
     img, lab = make_volume(1, dmin, H, W, classes, seed=1)
     step(img, lab)
     t0 = time.time(); step(img, lab); t = time.time() - t0
@@ -313,6 +353,10 @@ def run_b200(args, wl):
     assert _lib.load().b200seg_check_device() == 0, "not an sm_100 device"
 
     def make_net():
+        if is_swin(wl):
+            n = b200seg.SwinUNETR((D, H, W), 1, classes, feature_size=wl[1])
+            n.load_state_dict(oracle_state(wl), strict=False)            # relative_position_index buffers are derived
+            return n.to(dev)
         if med:
             n = b200seg.MedFormer(1, classes, BASE, conv_block="BasicBlock", expansion=4, attn_drop=0, proj_drop=0,
                                   proj_type="depthwise", norm="in", act="relu", **wl[0])
@@ -323,7 +367,14 @@ def run_b200(args, wl):
     net, ema = make_net(), make_net()
     if world > 1:
         from torch.nn.parallel import DistributedDataParallel as DDP
-        net = DDP(net, device_ids=[local], find_unused_parameters=True)      # train_ddp.py:353
+        # train_ddp.py:353 wraps with find_unused_parameters=True; every parameter of these models receives a gradient
+        # (SURVEY.md §8a "No unused parameters", tests/test_ddp_gloo.py), so the extra autograd-graph walk is dropped
+        # here, and gradients live directly in the all-reduce buckets (no copy into them).  tests/test_gpu_ddp_nccl.py
+        # keeps the reference's own flags.
+        net = DDP(net, device_ids=[local], find_unused_parameters=False, gradient_as_bucket_view=True)
+        if args.grad_compress:
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            net.register_comm_hook(None, default_hooks.fp16_compress_hook)      # half the all-reduce bytes
     for p in ema.parameters():
         p.requires_grad_(False)                                             # train_ddp.py:360-361
     ts = TrainStep(net, ema, ce_weight=torch.tensor(weight), amp=True, aux_weight=AUX_WEIGHT if med else None)
@@ -386,8 +437,12 @@ def run_b200(args, wl):
         out["roofline"] = biattn_roofline(torch, ops, _lib, dev, B)
     if rank == 0 and not med:
         # ---- roofline of the dominant kernel: conv3d forward on the costliest layer shape
-        L = conv_layers(scale, kernel, classes, B, D, H, W)
-        fl_step = 3 * conv_flops(L, B) - conv_flops(L[:1], B)
+        if is_swin(wl):
+            L = swin_conv_layers(wl[1], classes, D, H, W)
+            fl_step = 4544.0e9          # fwd 1516.6 (conv 1392.5 + bmm 61.4 + addmm 58.3 + mm 4.5) + bwd 3027.4 GFLOP
+        else:
+            L = conv_layers(scale, kernel, classes, B, D, H, W)
+            fl_step = 3 * conv_flops(L, B) - conv_flops(L[:1], B)
         out["config"]["algorithmic_gflop_per_step"] = fl_step / 1e9
         out["achieved_tflops_step"] = fl_step / (ms / args.steps / 1e3) / 1e12
         groups = {}
@@ -567,6 +622,7 @@ def main():
     ap.add_argument("--workload", default="resunet_acdc_128", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cudnn", action="store_true")
+    ap.add_argument("--grad-compress", action="store_true", help="fp16 gradient all-reduce (DDP comm hook); default fp32 like the reference")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -7,7 +7,8 @@ from ._lib import B200SegError, EXPORTED_SYMBOLS, LIB_PATH
 from .factory import get_model
 from .losses import CrossEntropyLoss, DiceCELoss, DiceLoss
 from .medformer import MedFormer
+from .swin_unetr import SwinUNETR
 from .unet3d import UNet
 
-__all__ = ["get_model", "UNet", "MedFormer", "DiceLoss", "DiceCELoss", "CrossEntropyLoss", "B200SegError",
+__all__ = ["get_model", "UNet", "MedFormer", "SwinUNETR", "DiceLoss", "DiceCELoss", "CrossEntropyLoss", "B200SegError",
            "EXPORTED_SYMBOLS", "LIB_PATH"]

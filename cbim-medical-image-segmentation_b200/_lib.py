@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libb200seg.so")
 
 F32, F16 = 0, 1
 ALGO_AUTO, ALGO_DIRECT, ALGO_TC = 0, 1, 2
-ACT_NONE, ACT_RELU = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 
 P = c_void_p
 I = c_int
@@ -58,6 +58,15 @@ _PROTOS = {
     "b200seg_layernorm_bwd": [P, P, P, P, P, P, P, I, I, I, P],
     "b200seg_gelu": [P, P, P, L, I, P],
     "b200seg_mhsa": [P, P, P, P, I, I, I, I, F, I, P],
+    "b200seg_resblock_out_fwd": [P, I, P, P, I, I, P, F, I, P, I, I, L, I, I, P],
+    "b200seg_resblock_out_bwd_reduce": [P, I, P, I, P, I, P, P, I, I, P, F, I, P, P, I, L, I, I, P],
+    "b200seg_window_attn_workspace": [I, I, I, I, I, P],
+    "b200seg_window_attn_fwd": [P, P, P, P, P, I, I, I, I, I, I, P, P, I, P],
+    "b200seg_window_attn_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P, P, I, P],
+    "b200seg_swin_merge": [P, P, I, I, I, I, I, I, I, I, P],
+    "b200seg_optim_chunk_elems": [],
+    "b200seg_grads_nonfinite": [P, P, I, P, P],
+    "b200seg_adamw_ema_step": [P, P, I, F, F, F, F, F, F, P, P, P, P],
     "b200seg_biattn_workspace": [I, L, I, I],
     "b200seg_biattn_fwd": [P, I, I, P, I, I, P, I, P, I, I, P, I, I, P, I, I, P, P, I, L, I, I, I, F, I, P],
     "b200seg_biattn_bwd": [P, I, I, P, I, I, P, I, P, I, I, P, I, I, P, P, I, I, P, I, I, P, I, I, P, I, I,
@@ -65,7 +74,7 @@ _PROTOS = {
 }
 _RESTYPES = {"b200seg_strerror": c_char_p, "b200seg_last_cuda_error": c_char_p,
              "b200seg_conv3d_wgrad_workspace": ctypes.c_size_t, "b200seg_biattn_workspace": ctypes.c_size_t,
-             "b200seg_mapgen_workspace": ctypes.c_size_t}
+             "b200seg_mapgen_workspace": ctypes.c_size_t, "b200seg_window_attn_workspace": ctypes.c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 
@@ -103,7 +112,7 @@ def check(rc, what):
 
 
 # kernels launched per entry point (dice fwd = reduce + finalize; its memset is not ours)
-_KERNELS = {"b200seg_dice_ce_fwd": 2, "b200seg_biattn_fwd": 2, "b200seg_biattn_bwd": 2,
+_KERNELS = {"b200seg_dice_ce_fwd": 2, "b200seg_biattn_fwd": 2, "b200seg_window_attn_bwd": 2, "b200seg_adamw_ema_step": 2, "b200seg_biattn_bwd": 2,
             "b200seg_mapgen_fwd": 2}
 launch_count = 0
 

@@ -39,7 +39,8 @@ extern "C" int b200seg_check_device(void) {
 }
 
 extern "C" int b200seg_conv3d_algo(int Cin, int Cout, int kd, int kh, int kw, int dtype, int B) {
-  if (conv3d_tc_shape_ok(Cin, Cout, kd, kh, kw, dtype) && B * Cin <= 4096 && B * Cout <= 2048) return B200SEG_ALGO_TC;
+  // (outputs wider than 2048 channels per batch run on the tensor cores only without fused statistics, conv_tc.cu)
+  if (conv3d_tc_shape_ok(Cin, Cout, kd, kh, kw, dtype) && B * Cin <= 4096 && B * Cout <= 8192) return B200SEG_ALGO_TC;
   return B200SEG_ALGO_DIRECT;
 }
 

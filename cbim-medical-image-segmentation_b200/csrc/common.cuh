@@ -64,6 +64,16 @@ template <> __device__ __forceinline__ void st8<__half>(__half* p, const float (
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// ---- activations (B200SEG_ACT_*) ------------------------------------------------
+#define B200SEG_LRELU_SLOPE 0.01f
+__device__ __forceinline__ float act_apply(float h, int act) {
+  return act == B200SEG_ACT_RELU ? fmaxf(h, 0.f) : (act == B200SEG_ACT_LRELU ? (h > 0.f ? h : B200SEG_LRELU_SLOPE * h) : h);
+}
+// derivative of the activation at pre-activation h, as the factor the incoming gradient is multiplied with
+__device__ __forceinline__ float act_grad(float h, int act) {
+  return act == B200SEG_ACT_RELU ? (h > 0.f ? 1.f : 0.f) : (act == B200SEG_ACT_LRELU ? (h > 0.f ? 1.f : B200SEG_LRELU_SLOPE) : 1.f);
+}
+
 // ---- reductions ---------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

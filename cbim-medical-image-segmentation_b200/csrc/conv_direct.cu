@@ -79,9 +79,9 @@ conv_fwd_direct_kernel(ConvArgs a) {
 #pragma unroll
               for (int j = 0; j < CIV; ++j) xv[j] = (xv[j] - s_mean[ci0 + j]) * s_rstd[ci0 + j];
             }
-            if (a.act == B200SEG_ACT_RELU) {
+            if (a.act) {
 #pragma unroll
-              for (int j = 0; j < CIV; ++j) xv[j] = fmaxf(xv[j], 0.f);
+              for (int j = 0; j < CIV; ++j) xv[j] = act_apply(xv[j], a.act);
             }
             // operands are rounded to the storage dtype exactly as the tensor-core path feeds them
 #pragma unroll
@@ -117,7 +117,7 @@ conv_fwd_direct_kernel(ConvArgs a) {
         float mean, rstd;
         stats_to_mean_rstd(a.g_stats + ((int64_t)b * a.Cout + co0 + co) * 2, (double)V, a.g_eps, mean, rstd);
         float hx = (Elem<T>::ld(gp + co) - mean) * rstd;
-        if (a.g_act == B200SEG_ACT_RELU && !(hx > 0.f)) r = 0.f;
+        r *= act_grad(hx, a.g_act);
         r = Elem<T>::round(r);
         s1[co] = r; s2[co] = r * hx;
       } else {
@@ -198,7 +198,7 @@ conv_wgrad_direct_kernel(WgradArgs a) {
           if ((unsigned)d < (unsigned)a.D && (unsigned)h < (unsigned)a.H && (unsigned)w < (unsigned)a.W) {
             av = Elem<T>::ld(xb + (((int64_t)d * a.H + h) * a.W + w) * a.x_ld + ci0 + lc);
             if (norm) av = (av - mean) * rstd;
-            if (a.act == B200SEG_ACT_RELU) av = fmaxf(av, 0.f);
+            av = act_apply(av, a.act);
             av = Elem<T>::round(av);
           }
         }

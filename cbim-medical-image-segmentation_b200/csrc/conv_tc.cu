@@ -52,9 +52,12 @@ constexpr int kWgtWarp = 16;
 constexpr int kMmaWarp = 17;
 constexpr int kThreads = 20 * 32;   // 640: five complete warpgroups (setmaxnreg is a warpgroup-wide instruction);
                                     // warps 18-19 only take part in the block-wide barriers
-// registers per thread after the role dispatch (launch allotment: 65536 / 640 -> 96 each):
-//   2 epilogue warpgroups x 144 + 2 loader warpgroups x 72 + {weights, MMA, 2 idle} x 80  == 65536
-constexpr int kRegsEpi = 144, kRegsLoad = 72, kRegsMma = 80;
+// Registers per thread after the role dispatch.  setmaxnreg trades registers inside the CTA's OWN pool — what the
+// launch allotted: 640 threads x 96 = 61440, not the SM's 65536 (an over-subscribed split makes setmaxnreg.inc spin
+// forever: measured the hard way) — so:  2 epilogue warpgroups x 144 + 2 loader warpgroups x 64 + {weights, MMA,
+// 2 idle} x 64 == 61440.
+constexpr int kRegsLaunch = 96, kRegsEpi = 144, kRegsLoad = 64, kRegsMma = 64;
+static_assert(2 * 128 * kRegsEpi + 2 * 128 * kRegsLoad + 128 * kRegsMma <= kThreads * kRegsLaunch, "register split exceeds the CTA pool");
 
 struct TcParams {
   ConvArgs a;
@@ -164,7 +167,7 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
   const int c8 = lt % cpv, v0 = lt / cpv;
   const int ph = a.kh / 2, pw = a.kw / 2;
   const bool xform = (a.x_stats != nullptr) || (a.act != 0);
-  const bool relu = a.act == B200SEG_ACT_RELU;
+  const int act = a.act;
   const __half* xbase = reinterpret_cast<const __half*>(a.x);
   const uint32_t smem_a = smem_u32(smem + p.smem_a_off) + (uint32_t)(c8 * p.plane_stride);
   uint8_t* smem_a_gen = smem + p.smem_a_off + c8 * p.plane_stride;
@@ -243,7 +246,7 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
           for (int j = 0; j < 4; ++j) {
             float2 f = __half22float2(hv[j]);
             f.x = fmaf(f.x, sc[2 * j], sf[2 * j]); f.y = fmaf(f.y, sc[2 * j + 1], sf[2 * j + 1]);
-            if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+            if (act) { f.x = act_apply(f.x, act); f.y = act_apply(f.y, act); }
             hv[j] = __floats2half2_rn(f.x, f.y);
           }
           *reinterpret_cast<uint4*>(sp + ((i0 + u) * vstep) * 16) = raw[u];
@@ -291,7 +294,7 @@ __device__ __forceinline__ void epi_chunk(const ConvArgs& a, bool valid, bool dg
     for (int j = 0; j < 16; ++j) {
       const float2 mr = gnorm[j];
       const float hx = (sv[j] - mr.x) * mr.y;
-      float g = (a.g_act == B200SEG_ACT_RELU && !(hx > 0.f)) ? 0.f : r[j];
+      float g = r[j] * act_grad(hx, a.g_act);
       g = __half2float(__float2half_rn(g));
       r[j] = g; s2[j] = g * hx;
     }
@@ -499,7 +502,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         s_gnorm[i] = make_float2(m, r);
       }
     }
-    const int nstat = kStatCopies * a.B * a.Cout * 2;
+    const int nstat = a.y_stats ? kStatCopies * a.B * a.Cout * 2 : 0;
     for (int i = threadIdx.x; i < nstat; i += kThreads) s_stat[i] = 0.f;
   }
   tc_fence_before();
@@ -676,7 +679,9 @@ bool conv3d_fwd_tc_supported(const ConvArgs& a, int dtype) {
   if (a.res && ((a.r_ld % 8) || (a.r_coff % 8))) return false;
   if (a.gx && ((a.gx_ld % 8) || (a.gx_coff % 8))) return false;
   if ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.y) | reinterpret_cast<uintptr_t>(a.w)) & 15) return false;
-  if (a.B * a.Cin > 4096 || a.B * a.Cout > 2048) return false;
+  if (a.B * a.Cin > 4096 || a.B * a.Cout > 8192) return false;
+  // per-CTA InstanceNorm partial sums / dgrad constants live in shared memory: [B][Cout] tables
+  if ((a.y_stats || a.gx) && a.B * a.Cout > 2048) return false;
   return true;
 }
 
@@ -706,8 +711,9 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   p.tmem_cols = pow2;
   // shared memory carve-up
   const int norm_bytes = a.B * a.Cin * 8;
-  const int stat_bytes = kStatCopies * a.B * a.Cout * 2 * 4;
-  const int budget = 227 * 1024 - 1024 - norm_bytes - stat_bytes - a.B * a.Cout * 8 - 512;
+  const int stat_bytes = a.y_stats ? kStatCopies * a.B * a.Cout * 2 * 4 : 0;
+  const int gnorm_bytes = a.gx ? a.B * a.Cout * 8 : 0;
+  const int budget = 227 * 1024 - 1024 - norm_bytes - stat_bytes - gnorm_bytes - 512;
   const int64_t w_total = (int64_t)a.kd * a.kh * a.kw * a.Cin * a.Cout * 2;
   int b_region;
   if (w_total <= 112 * 1024 && w_total + 2 * p.a_stage_bytes <= budget) {
@@ -733,7 +739,7 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   off = (off + 15) / 16 * 16;
   p.smem_norm_off = off; off += norm_bytes;
   off = (off + 15) / 16 * 16;
-  p.smem_gnorm_off = off; off += a.B * a.Cout * 8;
+  p.smem_gnorm_off = off; off += gnorm_bytes;
   off = (off + 15) / 16 * 16;
   p.smem_stat_off = off; off += stat_bytes;
   const int smem_bytes = off + 1024;       // slack for the 1024-B alignment of the dynamic segment

@@ -103,7 +103,7 @@ apply_kernel(const T* __restrict__ x, int x_ld, int x_coff, const double* __rest
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       float h = (a[i] - mean[i]) * rstd[i];
-      a[i] = (act == B200SEG_ACT_RELU) ? fmaxf(h, 0.f) : h;
+      a[i] = act_apply(h, act);
     }
     Vec<VEC, T>::st(yb + v * y_ld, a);
   }
@@ -135,7 +135,7 @@ bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, int dy_coff, const T* __r
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         float h = (a[i] - mean[i]) * rstd[i];
-        float gg = (act == B200SEG_ACT_RELU && !(h > 0.f)) ? 0.f : d[i];
+        float gg = d[i] * act_grad(h, act);
         gg = Elem<T>::round(gg);
         d[i] = gg;
         acc[i] += gg;
@@ -220,6 +220,90 @@ inline int64_t pick_vpb(int64_t V, int B, int C) {
   if (vpp < 1) vpp = 1;
   if (vpb < 8 * vpp) vpb = 8 * vpp;
   return vpb;
+}
+
+
+// ---- output stage of monai's UnetResBlock (call sites swin_unetr.py:129-226):
+//   y = lrelu( IN(r2) + res ),  res = IN(r3) when the block has its 1x1 projection (stats3 != NULL), else r3 as is.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+resout_fwd_kernel(const T* __restrict__ r2, int r2_ld, const double* __restrict__ stats2, const T* __restrict__ r3, int r3_ld,
+                  int r3_coff, const double* __restrict__ stats3, float eps, int act, T* __restrict__ y, int y_ld,
+                  int64_t V, int C, int64_t vpb) {
+  Iter it = make_iter<VEC>(C, V, vpb);
+  const int b = blockIdx.y;
+  if (!it.active) return;
+  float m2[VEC], s2[VEC], m3[VEC], s3[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int64_t o = ((int64_t)b * C + it.cchunk * VEC + i) * 2;
+    stats_to_mean_rstd(stats2 + o, (double)V, eps, m2[i], s2[i]);
+    m3[i] = 0.f; s3[i] = 1.f;
+    if (stats3) stats_to_mean_rstd(stats3 + o, (double)V, eps, m3[i], s3[i]);
+  }
+  const T* a2 = r2 + (int64_t)b * V * r2_ld + it.cchunk * VEC;
+  const T* a3 = r3 + (int64_t)b * V * r3_ld + r3_coff + it.cchunk * VEC;
+  T* yb = y + (int64_t)b * V * y_ld + it.cchunk * VEC;
+  for (int64_t v = it.v0 + it.vloc; v < it.v1; v += it.vpp) {
+    float a[VEC], c[VEC];
+    Vec<VEC, T>::ld(a2 + v * r2_ld, a);
+    Vec<VEC, T>::ld(a3 + v * r3_ld, c);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      // both normalised branches are rounded to the storage dtype before the add, like the reference's tensors
+      const float h2 = Elem<T>::round((a[i] - m2[i]) * s2[i]);
+      const float h3 = stats3 ? Elem<T>::round((c[i] - m3[i]) * s3[i]) : c[i];
+      a[i] = act_apply(Elem<T>::round(h2 + h3), act);
+    }
+    Vec<VEC, T>::st(yb + v * y_ld, a);
+  }
+}
+
+// g = dy * act'(y) (the sign of y is the sign of the pre-activation) and the three sums {g, g*xhat2, g*xhat3} per (b,c)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+resout_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ y, int y_ld, const T* __restrict__ r2, int r2_ld,
+                         const double* __restrict__ stats2, const T* __restrict__ r3, int r3_ld, int r3_coff,
+                         const double* __restrict__ stats3, float eps, int act, T* __restrict__ g, double* __restrict__ sums,
+                         int64_t V, int C, int64_t vpb) {
+  extern __shared__ float smem[];
+  Iter it = make_iter<VEC>(C, V, vpb);
+  const int b = blockIdx.y;
+  float acc[3 * VEC];
+#pragma unroll
+  for (int i = 0; i < 3 * VEC; ++i) acc[i] = 0.f;
+  if (it.active) {
+    float m2[VEC], s2[VEC], m3[VEC], s3[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int64_t o = ((int64_t)b * C + it.cchunk * VEC + i) * 2;
+      stats_to_mean_rstd(stats2 + o, (double)V, eps, m2[i], s2[i]);
+      m3[i] = 0.f; s3[i] = 1.f;
+      if (stats3) stats_to_mean_rstd(stats3 + o, (double)V, eps, m3[i], s3[i]);
+    }
+    const T* dyb = dy + (int64_t)b * V * dy_ld + it.cchunk * VEC;
+    const T* yb = y + (int64_t)b * V * y_ld + it.cchunk * VEC;
+    const T* a2 = r2 + (int64_t)b * V * r2_ld + it.cchunk * VEC;
+    const T* a3 = r3 + (int64_t)b * V * r3_ld + r3_coff + it.cchunk * VEC;
+    T* gb = g + (int64_t)b * V * C + it.cchunk * VEC;
+    for (int64_t v = it.v0 + it.vloc; v < it.v1; v += it.vpp) {
+      float d[VEC], o[VEC], a[VEC], c[VEC];
+      Vec<VEC, T>::ld(dyb + v * dy_ld, d);
+      Vec<VEC, T>::ld(yb + v * y_ld, o);
+      Vec<VEC, T>::ld(a2 + v * r2_ld, a);
+      if (stats3) Vec<VEC, T>::ld(a3 + v * r3_ld, c);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float gg = Elem<T>::round(d[i] * act_grad(o[i], act));
+        d[i] = gg;
+        acc[i] += gg;
+        acc[VEC + i] += gg * ((a[i] - m2[i]) * s2[i]);
+        if (stats3) acc[2 * VEC + i] += gg * ((c[i] - m3[i]) * s3[i]);
+      }
+      Vec<VEC, T>::st(gb + v * C, d);
+    }
+  }
+  block_reduce_to_global<VEC, 3>(acc, it, smem, sums + (int64_t)b * C * 3, C);
 }
 
 }  // namespace
@@ -328,5 +412,42 @@ extern "C" int b200seg_copy_channels(const void* x, int x_dtype, int x_ld, int x
   else return B200SEG_EINVAL;
   if (rc) return rc;
   B200_CHECK_LAUNCH("copy_kernel");
+  return B200SEG_OK;
+}
+
+extern "C" int b200seg_resblock_out_fwd(const void* r2, int r2_ld, const double* stats2, const void* r3, int r3_ld, int r3_coff,
+                                        const double* stats3, float eps, int act, void* y, int y_ld, int B, int64_t V, int C,
+                                        int dtype, void* stream) {
+  if (!r2 || !stats2 || !r3 || !y || B <= 0 || V <= 0 || C <= 0) return B200SEG_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  int64_t vpb = pick_vpb(V, B, C);
+  dim3 grid(ceil_div(V, vpb), B);
+  bool vok = vec_ok(r2, r2_ld, 0, C, 1) && vec_ok(r3, r3_ld, r3_coff, C, 1) && vec_ok(y, y_ld, 0, C, 1);
+  if (!vok && C > kThreads) return B200SEG_EUNSUPPORTED;
+  DISPATCH_TV(dtype, vok, {
+    resout_fwd_kernel<T, VEC><<<grid, kThreads, 0, st>>>((const T*)r2, r2_ld, stats2, (const T*)r3, r3_ld, r3_coff, stats3, eps, act,
+                                                        (T*)y, y_ld, V, C, vpb);
+  })
+  B200_CHECK_LAUNCH("resout_fwd_kernel");
+  return B200SEG_OK;
+}
+
+extern "C" int b200seg_resblock_out_bwd_reduce(const void* dy, int dy_ld, const void* y, int y_ld, const void* r2, int r2_ld,
+                                               const double* stats2, const void* r3, int r3_ld, int r3_coff,
+                                               const double* stats3, float eps, int act, void* g, double* sums, int B,
+                                               int64_t V, int C, int dtype, void* stream) {
+  if (!dy || !y || !r2 || !stats2 || !r3 || !g || !sums || B <= 0 || V <= 0 || C <= 0) return B200SEG_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  int64_t vpb = pick_vpb(V, B, C);
+  dim3 grid(ceil_div(V, vpb), B);
+  bool vok = vec_ok(dy, dy_ld, 0, C, 1) && vec_ok(y, y_ld, 0, C, 1) && vec_ok(r2, r2_ld, 0, C, 1) &&
+             vec_ok(r3, r3_ld, r3_coff, C, 1) && vec_ok(g, C, 0, C, 1);
+  if (!vok && C > kThreads) return B200SEG_EUNSUPPORTED;
+  DISPATCH_TV(dtype, vok, {
+    size_t sm = sizeof(float) * kThreads * 3 * VEC;
+    resout_bwd_reduce_kernel<T, VEC><<<grid, kThreads, sm, st>>>((const T*)dy, dy_ld, (const T*)y, y_ld, (const T*)r2, r2_ld, stats2,
+                                                                (const T*)r3, r3_ld, r3_coff, stats3, eps, act, (T*)g, sums, V, C, vpb);
+  })
+  B200_CHECK_LAUNCH("resout_bwd_reduce_kernel");
   return B200SEG_OK;
 }

@@ -12,11 +12,12 @@
 namespace {
 
 // ------------------------------------------------------------------ space to depth (and its inverse)
-template <typename T>
+template <typename T, int VEC>
 __global__ void s2d_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Do, int Ho, int Wo, int C,
                            int sd, int sh, int sw, int reverse) {
   // forward: y[b,d,h,w,(q,c)] = x[b, d*sd+i, h*sh+j, w*sw+k, c],  q = (i*sh + j)*sw + k   (:165-169 nesting)
-  const int ncg = C >> 3, Q = sd * sh * sw;
+  // VEC = 8 channels per thread (16-byte accesses) when C % 8 == 0, else 1 (e.g. the single-channel SwinUNETR input)
+  const int ncg = C / VEC, Q = sd * sh * sw;
   const int64_t total = (int64_t)B * Do * Ho * Wo * Q * ncg;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = it;
@@ -26,11 +27,15 @@ __global__ void s2d_kernel(const T* __restrict__ x, T* __restrict__ y, int B, in
     const int h = (int)(r % Ho); r /= Ho;
     const int d = (int)(r % Do); const int b = (int)(r / Do);
     const int k = q % sw, j = (q / sw) % sh, i = q / (sw * sh);
-    const int64_t xo = ((((int64_t)b * Do * sd + d * sd + i) * (Ho * sh) + h * sh + j) * (Wo * sw) + w * sw + k) * C + cg * 8;
-    const int64_t yo = ((((int64_t)b * Do + d) * Ho + h) * Wo + w) * ((int64_t)Q * C) + (int64_t)q * C + cg * 8;
-    float v[8];
-    if (!reverse) { ld8<T>(x + xo, v); st8<T>(y + yo, v); }
-    else { ld8<T>(y + yo, v); st8<T>(const_cast<T*>(x) + xo, v); }
+    const int64_t xo = ((((int64_t)b * Do * sd + d * sd + i) * (Ho * sh) + h * sh + j) * (Wo * sw) + w * sw + k) * C + cg * VEC;
+    const int64_t yo = ((((int64_t)b * Do + d) * Ho + h) * Wo + w) * ((int64_t)Q * C) + (int64_t)q * C + cg * VEC;
+    if constexpr (VEC == 8) {
+      float v[8];
+      if (!reverse) { ld8<T>(x + xo, v); st8<T>(y + yo, v); }
+      else { ld8<T>(y + yo, v); st8<T>(const_cast<T*>(x) + xo, v); }
+    } else {
+      if (!reverse) y[yo] = x[xo]; else const_cast<T*>(x)[xo] = y[yo];
+    }
   }
 }
 
@@ -327,23 +332,34 @@ __global__ void layernorm_fwd_kernel(const T* x, const float* gamma, const float
   for (int c = lane; c < C; c += 32) Elem<T>::st(y + (int64_t)row * C + c, (Elem<T>::ld(xr + c) - mean) * rstd * gamma[c] + beta[c]);
   if (lane == 0) { mr[row * 2] = mean; mr[row * 2 + 1] = rstd; }
 }
+// Persistent blocks (4 warps, one row per warp per step); d(gamma) / d(beta) are accumulated in shared memory and
+// flushed with ONE global atomic per (block, channel) — the Swin token streams have 10^5..10^6 rows per LayerNorm.
 template <typename T>
 __global__ void layernorm_bwd_kernel(const T* dy, const T* x, const float* gamma, const float* mr, T* dx, float* dgamma, float* dbeta, int R, int C) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= R) return;
-  const float mean = mr[row * 2], rstd = mr[row * 2 + 1];
-  const T* xr = x + (int64_t)row * C; const T* gr = dy + (int64_t)row * C;
-  float s1 = 0.f, s2 = 0.f;
-  for (int c = lane; c < C; c += 32) {
-    const float xh = (Elem<T>::ld(xr + c) - mean) * rstd, g = Elem<T>::ld(gr + c);
-    const float gg = g * gamma[c];
-    s1 += gg; s2 = fmaf(gg, xh, s2);
-    atomicAdd(&dgamma[c], g * xh); atomicAdd(&dbeta[c], g);
+  extern __shared__ float s_gb[];               // [2][C]
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) s_gb[c] = 0.f;
+  __syncthreads();
+  const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < R; row += gridDim.x * wpb) {
+    const float mean = mr[row * 2], rstd = mr[row * 2 + 1];
+    const T* xr = x + (int64_t)row * C; const T* gr = dy + (int64_t)row * C;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (Elem<T>::ld(xr + c) - mean) * rstd, g = Elem<T>::ld(gr + c);
+      const float gg = g * gamma[c];
+      s1 += gg; s2 = fmaf(gg, xh, s2);
+      atomicAdd(&s_gb[c], g * xh); atomicAdd(&s_gb[C + c], g);
+    }
+    s1 = warp_sum(s1) / C; s2 = warp_sum(s2) / C;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (Elem<T>::ld(xr + c) - mean) * rstd, gg = Elem<T>::ld(gr + c) * gamma[c];
+      Elem<T>::st(dx + (int64_t)row * C + c, rstd * (gg - s1 - xh * s2));
+    }
   }
-  s1 = warp_sum(s1) / C; s2 = warp_sum(s2) / C;
-  for (int c = lane; c < C; c += 32) {
-    const float xh = (Elem<T>::ld(xr + c) - mean) * rstd, gg = Elem<T>::ld(gr + c) * gamma[c];
-    Elem<T>::st(dx + (int64_t)row * C + c, rstd * (gg - s1 - xh * s2));
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (s_gb[c] != 0.f) atomicAdd(&dgamma[c], s_gb[c]);
+    if (s_gb[C + c] != 0.f) atomicAdd(&dbeta[c], s_gb[C + c]);
   }
 }
 
@@ -479,9 +495,10 @@ inline bool ok_dtype(int d) { return d == B200SEG_F16 || d == B200SEG_F32; }
 extern "C" int b200seg_space_to_depth(void* x, void* y, int B, int Do, int Ho, int Wo, int C, int sd, int sh, int sw,
                                       int reverse, int dtype, void* stream) {
   if (!x || !y || B <= 0 || Do <= 0 || Ho <= 0 || Wo <= 0 || sd <= 0 || sh <= 0 || sw <= 0 || !ok_dtype(dtype)) return B200SEG_EINVAL;
-  if (C % 8) return B200SEG_EUNSUPPORTED;
-  const int64_t total = (int64_t)B * Do * Ho * Wo * sd * sh * sw * (C / 8);
-  DISPATCH_T(dtype, s2d_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, B, Do, Ho, Wo, C, sd, sh, sw, reverse));
+  const bool vec = (C % 8) == 0;
+  const int64_t total = (int64_t)B * Do * Ho * Wo * sd * sh * sw * (vec ? C / 8 : C);
+  if (vec) { DISPATCH_T(dtype, s2d_kernel<T, 8><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, B, Do, Ho, Wo, C, sd, sh, sw, reverse)); }
+  else { DISPATCH_T(dtype, s2d_kernel<T, 1><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, B, Do, Ho, Wo, C, sd, sh, sw, reverse)); }
   B200_CHECK_LAUNCH("space_to_depth");
   return B200SEG_OK;
 }
@@ -607,7 +624,10 @@ extern "C" int b200seg_layernorm_fwd(const void* x, const float* gamma, const fl
 extern "C" int b200seg_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean_rstd, void* dx,
                                      float* dgamma, float* dbeta, int R, int C, int dtype, void* stream) {
   if (!dy || !x || !gamma || !mean_rstd || !dx || !dgamma || !dbeta || R <= 0 || C <= 0 || !ok_dtype(dtype)) return B200SEG_EINVAL;
-  DISPATCH_T(dtype, layernorm_bwd_kernel<T><<<(R + 3) / 4, 128, 0, as_stream(stream)>>>((const T*)dy, (const T*)x, gamma, mean_rstd, (T*)dx, dgamma, dbeta, R, C));
+  if (C > 6000) return B200SEG_EUNSUPPORTED;
+  int grid = (R + 3) / 4; if (grid > B200SEG_NUM_SMS * 8) grid = B200SEG_NUM_SMS * 8;
+  const size_t sm = sizeof(float) * 2 * (size_t)C;
+  DISPATCH_T(dtype, layernorm_bwd_kernel<T><<<grid, 128, sm, as_stream(stream)>>>((const T*)dy, (const T*)x, gamma, mean_rstd, (T*)dx, dgamma, dbeta, R, C));
   B200_CHECK_LAUNCH("layernorm_bwd");
   return B200SEG_OK;
 }

@@ -184,7 +184,7 @@ wgrad_head_kernel(WgradArgs a) {
         for (int k = 0; k < CPT; ++k) {
           float t = xv[u][k];
           if (a.x_stats) t = (t - mean[k]) * rstd[k];
-          if (a.act == B200SEG_ACT_RELU) t = fmaxf(t, 0.f);
+          t = act_apply(t, a.act);
           t = in ? Elem<T>::round(t) : 0.f;
 #pragma unroll
           for (int c = 0; c < MAXCO; ++c) acc[k][c] = fmaf(g[u][c], t, acc[k][c]);

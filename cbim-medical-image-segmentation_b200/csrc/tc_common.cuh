@@ -7,7 +7,7 @@
 
 namespace tc {
 
-constexpr uint32_t kSpinLimit = 1u << 17;     // x up to kSuspendNs each: a protocol bug traps after a few seconds
+constexpr long long kWaitTimeoutCycles = 4000000000ll;   // ~2 s at 1.9 GHz: a protocol bug traps, it never hangs the GPU
 constexpr uint32_t kSuspendNs = 20000;         // suspend-time hint of a blocked try_wait (the thread is woken on completion)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -37,9 +37,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
   (void)code;
   if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > kSpinLimit) __trap();
+    if (clock64() - t0 > kWaitTimeoutCycles) __trap();
   }
 }
 // (kept as a separate name for the MMA warp's waits: with a call on the slow path the compiler keeps the loop-carried

@@ -170,7 +170,7 @@ __device__ __forceinline__ void wg_loader(const WgParams& p, const Job& job, uin
         const float2 mr = s_norm[cd.b * p.NTC + c8_a * 8 + j];
         sc[j] = mr.y; sf[j] = -mr.x * mr.y;
       }
-      const bool relu = p.act == B200SEG_ACT_RELU;
+      const int act = p.act;
       int hh = hh0, ww = ww0;
 #pragma unroll 2
       for (int v = v0_a; v < p.nvox_h; v += vstep_a) {
@@ -182,7 +182,7 @@ __device__ __forceinline__ void wg_loader(const WgParams& p, const Job& job, uin
           for (int j = 0; j < 4; ++j) {
             float2 f = __half22float2(hv[j]);
             f.x = fmaf(f.x, sc[2 * j], sf[2 * j]); f.y = fmaf(f.y, sc[2 * j + 1], sf[2 * j + 1]);
-            if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+            if (act) { f.x = act_apply(f.x, act); f.y = act_apply(f.y, act); }
             hv[j] = __floats2half2_rn(f.x, f.y);
           }
           *reinterpret_cast<uint4*>(sp + v * 16) = raw;

@@ -21,7 +21,12 @@ def get_model(args, pretrain=False):
                              fusion_heads=args.fusion_heads, expansion=args.expansion, attn_drop=args.attn_drop,
                              proj_drop=args.proj_drop, proj_type=args.proj_type, norm=args.norm, act=args.act,
                              kernel_size=args.kernel_size, scale=args.down_scale, aux_loss=args.aux_loss)   # :95
-        raise ValueError("model %r (3d) is not implemented by the B200 path yet" % (args.model,))
+        if args.model == 'swin_unetr':
+            from .swin_unetr import SwinUNETR
+            if getattr(args, 'pretrain', False) or pretrain:
+                raise ValueError('No pretrain model available')   # model/utils.py:113-115 loads a site-local file
+            return SwinUNETR(args.window_size, args.in_chan, args.classes, feature_size=args.base_chan)   # :111
+        raise ValueError("model %r (3d) is not implemented by the B200 path" % (args.model,))
     if args.dimension == '2d':
         raise ValueError("2d models are outside the B200 hot path (SURVEY.md §2); use the reference")
     raise ValueError("Invalid dimension, should be '2d' or '3d'")

@@ -53,7 +53,8 @@ enum {
 enum { B200SEG_ALGO_AUTO = 0, B200SEG_ALGO_DIRECT = 1, B200SEG_ALGO_TC = 2 };
 
 /* activation applied to the (optionally normalised) conv input in the loader */
-enum { B200SEG_ACT_NONE = 0, B200SEG_ACT_RELU = 1 };
+enum { B200SEG_ACT_NONE = 0, B200SEG_ACT_RELU = 1,
+       B200SEG_ACT_LRELU = 2 /* LeakyReLU(negative_slope = 0.01): monai UnetResBlock, swin_unetr.py:129-226 */ };
 
 int         b200seg_version(void);
 const char* b200seg_strerror(int code);
@@ -327,6 +328,74 @@ int b200seg_layernorm_bwd(const void* dy, const void* x, const float* gamma, con
 int b200seg_gelu(const void* x, const void* dy, void* out, int64_t n, int dtype, void* stream);
 int b200seg_mhsa(const void* qkv, const void* dout, void* out, void* dqkv, int B, int L, int heads, int dim_head,
                  float scale, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * SwinUNETR operators (model/dim3/swin_unetr.py; monai 1.1.0 blocks at its call
+ * sites :129-228).  Channels-last tensors.
+ *
+ * resblock_out: output stage of monai's UnetResBlock,
+ *   y = act( IN(r2) + res ),  res = IN(r3) when stats3 != NULL (the block's 1x1
+ *   projection branch) else r3 itself; act = B200SEG_ACT_LRELU.
+ *   bwd_reduce: g = dy * act'(y) (dense [V][C]) and sums[b][c][3] =
+ *   {sum g, sum g*xhat2, sum g*xhat3} for the two InstanceNorm backward passes.
+ * window_attn: WindowAttention.forward :467-490 between the qkv and proj Linears,
+ *   fused with forward_part1's pad / roll / window_partition / window_reverse
+ *   (:554-606), compute_mask (:737-773) and the relative-position-bias gather
+ *   (:417-459,473-476).  qkv [B,D,H,W,3*heads*dh] ({q,k,v} x heads x dh), out
+ *   [B,D,H,W,heads*dh]; window/shift are the module's nominal int[3] (clamping to
+ *   short axes, get_window_size :358-381, happens inside).  qkv_bias (nullable)
+ *   stands in for the q/k/v of padding tokens (the reference pads before the qkv
+ *   Linear); bwd adds those tokens' gradients to dbias_pad [3*heads*dh] and the
+ *   bias-table gradient to dtable [(2w0-1)(2w1-1)(2w2-1)][heads] (both +=).
+ *   lse / delta: fp32 buffers of b200seg_window_attn_workspace() bytes.
+ * swin_merge: PatchMerging gather, v2 == 0: the v0.9 slice list of :717-727 WITH its
+ *   duplicated slices (x5 == x2, x6 == x3), v2 != 0: PatchMergingV2's product order
+ *   (:693-695); x [B,D,H,W,C] -> y [B,ceil(D/2),ceil(H/2),ceil(W/2),8C] (odd
+ *   extents zero-padded, :714-716); reverse != 0: x is dy, y receives dx.
+ * ------------------------------------------------------------------------- */
+int b200seg_resblock_out_fwd(const void* r2, int r2_ld, const double* stats2,
+                             const void* r3, int r3_ld, int r3_coff, const double* stats3,
+                             float eps, int act, void* y, int y_ld,
+                             int B, int64_t V, int C, int dtype, void* stream);
+int b200seg_resblock_out_bwd_reduce(const void* dy, int dy_ld, const void* y, int y_ld,
+                                    const void* r2, int r2_ld, const double* stats2,
+                                    const void* r3, int r3_ld, int r3_coff, const double* stats3,
+                                    float eps, int act, void* g, double* sums,
+                                    int B, int64_t V, int C, int dtype, void* stream);
+size_t b200seg_window_attn_workspace(int B, int D, int H, int W, int heads, const int* window);
+int b200seg_window_attn_fwd(const void* qkv, const float* qkv_bias, const float* bias_table,
+                            void* out, float* lse, int B, int D, int H, int W, int heads, int dh,
+                            const int* window, const int* shift, int dtype, void* stream);
+int b200seg_window_attn_bwd(const void* qkv, const float* qkv_bias, const float* bias_table,
+                            const void* out, const void* dout, const float* lse, float* delta,
+                            void* dqkv, float* dtable, float* dbias_pad,
+                            int B, int D, int H, int W, int heads, int dh,
+                            const int* window, const int* shift, int dtype, void* stream);
+int b200seg_swin_merge(const void* x, void* y, int B, int D, int H, int W, int C,
+                       int reverse, int v2, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Optimiser tail: GradScaler non-finite check + unscale, AdamW
+ * (training/utils.py:8-14, eps 1e-5) and the EMA update (training/utils.py:98-105,
+ * ema_alpha = this iteration's min(1 - 1/(iter+1), cap), computed by the caller) as
+ * multi-tensor kernels over a device table.
+ *   table_dev : int64 [ntensors][6] = {grad, param, exp_avg, exp_avg_sq, ema param
+ *               (0 = none), numel}; all fp32, contiguous
+ *   chunks_dev: int64 [nchunks][2] = {tensor index, first element}; a chunk covers
+ *               b200seg_optim_chunk_elems() elements
+ * grads_nonfinite raises *found_inf (device float, zeroed by the caller) when any
+ * gradient element is inf / nan.  adamw_ema_step applies one AdamW step unless
+ * *found_inf != 0 (the EMA update runs either way, as in the reference loop);
+ * gradients are divided by *scale (nullable); *step_dev counts the APPLIED steps
+ * (bias corrections) and is advanced on device.
+ * ------------------------------------------------------------------------- */
+int b200seg_optim_chunk_elems(void);
+int b200seg_grads_nonfinite(const int64_t* table_dev, const int64_t* chunks_dev, int nchunks,
+                            float* found_inf, void* stream);
+int b200seg_adamw_ema_step(const int64_t* table_dev, const int64_t* chunks_dev, int nchunks,
+                           float lr, float beta1, float beta2, float eps, float weight_decay,
+                           float ema_alpha, float* step_dev, const float* scale,
+                           const float* found_inf, void* stream);
 
 #ifdef __cplusplus
 }

@@ -122,7 +122,7 @@ def install_monai_standin():
 
 
 CASES = {  # name: (img size, in_ch, classes, feature_size, ce weight, seeds)
-    "swin_unetr_small": ((64, 64, 64), 1, 3, 12, [0.5, 1.0, 2.0], (71, 72)),
+    "swin_unetr_small": ((64, 64, 64), 1, 3, 24, [0.5, 1.0, 2.0], (71, 72)),
 }
 
 
