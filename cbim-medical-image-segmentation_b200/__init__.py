@@ -5,10 +5,14 @@ Importing this package never touches the GPU; every op fails loudly without libb
 from . import _lib
 from ._lib import B200SegError, EXPORTED_SYMBOLS, LIB_PATH
 from .factory import get_model
+from .inference import (calculate_dice, calculate_dice_split, get_inference, inference_sliding_window,
+                        inference_whole_image)
 from .losses import CrossEntropyLoss, DiceCELoss, DiceLoss
 from .medformer import MedFormer
 from .swin_unetr import SwinUNETR
 from .unet3d import UNet
+from .unetpp import UNetPlusPlus
 
-__all__ = ["get_model", "UNet", "MedFormer", "SwinUNETR", "DiceLoss", "DiceCELoss", "CrossEntropyLoss", "B200SegError",
-           "EXPORTED_SYMBOLS", "LIB_PATH"]
+__all__ = ["get_model", "UNet", "MedFormer", "SwinUNETR", "UNetPlusPlus", "DiceLoss", "DiceCELoss", "CrossEntropyLoss", "B200SegError",
+           "EXPORTED_SYMBOLS", "LIB_PATH", "get_inference", "inference_sliding_window", "inference_whole_image",
+           "calculate_dice", "calculate_dice_split"]

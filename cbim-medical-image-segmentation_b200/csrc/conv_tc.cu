@@ -186,6 +186,8 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
     hw[i] = have ? ((uint32_t)hh << 16) | (uint32_t)ww : 0xffffffffu;
   }
 
+  const int nch = (p.nvox_h + vstep - 1) / vstep;       // chunks per thread actually present (warp-uniform loop bound)
+
   TileWalk tw; tw.init(p);
   StageCursor ci, cd;
   ci.init(tw, p); cd.init(tw, p);
@@ -199,7 +201,7 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
     const __half* xs = xbase + (((int64_t)(ci.ti.b * a.D + ci.din) * a.H + hb) * a.W + wb) * a.x_ld + a.x_coff + ci.kc * p.KC + c8 * 8;
 #pragma unroll
     for (int i = 0; i < kMaxChunks; ++i) {
-      if (hw[i] != 0xffffffffu) {
+      if (i < nch && hw[i] != 0xffffffffu) {
         const bool ok = interior || (((unsigned)(hb + (int)(hw[i] >> 16)) < (unsigned)a.H) && ((unsigned)(wb + (int)(hw[i] & 0xffffu)) < (unsigned)a.W));
         cp_async16(dst + (uint32_t)(i * vstep) * 16u, ok ? (const void*)(xs + rel[i]) : (const void*)xbase, ok ? 16u : 0u);
       }
@@ -230,11 +232,12 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
       // warp each scheduler has), zero-filled padding voxels are left untouched (the conv pads the NORMALISED tensor)
 #pragma unroll
       for (int i0 = 0; i0 < kMaxChunks; i0 += 3) {
+        if (i0 >= nch) break;
         uint4 raw[3]; bool ok[3];
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
           const int i = i0 + u;
-          ok[u] = hw[i] != 0xffffffffu &&
+          ok[u] = i < nch && hw[i] != 0xffffffffu &&
                   (interior || (((unsigned)(hb + (int)(hw[i] >> 16)) < (unsigned)a.H) && ((unsigned)(wb + (int)(hw[i] & 0xffffu)) < (unsigned)a.W)));
           if (ok[u]) raw[u] = *reinterpret_cast<const uint4*>(sp + (i * vstep) * 16);
         }
@@ -351,7 +354,29 @@ __device__ __forceinline__ void reg_chunk(const EpiCtx& e, int c, uint32_t trow,
   }
 }
 
-template <bool REGSTATS>
+// Per-row addresses of one tile for this thread
+struct EpiTile { bool valid; int b, co_base; __half* yp; const __half* side; };
+__device__ __forceinline__ EpiTile epi_tile(const TcParams& p, const TileCoord& tc, int hl, int wl, bool dgrad) {
+  const ConvArgs& a = p.a;
+  EpiTile t;
+  const int h = tc.h0 + hl, w = tc.w0 + wl;
+  t.valid = (h < a.H) && (w < a.W);
+  t.b = tc.b;
+  const int64_t vox = ((int64_t)(tc.b * a.D + tc.d) * a.H + h) * a.W + w;
+  t.co_base = tc.ntile * p.NT;
+  t.yp = reinterpret_cast<__half*>(a.y) + vox * a.y_ld + a.y_coff + t.co_base;
+  // side input of the epilogue: the residual, or x for the dgrad ReLU mask
+  t.side = dgrad ? reinterpret_cast<const __half*>(a.gx) + vox * a.gx_ld + a.gx_coff + t.co_base
+                 : (a.res ? reinterpret_cast<const __half*>(a.res) + vox * a.r_ld + a.r_coff + t.co_base : nullptr);
+  return t;
+}
+
+// CPW > 0: NT <= 32*CPW... the warp owns CPW (1 or 2) alternate 16-column chunks and keeps the InstanceNorm sums of
+// the stored values in REGISTERS across all tiles of the persistent CTA; the side input (residual / x) of tile t+1 is
+// requested before tile t is processed, so its global-memory latency never sits on the per-tile critical path
+// (measured: with the request issued at the top of its own tile, ~1.5k cycles per tile were exposed).
+// CPW == 0: wide tiles (NT > 64), butterfly statistics; the MMA time of such tiles hides this epilogue.
+template <int CPW>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, int warp, int lane, uint32_t tmem_base, uint32_t bar0,
                                               const float2* s_gnorm, float* s_stat) {
   const ConvArgs& a = p.a;
@@ -365,61 +390,72 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, int warp, int l
   const int hl = row >> 3, wl = row & 7;
   const bool dgrad = e.dgrad, want_stats = e.want_stats;
   const int nchunks = e.nchunks;
-  float as0[16], aq0[16], as1[16], aq1[16];
-  int acc_b = -1;
-  if (REGSTATS) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { as0[j] = 0.f; aq0[j] = 0.f; as1[j] = 0.f; aq1[j] = 0.f; }
-  }
+  const bool has_side = dgrad || a.res != nullptr;
   int it = 0;
   TileWalk tw; tw.init(p); TileIter ti; ti.init(tw);
-  for (; ti.valid(tw); ti.next(tw), ++it) {
-    const TileCoord tc = ti.coord();
-    const int acc = (p.acc_stages == 2) ? (it & 1) : 0;
-    const uint32_t acc_phase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
-    const int h = tc.h0 + hl, w = tc.w0 + wl;
-    const bool valid = (h < a.H) && (w < a.W);
-    const int64_t vox = ((int64_t)(tc.b * a.D + tc.d) * a.H + h) * a.W + w;
-    const int co_base = tc.ntile * p.NT;
-    __half* yp = reinterpret_cast<__half*>(a.y) + vox * a.y_ld + a.y_coff + co_base;
-    // side input of the epilogue: the residual, or x for the dgrad ReLU mask
-    const __half* side = dgrad ? reinterpret_cast<const __half*>(a.gx) + vox * a.gx_ld + a.gx_coff + co_base
-                               : (a.res ? reinterpret_cast<const __half*>(a.res) + vox * a.r_ld + a.r_coff + co_base : nullptr);
-    const bool has_side = side != nullptr;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
-    const float2* gn = s_gnorm + tc.b * a.Cout + co_base;
-    const float* bias = a.bias ? a.bias + co_base : nullptr;
-    if (REGSTATS) {
-      if (want_stats && tc.b != acc_b) {
-        if (acc_b >= 0) { flush_chunk(e, half, acc_b, as0, aq0); flush_chunk(e, half + 2, acc_b, as1, aq1); }
-        acc_b = tc.b;
+  if constexpr (CPW > 0) {
+    float as0[16], aq0[16], as1[CPW > 1 ? 16 : 1], aq1[CPW > 1 ? 16 : 1];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { as0[j] = 0.f; aq0[j] = 0.f; }
+    if (CPW > 1) {
+#pragma unroll
+      for (int j = 0; j < (CPW > 1 ? 16 : 1); ++j) { as1[j] = 0.f; aq1[j] = 0.f; }
+    }
+    int acc_b = -1;
+    const bool own0 = half < nchunks, own1 = CPW > 1 && half + 2 < nchunks;
+    uint4 n00 = make_uint4(0, 0, 0, 0), n01 = n00, n10 = n00, n11 = n00;       // side input of the NEXT tile
+    EpiTile cur;
+    if (ti.valid(tw)) {
+      cur = epi_tile(p, ti.coord(), hl, wl, dgrad);
+      if (has_side && cur.valid) {
+        if (own0) { n00 = __ldg(reinterpret_cast<const uint4*>(cur.side + 16 * half)); n01 = __ldg(reinterpret_cast<const uint4*>(cur.side + 16 * half + 8)); }
+        if (own1) { n10 = __ldg(reinterpret_cast<const uint4*>(cur.side + 16 * half + 32)); n11 = __ldg(reinterpret_cast<const uint4*>(cur.side + 16 * half + 40)); }
       }
-      // both chunks' side inputs are requested BEFORE waiting for the accumulator: their latency hides behind the MMA
-      uint4 sd00 = make_uint4(0, 0, 0, 0), sd01 = sd00, sd10 = sd00, sd11 = sd00;
-      if (has_side && valid) {
-        if (half < nchunks) {
-          sd00 = __ldg(reinterpret_cast<const uint4*>(side + 16 * half));
-          sd01 = __ldg(reinterpret_cast<const uint4*>(side + 16 * half + 8));
-        }
-        if (half + 2 < nchunks) {
-          sd10 = __ldg(reinterpret_cast<const uint4*>(side + 16 * half + 32));
-          sd11 = __ldg(reinterpret_cast<const uint4*>(side + 16 * half + 40));
+    }
+    for (; ti.valid(tw); ++it) {
+      const int acc = (p.acc_stages == 2) ? (it & 1) : 0;
+      const uint32_t acc_phase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
+      const uint4 s00 = n00, s01 = n01, s10 = n10, s11 = n11;
+      const EpiTile t = cur;
+      ti.next(tw);
+      if (ti.valid(tw)) {                       // request the next tile's side input now
+        cur = epi_tile(p, ti.coord(), hl, wl, dgrad);
+        if (has_side && cur.valid) {
+          if (own0) { n00 = __ldg(reinterpret_cast<const uint4*>(cur.side + 16 * half)); n01 = __ldg(reinterpret_cast<const uint4*>(cur.side + 16 * half + 8)); }
+          if (own1) { n10 = __ldg(reinterpret_cast<const uint4*>(cur.side + 16 * half + 32)); n11 = __ldg(reinterpret_cast<const uint4*>(cur.side + 16 * half + 40)); }
         }
       }
+      if (want_stats && t.b != acc_b) {
+        if (acc_b >= 0) { flush_chunk(e, half, acc_b, as0, aq0); if constexpr (CPW > 1) flush_chunk(e, half + 2, acc_b, as1, aq1); }
+        acc_b = t.b;
+      }
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
+      const float2* gn = s_gnorm + t.b * a.Cout + t.co_base;
+      const float* bias = a.bias ? a.bias + t.co_base : nullptr;
       mbar_wait(T_FULL(acc), acc_phase, 6);
       tc_fence_after();
-      reg_chunk(e, half, trow, T_EMPTY(acc), valid, sd00, sd01, has_side, gn, bias, yp, as0, aq0);
-      reg_chunk(e, half + 2, trow, T_EMPTY(acc), valid, sd10, sd11, has_side, gn, bias, yp, as1, aq1);
-      if (half >= nchunks) {            // a warp that owns no chunk of this tile (NT == 16) still has to release it
+      reg_chunk(e, half, trow, T_EMPTY(acc), t.valid, s00, s01, has_side, gn, bias, t.yp, as0, aq0);
+      if constexpr (CPW > 1) reg_chunk(e, half + 2, trow, T_EMPTY(acc), t.valid, s10, s11, has_side, gn, bias, t.yp, as1, aq1);
+      if (!own0) {                              // a warp that owns no chunk of this tile (NT == 16) still has to release it
         tc_fence_before();
         mbar_arrive(T_EMPTY(acc));
       }
-    } else {
-      float* wstat = s_stat + ((q * a.B + tc.b) * a.Cout + co_base) * 2;
+    }
+    if (want_stats && acc_b >= 0) { flush_chunk(e, half, acc_b, as0, aq0); if constexpr (CPW > 1) flush_chunk(e, half + 2, acc_b, as1, aq1); }
+  } else {
+    for (; ti.valid(tw); ti.next(tw), ++it) {
+      const TileCoord tc = ti.coord();
+      const int acc = (p.acc_stages == 2) ? (it & 1) : 0;
+      const uint32_t acc_phase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
+      const EpiTile t = epi_tile(p, tc, hl, wl, dgrad);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
+      const float2* gn = s_gnorm + tc.b * a.Cout + t.co_base;
+      const float* bias = a.bias ? a.bias + t.co_base : nullptr;
+      float* wstat = s_stat + ((q * a.B + tc.b) * a.Cout + t.co_base) * 2;
       uint4 nx0 = make_uint4(0, 0, 0, 0), nx1 = make_uint4(0, 0, 0, 0);
-      if (has_side && valid && half < nchunks) {
-        nx0 = __ldg(reinterpret_cast<const uint4*>(side + 16 * half));
-        nx1 = __ldg(reinterpret_cast<const uint4*>(side + 16 * half + 8));
+      if (has_side && t.valid && half < nchunks) {
+        nx0 = __ldg(reinterpret_cast<const uint4*>(t.side + 16 * half));
+        nx1 = __ldg(reinterpret_cast<const uint4*>(t.side + 16 * half + 8));
       }
       mbar_wait(T_FULL(acc), acc_phase, 6);
       tc_fence_after();
@@ -428,13 +464,13 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, int warp, int l
         uint32_t v[16];
         tmem_ld16(trow + (uint32_t)n0, v);
         const uint4 cur0 = nx0, cur1 = nx1;
-        if (has_side && valid && c + 2 < nchunks) {        // one chunk AHEAD
-          nx0 = __ldg(reinterpret_cast<const uint4*>(side + n0 + 32));
-          nx1 = __ldg(reinterpret_cast<const uint4*>(side + n0 + 40));
+        if (has_side && t.valid && c + 2 < nchunks) {        // one chunk AHEAD
+          nx0 = __ldg(reinterpret_cast<const uint4*>(t.side + n0 + 32));
+          nx1 = __ldg(reinterpret_cast<const uint4*>(t.side + n0 + 40));
         }
         tmem_ld_wait();
         float r[16], s2[16];
-        epi_chunk(a, valid, dgrad, v, cur0, cur1, has_side, !dgrad && has_side, gn + n0, bias ? bias + n0 : nullptr, yp + n0, r, s2);
+        epi_chunk(a, t.valid, dgrad, v, cur0, cur1, has_side, !dgrad && has_side, gn + n0, bias ? bias + n0 : nullptr, t.yp + n0, r, s2);
         if (want_stats) {
           // column sums over the warp's 32 rows with a halving butterfly: 16 shuffles per quantity
           const float u = column_sum16(r, lane), q2 = column_sum16(s2, lane);
@@ -449,7 +485,6 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, int warp, int l
       mbar_arrive(T_EMPTY(acc));
     }
   }
-  if (REGSTATS && want_stats && acc_b >= 0) { flush_chunk(e, half, acc_b, as0, aq0); flush_chunk(e, half + 2, acc_b, as1, aq1); }
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -644,8 +679,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   } else {
     // =========================== EPILOGUE (warps 0-7) ===========================
     setmaxnreg_inc<kRegsEpi>();
-    if (p.NT <= 64) epilogue_role<true>(p, warp, lane, tmem_base, bar0, s_gnorm, s_stat);
-    else epilogue_role<false>(p, warp, lane, tmem_base, bar0, s_gnorm, s_stat);
+    if (p.NT <= 32) epilogue_role<1>(p, warp, lane, tmem_base, bar0, s_gnorm, s_stat);
+    else if (p.NT <= 64) epilogue_role<2>(p, warp, lane, tmem_base, bar0, s_gnorm, s_stat);
+    else epilogue_role<0>(p, warp, lane, tmem_base, bar0, s_gnorm, s_stat);
   }
 
   // ---- teardown: flush the per-CTA InstanceNorm partial sums, free TMEM

@@ -30,6 +30,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity), "r"(kSuspendNs) : "memory");
   return ok != 0;
 }
+// non-blocking probe (no suspend): has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 // bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.  No out-of-line
 // diagnostics: a CALL anywhere in a kernel that uses setmaxnreg makes ptxas keep every role inside the SMALLEST
 // register allotment (measured: the epilogue stayed below R88 and spilled its accumulators), and a call inside the
@@ -54,6 +64,15 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// 5-D tensor TMA load (SASS: UTMALDG): one box of the tensor map into shared memory, zero-filling out-of-bound
+// coordinates (negative ones included), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 // 16-byte cp.async (SASS: LDGSTS); src_bytes == 0 zero-fills the destination (out-of-volume voxels)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {

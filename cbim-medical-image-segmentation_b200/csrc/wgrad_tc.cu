@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "conv_args.h"
 #include "tc_common.cuh"
+#include "tmap.h"
 #include <string.h>
 #include <stdlib.h>
 
@@ -51,7 +52,10 @@ struct WgParams {
   int tiles_h, tiles_w, nvt;
   int tmem_cols;
   int ts;                                  // A operand (dy^T) is fed from TENSOR MEMORY (narrow Cin: see file header)
+  int use_tma;                             // operand tiles are staged by tensor-TMA boxes (else 16-byte cp.async)
   int smem_bar_off, smem_norm_off;
+  alignas(64) CUtensorMap tm_dy;           // dy  as {8 ch, w, h, plane, b*D+d}
+  alignas(64) CUtensorMap tm_x;            // x   likewise
 };
 
 struct Job { int co_tile, ci_tile, zd, grp, tap0, ntaps, s; };
@@ -200,6 +204,96 @@ __device__ __forceinline__ void wg_loader(const WgParams& p, const Job& job, uin
   cp_async_wait<0>();
 }
 
+// ---- TMA staging: one elected loader thread issues two tensor-TMA boxes per stage (dy tile, x halo tile; out-of-volume
+// voxels zero-filled by the TMA unit), as many stages ahead as the ring has free slots.  When the input needs
+// InstanceNorm / activation, all loader threads then transform the landed halo tile in place and publish FULL; raw
+// operands are consumed straight off the TMA's own barrier (LAND).
+__device__ __forceinline__ void wg_loader_tma(const WgParams& p, const Job& job, uint8_t* smem, const float2* s_norm, uint32_t bar0) {
+  const int lt = threadIdx.x - kLoadWarp0 * 32;
+  const int ph = p.kh / 2, pw = p.kw / 2, zoff = job.zd - p.kd / 2;
+  const int co0 = job.co_tile * MT, ci0 = job.ci_tile * p.NTC;
+  const bool xform = (p.x_stats != nullptr) || (p.act != 0);
+  auto FULL = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  auto EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(p.NS + i); };
+  auto LAND = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.NS + 5 + i); };
+  VtWalk vw; vw.init(p);
+  const uint32_t stage_tx = (uint32_t)(p.dy_bytes + p.a_bytes);
+  if (!xform) {
+    if (lt == 0) {
+      VtCursor c; c.init(vw, p, job.s, zoff);
+      Ring r; r.init(p.NS);
+      for (; c.valid(p); c.next(vw, p, zoff)) {
+        mbar_wait(EMPTY(r.idx), r.phase ^ 1, 1);
+        const uint32_t sdy = smem_u32(smem + r.idx * p.stage_bytes);
+        mbar_arrive_expect_tx(LAND(r.idx), stage_tx);
+        tma_load_5d(sdy, &p.tm_dy, LAND(r.idx), 0, c.w0(), c.h0(), co0 / 8, c.b * p.D + c.d);
+        tma_load_5d(sdy + (uint32_t)p.dy_bytes, &p.tm_x, LAND(r.idx), 0, c.w0() - pw, c.h0() - ph, ci0 / 8, c.b * p.D + c.din);
+        r.advance();
+      }
+    }
+    return;
+  }
+  const int cpv_a = p.NTC / 8;
+  const int vstep_a = kLoadThreads / cpv_a;
+  const bool act_a = lt < vstep_a * cpv_a;
+  const int c8_a = lt % cpv_a, v0_a = lt / cpv_a;
+  const int sh_a = vstep_a / p.HALO_W, sw_a = vstep_a % p.HALO_W;
+  const int hh0 = v0_a / p.HALO_W, ww0 = v0_a % p.HALO_W;
+  const int act = p.act;
+  VtCursor ci, cd;
+  ci.init(vw, p, job.s, zoff); cd.init(vw, p, job.s, zoff);
+  Ring ri, rd; ri.init(p.NS); rd.init(p.NS);
+  int ahead = 0;
+  float sc[8], sf[8];
+  int norm_b = -1;
+  while (cd.valid(p)) {
+    if (lt == 0) {                 // run ahead as far as the ring has free slots; block only when nothing is in flight
+      while (ci.valid(p) && ahead < p.NS) {
+        if (!mbar_test_wait(EMPTY(ri.idx), ri.phase ^ 1)) { if (ahead > 0) break; mbar_wait(EMPTY(ri.idx), ri.phase ^ 1, 1); }
+        const uint32_t sdy = smem_u32(smem + ri.idx * p.stage_bytes);
+        mbar_arrive_expect_tx(LAND(ri.idx), stage_tx);
+        tma_load_5d(sdy, &p.tm_dy, LAND(ri.idx), 0, ci.w0(), ci.h0(), co0 / 8, ci.b * p.D + ci.d);
+        tma_load_5d(sdy + (uint32_t)p.dy_bytes, &p.tm_x, LAND(ri.idx), 0, ci.w0() - pw, ci.h0() - ph, ci0 / 8, ci.b * p.D + ci.din);
+        ri.advance(); ci.next(vw, p, zoff); ++ahead;
+      }
+    }
+    mbar_wait(LAND(rd.idx), rd.phase, 7);
+    if (act_a) {
+      if (cd.b != norm_b) {
+        norm_b = cd.b;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 mr = s_norm[cd.b * p.NTC + c8_a * 8 + j];
+          sc[j] = mr.y; sf[j] = -mr.x * mr.y;
+        }
+      }
+      uint8_t* sp = smem + rd.idx * p.stage_bytes + p.dy_bytes + c8_a * p.a_plane;
+      int hh = hh0, ww = ww0;
+#pragma unroll 2
+      for (int v = v0_a; v < p.nvox_h; v += vstep_a) {
+        const int h = cd.h0() - ph + hh, w = cd.w0() - pw + ww;
+        if ((unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W) {      // zero-filled padding voxels stay zero
+          uint4 raw = *reinterpret_cast<const uint4*>(sp + v * 16);
+          __half2* hv = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f = __half22float2(hv[j]);
+            f.x = act_apply(fmaf(f.x, sc[2 * j], sf[2 * j]), act); f.y = act_apply(fmaf(f.y, sc[2 * j + 1], sf[2 * j + 1]), act);
+            hv[j] = __floats2half2_rn(f.x, f.y);
+          }
+          *reinterpret_cast<uint4*>(sp + v * 16) = raw;
+        }
+        hh += sh_a; ww += sw_a;
+        if (ww >= p.HALO_W) { ww -= p.HALO_W; ++hh; }
+      }
+    }
+    fence_proxy_async();
+    mbar_arrive(FULL(rd.idx));
+    rd.advance(); cd.next(vw, p, zoff);
+    if (lt == 0) --ahead;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -219,13 +313,15 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   const uint32_t DONE = bar0 + 8u * (uint32_t)(2 * p.NS);
   auto A_READY = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.NS + 1 + i); };     // TS mode: dy^T tile i sits in TMEM
   auto A_FREE = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.NS + 3 + i); };      //          the MMAs reading it retired
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(bars + 2 * p.NS + 5);
+  auto LAND = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.NS + 5 + i); };         // TMA mode: the stage's boxes have landed
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(bars + 3 * p.NS + 5);
   float2* s_norm = reinterpret_cast<float2*>(smem + p.smem_norm_off);     // [B][NTC] {mean, rstd} of this job's channels
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.NS; ++i) { mbar_init(FULL(i), kLoadThreads); mbar_init(EMPTY(i), 1); }
     mbar_init(DONE, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(A_READY(i), kEpiWarps * 32); mbar_init(A_FREE(i), 1); }
+    for (int i = 0; i < p.NS; ++i) mbar_init(LAND(i), 1);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), (uint32_t)p.tmem_cols);
@@ -245,7 +341,8 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
 
   if (warp >= kLoadWarp0 && warp < kMmaWarp) {
     // =========================== LOADERS ===========================
-    if (p.prefetch >= 3) wg_loader<3>(p, job, smem, s_norm, bar0);
+    if (p.use_tma) wg_loader_tma(p, job, smem, s_norm, bar0);
+    else if (p.prefetch >= 3) wg_loader<3>(p, job, smem, s_norm, bar0);
     else if (p.prefetch == 2) wg_loader<2>(p, job, smem, s_norm, bar0);
     else wg_loader<1>(p, job, smem, s_norm, bar0);
   } else if (warp == kMmaWarp) {
@@ -267,12 +364,14 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
       VtWalk vw; vw.init(p);
       VtCursor c; c.init(vw, p, job.s, zoff);
       const int ts = p.ts;
+      // operands ready: FULL (published by the loaders) or, for raw operands staged by TMA, the TMA's own barrier
+      const uint32_t ready0 = (p.use_tma && !(p.x_stats || p.act)) ? LAND(0) : FULL(0);
       const uint32_t idesc_ts = (1u << 4) | (1u << 16) | ((uint32_t)(p.NTC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const int gmax = p.gbase + (p.grem ? 1 : 0);
       const uint32_t tmem_a0 = tmem_u + (uint32_t)(gmax * NTC);       // two 64-column dy^T buffers behind the accumulators
       int it = 0;
       for (; c.valid(p); c.next(vw, p, zoff), ++it) {
-        mbar_wait_nocall(FULL(idx), phase);
+        mbar_wait_nocall(ready0 + 8u * (uint32_t)idx, phase);
         if (ts) mbar_wait_nocall(A_READY(it & 1), (uint32_t)((it >> 1) & 1));
         tc_fence_after();
         const uint64_t da0 = dy_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16);
@@ -326,7 +425,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
       const uint8_t* lane_base = smem + (col >> 3) * p.dy_plane + (col & 7) * 2;
       int idx = 0; uint32_t phase = 0; int it = 0;
       for (; c.valid(p); c.next(vw, p, zoff), ++it) {
-        mbar_wait(FULL(idx), phase, 4);
+        mbar_wait(p.use_tma ? LAND(idx) : FULL(idx), phase, 4);       // dy is never transformed: landed is enough
         mbar_wait(A_FREE(it & 1), (uint32_t)(((it >> 1) & 1) ^ 1), 5);
         if (live) {
           tc_fence_after();
@@ -401,8 +500,9 @@ bool fill_params(const WgradArgs& a, WgParams& p) {
   p.gbase = taps_hw / p.ngroups; p.grem = taps_hw % p.ngroups;
   p.HALO_H = TH + a.kh - 1; p.HALO_W = TW + a.kw - 1; p.nvox_h = p.HALO_H * p.HALO_W;
   int slots = p.nvox_h; if ((slots & 1) == 0) ++slots;
-  p.a_plane = slots * 16;
-  p.dy_plane = (TH * TW + 1) * 16;
+  p.use_tma = getenv("B200SEG_WGRAD_NO_TMA") ? 0 : 1;      // (dense planes: a TMA box is written contiguously)
+  p.a_plane = p.use_tma ? p.nvox_h * 16 : slots * 16;
+  p.dy_plane = p.use_tma ? TH * TW * 16 : (TH * TW + 1) * 16;
   p.a_bytes = (p.NTC / 8) * p.a_plane; p.a_bytes = (p.a_bytes + 127) / 128 * 128;
   // only the real output-channel planes of the widest M tile are staged; the descriptor's 16-plane footprint beyond
   // them falls on the `a` tile / the next stage / the tail slack (allocated below), whose values feed rows never read
@@ -428,7 +528,7 @@ bool fill_params(const WgradArgs& a, WgParams& p) {
   p.tmem_cols = pow2;
   int off = p.NS * p.stage_bytes + 16 * p.dy_plane;       // + slack for the 16-plane descriptor footprint
   off = (off + 15) / 16 * 16;
-  p.smem_bar_off = off; off += (2 * p.NS + 6) * 8 + 16;
+  p.smem_bar_off = off; off += (3 * p.NS + 6) * 8 + 16;
   off = (off + 15) / 16 * 16;
   p.smem_norm_off = off;
   return true;
@@ -458,6 +558,19 @@ int conv3d_wgrad_tc(const WgradArgs& a, int dtype, void* /*workspace*/, size_t /
   p.x_stats = a.x_stats; p.eps = a.eps; p.act = a.act;
   p.dy = reinterpret_cast<const __half*>(a.dy); p.dy_ld = a.dy_ld; p.dy_coff = a.dy_coff;
   p.dw = a.dw;
+  if (p.use_tma) {
+    const int co_planes = (a.Cout < MT ? a.Cout : MT) / 8;
+    if (!b200seg_make_act_tmap(&p.tm_dy, a.dy, a.dy_ld, a.dy_coff, a.Cout, a.B * a.D, a.H, a.W, TW, TH, co_planes) ||
+        !b200seg_make_act_tmap(&p.tm_x, a.x, a.x_ld, a.x_coff, a.Cin, a.B * a.D, a.H, a.W, p.HALO_W, p.HALO_H, p.NTC / 8)) {
+      WgradArgs a2 = a;                       // tensor maps unavailable: fall back to the cp.async staging layout
+      setenv("B200SEG_WGRAD_NO_TMA", "1", 1);
+      fill_params(a2, p);
+      p.x = reinterpret_cast<const __half*>(a.x); p.x_ld = a.x_ld; p.x_coff = a.x_coff;
+      p.x_stats = a.x_stats; p.eps = a.eps; p.act = a.act;
+      p.dy = reinterpret_cast<const __half*>(a.dy); p.dy_ld = a.dy_ld; p.dy_coff = a.dy_coff;
+      p.dw = a.dw;
+    }
+  }
   const int64_t jobs = (int64_t)p.co_tiles * p.ci_tiles * a.kd * p.ngroups;
   const int smem_bytes = p.smem_norm_off + a.B * p.NTC * 8 + 64;
   static thread_local bool attr_set = false;

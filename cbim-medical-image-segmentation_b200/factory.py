@@ -11,6 +11,12 @@ def get_model(args, pretrain=False):
                 raise ValueError('No pretrain model available')   # model/utils.py:77-78
             return UNet(args.in_chan, args.base_chan, num_classes=args.classes, scale=args.down_scale,
                         norm=args.norm, kernel_size=args.kernel_size, block=args.block)
+        if args.model == 'unet++':
+            from .unetpp import UNetPlusPlus
+            if pretrain:
+                raise ValueError('No pretrain model available')   # model/utils.py:14-17
+            return UNetPlusPlus(args.in_chan, args.base_chan, num_classes=args.classes, scale=args.down_scale,
+                                norm=args.norm, kernel_size=args.kernel_size, block=args.block)   # :87
         if args.model == 'medformer':
             from .medformer import MedFormer
             if pretrain:

@@ -397,6 +397,24 @@ int b200seg_adamw_ema_step(const int64_t* table_dev, const int64_t* chunks_dev, 
                            float ema_alpha, float* step_dev, const float* scale,
                            const float* found_inf, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Evaluation consumers of net(x).
+ * softmax_accumulate: sliding-window inference, inference/inference3d.py:77-89:
+ *   prob[b][c][d0+d][h0+h][w0+w] += softmax_c(logits[b*sb + v*sv + c*sc]),
+ *   counter[b][..] += 1 for the window's wd x wh x ww voxels; prob fp32
+ *   [B][C][D][H][W], counter fp32 [B][D][H][W].
+ * normalize_argmax: prob /= counter (:91); label (nullable, uint8 [B][V]) = argmax_c.
+ * dice_metric: metric/utils.py:62-82, out uint64 [C][2] += {|pred==c & target==c|,
+ *   |pred==c| + |target==c|}; label maps uint8 (bytes = 1) or int64 (bytes = 8).
+ * ------------------------------------------------------------------------- */
+int b200seg_softmax_accumulate(const void* logits, int dtype, int64_t sb, int64_t sv, int64_t sc,
+                               float* prob, float* counter, int B, int C, int wd, int wh, int ww,
+                               int D, int H, int W, int d0, int h0, int w0, void* stream);
+int b200seg_normalize_argmax(float* prob, const float* counter, uint8_t* label, int B, int C,
+                             int64_t V, void* stream);
+int b200seg_dice_metric(const void* pred, int pred_bytes, const void* target, int target_bytes,
+                        int64_t N, int C, unsigned long long* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

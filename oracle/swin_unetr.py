@@ -72,7 +72,7 @@ def basic_layer(sd, pre, x, depth, heads, window_size):
     ws, ss = so.get_window_size((d, h, w), window_size, shift)
     x = x.permute(0, 2, 3, 4, 1)
     dp, hp, wp = [-(-s // k) * k for s, k in zip((d, h, w), ws)]
-    mask = so.compute_mask([dp, hp, wp], ws, ss).to(x.dtype) if any(s > 0 for s in ss) else None
+    mask = so.compute_mask([dp, hp, wp], ws, ss).to(device=x.device, dtype=x.dtype) if any(s > 0 for s in ss) else None
     for i in range(depth):
         x = swin_block(sd, "%sblocks.%d." % (pre, i), x, heads, window_size, (0, 0, 0) if i % 2 == 0 else shift, mask)
     x = x.reshape(b, d, h, w, -1)

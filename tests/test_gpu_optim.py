@@ -30,6 +30,8 @@ def test_fused_adamw_ema_matches_torch(amp):
         grads = [torch.randn_like(p) * 0.1 for p in net]
         if amp and it == 2:
             grads[1][17] = float("inf")                  # an overflow step
+        if amp:
+            scaler.scale(torch.zeros(1, device="cuda"))      # lazily creates the scaler's device-side scale tensor
         scale = scaler.get_scale() if amp else 1.0
         for p, r, g in zip(net, ref, grads):
             p.grad = (g * scale).clone()
