@@ -34,6 +34,7 @@
 #include "common.cuh"
 #include "conv_args.h"
 #include "tc_common.cuh"
+#include "tmap.h"
 #include <string.h>
 #include <stdlib.h>
 
@@ -69,7 +70,9 @@ struct TcParams {
   int tmem_cols, acc_stages;
   int w_resident;          // all weights of the layer live in shared memory for the CTA's lifetime (no B ring)
   int prefetch;            // A stages the loaders keep in flight (1..3, < SA)
+  int use_tma;             // halo tiles are staged by ONE tensor-TMA box per stage (else 16-byte cp.async copies)
   int smem_a_off, smem_b_off, smem_bar_off, smem_norm_off, smem_gnorm_off, smem_stat_off;
+  alignas(64) CUtensorMap tm_x;      // x as {8 ch, w, h, channel plane, b*D + d}
 };
 
 // Straight-line issue of one staged halo tile against RESIDENT weights: every tap and K step unrolled, descriptor low
@@ -263,6 +266,99 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
     cp_async_commit();
   }
   cp_async_wait<0>();
+}
+
+// ---- TMA staging (default): one elected loader thread issues ONE tensor-TMA box {8 ch, HALO_W, HALO_H, KC/8 planes}
+// per stage — the TMA unit writes the [plane][halo voxel][8 ch] image and zero-fills conv padding / ragged tiles —
+// running ahead as far as the ring has free slots.  Raw inputs (every data-gradient launch) are consumed by the MMA
+// warp straight off the TMA's barrier: no loader instruction touches the data.  When the input needs InstanceNorm /
+// activation the eight loader warps transform the landed tile in place (warp = 32 consecutive voxels of one plane:
+// conflict-free 16-byte shared-memory accesses) and publish A_FULL.
+__device__ __forceinline__ void loader_role_tma(const TcParams& p, uint8_t* smem, const float2* s_norm, uint32_t bar0) {
+  const ConvArgs& a = p.a;
+  const int lt = threadIdx.x - kLoadWarp0 * 32, lw = lt >> 5, lane = lt & 31;
+  const int ph = a.kh / 2, pw = a.kw / 2;
+  const bool xform = (a.x_stats != nullptr) || (a.act != 0);
+  const int act = a.act;
+  const uint32_t smem_a = smem_u32(smem + p.smem_a_off);
+  auto A_FULL = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  auto A_EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(p.SA + i); };
+  auto A_LAND = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.SA + 2 * p.SB + 4 + 1 + i); };
+  TileWalk tw; tw.init(p);
+  const uint32_t stage_tx = (uint32_t)((p.KC / 8) * p.nvox_h * 16);
+  auto issue = [&](const StageCursor& c, int slot) {
+    mbar_arrive_expect_tx(A_LAND(slot), stage_tx);
+    tma_load_5d(smem_a + (uint32_t)(slot * p.a_stage_bytes), &p.tm_x, A_LAND(slot), 0, c.ti.wi * TW - pw, c.ti.hi * TH - ph,
+                c.kc * (p.KC / 8), c.ti.b * a.D + c.din);
+  };
+  if (!xform) {
+    if (lt == 0) {
+      StageCursor c; c.init(tw, p);
+      Ring r; r.init(p.SA);
+      for (; c.valid(tw); c.next(tw, p)) {
+        mbar_wait(A_EMPTY(r.idx), r.phase ^ 1, 1);
+        issue(c, r.idx);
+        r.advance();
+      }
+    }
+    return;
+  }
+  // transform work items: (32-voxel group g, plane c8), item = c8 + cpv*g; warp lw takes items lw, lw+8, ...
+  const int cpv = p.KC / 8;
+  const int nitems = cpv * ((p.nvox_h + 31) / 32);
+  const bool fixed_plane = (8 % cpv) == 0;         // then every item of this warp is on plane lw % cpv
+  const uint32_t w_recip = 65536u / (uint32_t)p.HALO_W + 1u;      // v / HALO_W == (v * w_recip) >> 16 exactly for v < 192
+  StageCursor ci, cd;
+  ci.init(tw, p); cd.init(tw, p);
+  Ring ri, rd; ri.init(p.SA); rd.init(p.SA);
+  int ahead = 0;
+  float sc[8], sf[8];
+  int norm_key = -1;
+  while (cd.valid(tw)) {
+    if (lt == 0) {                 // run ahead as far as the ring has free slots; block only when nothing is in flight
+      while (ci.valid(tw) && ahead < p.SA) {
+        if (!mbar_test_wait(A_EMPTY(ri.idx), ri.phase ^ 1)) { if (ahead > 0) break; mbar_wait(A_EMPTY(ri.idx), ri.phase ^ 1, 1); }
+        issue(ci, ri.idx);
+        ri.advance(); ci.next(tw, p); ++ahead;
+      }
+    }
+    mbar_wait(A_LAND(rd.idx), rd.phase, 7);
+    const int hb = cd.ti.hi * TH - ph, wb = cd.ti.wi * TW - pw;
+    const bool interior = hb >= 0 && wb >= 0 && hb + p.HALO_H <= a.H && wb + p.HALO_W <= a.W;
+    uint8_t* stage = smem + p.smem_a_off + rd.idx * p.a_stage_bytes;
+    int c8 = lw % cpv, g = lw / cpv;
+    for (int item = lw; item < nitems; item += 8, c8 += 8) {
+      while (c8 >= cpv) { c8 -= cpv; ++g; }
+      const int key = (cd.ti.b * p.NKC + cd.kc) * 8 + c8;
+      if (!fixed_plane || key != norm_key) {
+        norm_key = key;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 mr = s_norm[cd.ti.b * a.Cin + cd.kc * p.KC + c8 * 8 + j];
+          sc[j] = mr.y; sf[j] = -mr.x * mr.y;
+        }
+      }
+      const uint32_t v = (uint32_t)(g * 32 + lane);
+      const uint32_t hr = (v * w_recip) >> 16, wc = v - hr * (uint32_t)p.HALO_W;
+      // zero-filled padding voxels are left untouched: the conv pads the NORMALISED activation
+      if ((int)v < p.nvox_h && (interior || (((unsigned)(hb + (int)hr) < (unsigned)a.H) && ((unsigned)(wb + (int)wc) < (unsigned)a.W)))) {
+        uint8_t* sp = stage + c8 * p.plane_stride + v * 16;
+        uint4 raw = *reinterpret_cast<const uint4*>(sp);
+        __half2* hv = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __half22float2(hv[j]);
+          f.x = act_apply(fmaf(f.x, sc[2 * j], sf[2 * j]), act); f.y = act_apply(fmaf(f.y, sc[2 * j + 1], sf[2 * j + 1]), act);
+          hv[j] = __floats2half2_rn(f.x, f.y);
+        }
+        *reinterpret_cast<uint4*>(sp) = raw;
+      }
+    }
+    fence_proxy_async();
+    mbar_arrive(A_FULL(rd.idx));
+    rd.advance(); cd.next(tw, p);
+    if (lt == 0) --ahead;
+  }
 }
 
 // ------------------------------------------------------------------ epilogue
@@ -508,6 +604,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   auto T_FULL = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.SA + 2 * p.SB + i); };
   auto T_EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.SA + 2 * p.SB + 2 + i); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(bars + 2 * p.SA + 2 * p.SB + 4);
+  auto A_LAND = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.SA + 2 * p.SB + 4 + 1 + i); };   // TMA mode: the stage's box has landed
 
   float2* s_norm = reinterpret_cast<float2*>(smem + p.smem_norm_off);   // [B][Cin] {mean, rstd}
   float2* s_gnorm = reinterpret_cast<float2*>(smem + p.smem_gnorm_off); // [B][Cout] {mean, rstd} of dgrad_x
@@ -517,7 +614,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.SA; ++i) { mbar_init(A_FULL(i), kLoadThreads); mbar_init(A_EMPTY(i), 1); }
+    for (int i = 0; i < p.SA; ++i) { mbar_init(A_FULL(i), kLoadThreads); mbar_init(A_EMPTY(i), 1); mbar_init(A_LAND(i), 1); }
     for (int i = 0; i < p.SB; ++i) { mbar_init(B_FULL(i), 1); mbar_init(B_EMPTY(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(T_FULL(i), 1); mbar_init(T_EMPTY(i), kEpiWarps * 32); }
     fence_barrier_init();
@@ -550,7 +647,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   if (warp >= kLoadWarp0 && warp < kWgtWarp) {
     // =========================== A LOADERS ===========================
     setmaxnreg_dec<kRegsLoad>();
-    if (p.prefetch >= 3) loader_role<3>(p, smem, s_norm, bar0);
+    if (p.use_tma) loader_role_tma(p, smem, s_norm, bar0);
+    else if (p.prefetch >= 3) loader_role<3>(p, smem, s_norm, bar0);
     else if (p.prefetch == 2) loader_role<2>(p, smem, s_norm, bar0);
     else loader_role<1>(p, smem, s_norm, bar0);
   } else if (warp >= kWgtWarp) {
@@ -609,6 +707,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const int resident = p.w_resident, acc_stages = p.acc_stages;
       const int taps_all = kd * taps_hw;
       const uint32_t res_step = (uint32_t)NKC * b_stage16;
+      // A stage ready: published by the loaders, or (raw input staged by TMA) the TMA's own transaction barrier
+      const uint32_t a_ready0 = (p.use_tma && !(a.x_stats || a.act)) ? A_LAND(0) : A_FULL(0);
       int it = 0;
       if (resident) { mbar_wait_nocall(B_FULL(0), 0); tc_fence_after(); }
       TileWalk tw; tw.init(p); TileIter ti; ti.init(tw);
@@ -624,7 +724,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           for (int zd = 0; zd < kd; ++zd) {
             const int din = tc.d + zd - pd;
             if ((unsigned)din >= (unsigned)D) continue;
-            mbar_wait_nocall(A_FULL(ra.idx), ra.phase);
+            mbar_wait_nocall(a_ready0 + 8u * (uint32_t)ra.idx, ra.phase);
             tc_fence_after();
             uint64_t da_row = a_tmpl + (uint64_t)(smem_a16 + (uint32_t)ra.idx * a_stage16);
             uint64_t db_res = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)((tc.ntile * taps_all + zd * taps_hw) * NKC + kc) * b_stage16);
@@ -733,7 +833,9 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   p.HALO_H = TH + a.kh - 1; p.HALO_W = TW + a.kw - 1;
   p.nvox_h = p.HALO_H * p.HALO_W;
   int slots = p.nvox_h; if ((slots & 1) == 0) slots += 1;     // odd number of 16-B slots -> conflict-free plane stride
-  p.plane_stride = slots * 16;
+  p.use_tma = (!getenv("B200SEG_CONV_NO_TMA") && p.nvox_h <= 192 &&
+               b200seg_make_act_tmap(&p.tm_x, a.x, a.x_ld, a.x_coff, a.Cin, a.B * a.D, a.H, a.W, p.HALO_W, p.HALO_H, p.KC / 8)) ? 1 : 0;
+  p.plane_stride = p.use_tma ? p.nvox_h * 16 : slots * 16;    // a TMA box is written densely
   p.a_stage_bytes = (p.KC / 8) * p.plane_stride;
   p.a_stage_bytes = (p.a_stage_bytes + 127) / 128 * 128;
   p.b_stage_bytes = p.KC * p.NT * 2;
@@ -771,7 +873,7 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   off = (off + 127) / 128 * 128;
   p.smem_b_off = off; off += b_region;
   off = (off + 15) / 16 * 16;
-  p.smem_bar_off = off; off += (2 * p.SA + 2 * p.SB + 4) * 8 + 16;
+  p.smem_bar_off = off; off += (3 * p.SA + 2 * p.SB + 5) * 8 + 16;
   off = (off + 15) / 16 * 16;
   p.smem_norm_off = off; off += norm_bytes;
   off = (off + 15) / 16 * 16;
