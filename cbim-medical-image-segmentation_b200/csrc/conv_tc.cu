@@ -217,7 +217,7 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
 #pragma unroll
   for (int i = 0; i < P; ++i) { if (ci.valid(tw)) issue(); cp_async_commit(); }
   while (cd.valid(tw)) {
-    cp_async_wait<P - 1>();                       // this thread's copies of the oldest stage have landed
+    { TC_PROF(11); cp_async_wait<P - 1>(); }      // this thread's copies of the oldest stage have landed
     if (xform && active) {
       const int key = cd.ti.b * p.NKC + cd.kc;
       if (key != norm_key) {
@@ -323,6 +323,7 @@ __device__ __forceinline__ void loader_role_tma(const TcParams& p, uint8_t* smem
       }
     }
     mbar_wait(A_LAND(rd.idx), rd.phase, 7);
+    TC_PROF(12);
     const int hb = cd.ti.hi * TH - ph, wb = cd.ti.wi * TW - pw;
     const bool interior = hb >= 0 && wb >= 0 && hb + p.HALO_H <= a.H && wb + p.HALO_W <= a.W;
     uint8_t* stage = smem + p.smem_a_off + rd.idx * p.a_stage_bytes;
@@ -530,8 +531,11 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, int warp, int l
       const float* bias = a.bias ? a.bias + t.co_base : nullptr;
       mbar_wait(T_FULL(acc), acc_phase, 6);
       tc_fence_after();
-      reg_chunk(e, half, trow, T_EMPTY(acc), t.valid, s00, s01, has_side, gn, bias, t.yp, as0, aq0);
-      if constexpr (CPW > 1) reg_chunk(e, half + 2, trow, T_EMPTY(acc), t.valid, s10, s11, has_side, gn, bias, t.yp, as1, aq1);
+      {
+        TC_PROF(13);
+        reg_chunk(e, half, trow, T_EMPTY(acc), t.valid, s00, s01, has_side, gn, bias, t.yp, as0, aq0);
+        if constexpr (CPW > 1) reg_chunk(e, half + 2, trow, T_EMPTY(acc), t.valid, s10, s11, has_side, gn, bias, t.yp, as1, aq1);
+      }
       if (!own0) {                              // a warp that owns no chunk of this tile (NT == 16) still has to release it
         tc_fence_before();
         mbar_arrive(T_EMPTY(acc));
@@ -587,6 +591,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, int warp, int l
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  TC_PROF(31);
   const ConvArgs& a = p.a;
   // canonical warp index: the shuffle makes it provably warp-uniform, so the role branches below are uniform
   // branches and the MMA warp's loop compiles to the uniform datapath (UIADD3 + UTCHMMA, no R2UR per operand)
@@ -710,13 +715,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       // A stage ready: published by the loaders, or (raw input staged by TMA) the TMA's own transaction barrier
       const uint32_t a_ready0 = (p.use_tma && !(a.x_stats || a.act)) ? A_LAND(0) : A_FULL(0);
       int it = 0;
-      if (resident) { mbar_wait_nocall(B_FULL(0), 0); tc_fence_after(); }
+      if (resident) { mbar_wait_nocall(B_FULL(0), 0, 10); tc_fence_after(); }
       TileWalk tw; tw.init(p); TileIter ti; ti.init(tw);
       for (; ti.valid(tw); ti.next(tw), ++it) {
         const TileCoord tc = ti.coord();
         const int acc = (acc_stages == 2) ? (it & 1) : 0;
         const uint32_t acc_phase = (acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
-        mbar_wait_nocall(T_EMPTY(acc), acc_phase ^ 1);
+        mbar_wait_nocall(T_EMPTY(acc), acc_phase ^ 1, 8);
         tc_fence_after();
         const uint32_t tmem_d = tmem_u + (uint32_t)(acc * NT);
         uint32_t accumulate = 0;
@@ -724,7 +729,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
           for (int zd = 0; zd < kd; ++zd) {
             const int din = tc.d + zd - pd;
             if ((unsigned)din >= (unsigned)D) continue;
-            mbar_wait_nocall(a_ready0 + 8u * (uint32_t)ra.idx, ra.phase);
+            mbar_wait_nocall(a_ready0 + 8u * (uint32_t)ra.idx, ra.phase, 9);
             tc_fence_after();
             uint64_t da_row = a_tmpl + (uint64_t)(smem_a16 + (uint32_t)ra.idx * a_stage16);
             uint64_t db_res = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)((tc.ntile * taps_all + zd * taps_hw) * NKC + kc) * b_stage16);
@@ -748,7 +753,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                     db = db_res;
                     db_res += (uint64_t)res_step;
                   } else {
-                    mbar_wait_nocall(B_FULL(rb.idx), rb.phase);
+                    mbar_wait_nocall(B_FULL(rb.idx), rb.phase, 10);
                     tc_fence_after();
                     db = b_tmpl + (uint64_t)(smem_b16 + (uint32_t)rb.idx * b_stage16);
                   }
@@ -802,6 +807,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 
 }  // namespace
 
+TC_PROF_ENTRY(b200seg_conv_tc_prof)
+
 bool conv3d_tc_shape_ok(int Cin, int Cout, int kd, int kh, int kw, int dtype) {
   if (dtype != B200SEG_F16) return false;
   if (tc_pick_nt(Cout) == 0 || tc_pick_kc(Cin) == 0) return false;
@@ -833,7 +840,11 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   p.HALO_H = TH + a.kh - 1; p.HALO_W = TW + a.kw - 1;
   p.nvox_h = p.HALO_H * p.HALO_W;
   int slots = p.nvox_h; if ((slots & 1) == 0) slots += 1;     // odd number of 16-B slots -> conflict-free plane stride
-  p.use_tma = (!getenv("B200SEG_CONV_NO_TMA") && p.nvox_h <= 192 &&
+  // measured (profiles/r2_layer_times.txt): raw inputs (every data-gradient launch) gain 5-25 % from the TMA path; inputs
+  // that need the in-place transform are faster with per-thread cp.async copies (each thread transforms exactly the
+  // chunks it copied, no second barrier round) — so those keep cp.async unless B200SEG_CONV_TMA_ALL is set
+  const bool raw_input = !a.x_stats && a.act == 0;
+  p.use_tma = (!getenv("B200SEG_CONV_NO_TMA") && (raw_input || getenv("B200SEG_CONV_TMA_ALL")) && p.nvox_h <= 192 &&
                b200seg_make_act_tmap(&p.tm_x, a.x, a.x_ld, a.x_coff, a.Cin, a.B * a.D, a.H, a.W, p.HALO_W, p.HALO_H, p.KC / 8)) ? 1 : 0;
   p.plane_stride = p.use_tma ? p.nvox_h * 16 : slots * 16;    // a TMA box is written densely
   p.a_stage_bytes = (p.KC / 8) * p.plane_stride;
@@ -887,6 +898,7 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
     B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  tc_apply_env();
   conv_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(p);
   B200_CHECK_LAUNCH("conv_tc_kernel");
   return B200SEG_OK;

@@ -4,11 +4,51 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace tc {
 
 constexpr long long kWaitTimeoutCycles = 4000000000ll;   // ~2 s at 1.9 GHz: a protocol bug traps, it never hangs the GPU
 constexpr uint32_t kSuspendNs = 20000;         // suspend-time hint of a blocked try_wait (the thread is woken on completion)
+// per-TU copy of the hint the kernels actually pass (tuning knob: env B200SEG_SUSPEND_NS, read once by tc_apply_env())
+__constant__ uint32_t c_suspend_ns = kSuspendNs;
+
+// ---- role profiler (tools/tc_prof.py; compiled only into libb200seg_prof.so with -DB200SEG_TC_PROFILE) ----
+// Lane 0 of every warp adds the cycles it spends inside a TC_PROF(code) scope (and inside every mbar_wait, keyed by
+// the wait site's code) to a per-CTA row; slot 31 = kernel lifetime of thread 0, slots 32+code = scope entry counts.
+#ifdef B200SEG_TC_PROFILE
+constexpr int kProfSlots = 64, kProfRows = 160;
+__device__ unsigned long long g_tc_prof[kProfRows * kProfSlots];
+struct ProfScope {
+  int code; long long t0;
+  __device__ __forceinline__ explicit ProfScope(int c) { code = c; t0 = clock64(); }
+  __device__ __forceinline__ ~ProfScope() {
+    if ((threadIdx.x & 31) == 0 && blockIdx.x < kProfRows) {
+      atomicAdd(&g_tc_prof[blockIdx.x * kProfSlots + (code & 31)], (unsigned long long)(clock64() - t0));
+      atomicAdd(&g_tc_prof[blockIdx.x * kProfSlots + 32 + (code & 31)], 1ull);
+    }
+  }
+};
+#define TC_PROF(code) ProfScope prof_scope_##code(code)
+#define TC_PROF_ENTRY(name) \
+  extern "C" int name(unsigned long long* out, int reset) { \
+    static unsigned long long h[kProfRows * kProfSlots]; \
+    if (cudaMemcpyFromSymbol(h, g_tc_prof, sizeof(h)) != cudaSuccess) return -1; \
+    for (int i = 0; i < kProfSlots; ++i) { out[i] = 0; for (int r = 0; r < kProfRows; ++r) out[i] += h[r * kProfSlots + i]; } \
+    if (reset) { memset(h, 0, sizeof(h)); cudaMemcpyToSymbol(g_tc_prof, h, sizeof(h)); } \
+    return 0; }
+#else
+#define TC_PROF(code)
+#define TC_PROF_ENTRY(name)
+#endif
+
+inline void tc_apply_env() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  if (const char* e = getenv("B200SEG_SUSPEND_NS")) { const uint32_t v = (uint32_t)atoi(e); cudaMemcpyToSymbol(c_suspend_ns, &v, sizeof(v)); }
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -27,7 +67,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity), "r"(kSuspendNs) : "memory");
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(c_suspend_ns) : "memory");
   return ok != 0;
 }
 // non-blocking probe (no suspend): has the phase with this parity completed?
@@ -46,6 +86,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
 // MMA issue loop pushes the loop off the uniform datapath.  `code` only documents the wait site.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
   (void)code;
+  TC_PROF(code);
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
@@ -54,7 +95,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int cod
 }
 // (kept as a separate name for the MMA warp's waits: with a call on the slow path the compiler keeps the loop-carried
 // descriptors in vector registers and every tcgen05.mma needs five R2UR.BROADCASTs, ~250 cycles per MMA measured)
-__device__ __forceinline__ void mbar_wait_nocall(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity, 0); }
+__device__ __forceinline__ void mbar_wait_nocall(uint32_t bar, uint32_t parity, int code = 0) { mbar_wait(bar, parity, code); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -165,8 +165,9 @@ __device__ __forceinline__ void wg_loader(const WgParams& p, const Job& job, uin
 #pragma unroll
   for (int i = 0; i < P; ++i) { if (ci.valid(p)) issue(); cp_async_commit(); }
   while (cd.valid(p)) {
-    cp_async_wait<P - 1>();
+    { TC_PROF(11); cp_async_wait<P - 1>(); }
     if (xform && act_a) {
+      TC_PROF(12);
       uint8_t* sp = smem + rd.idx * p.stage_bytes + p.dy_bytes + c8_a * p.a_plane;
       float sc[8], sf[8];                          // x*sc + sf == (x - mean) * rstd
 #pragma unroll
@@ -198,7 +199,7 @@ __device__ __forceinline__ void wg_loader(const WgParams& p, const Job& job, uin
     fence_proxy_async();
     mbar_arrive(FULL(rd.idx));
     rd.advance(); cd.next(vw, p, zoff);
-    if (ci.valid(p)) issue();
+    if (ci.valid(p)) { TC_PROF(15); issue(); }
     cp_async_commit();
   }
   cp_async_wait<0>();
@@ -297,6 +298,7 @@ __device__ __forceinline__ void wg_loader_tma(const WgParams& p, const Job& job,
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  TC_PROF(31);
   // canonical warp index: the shuffle makes it provably warp-uniform, so the role branches below are uniform
   // branches and the MMA warp's loop compiles to the uniform datapath (UIADD3 + UTCHMMA, no R2UR per operand)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -371,8 +373,8 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
       const uint32_t tmem_a0 = tmem_u + (uint32_t)(gmax * NTC);       // two 64-column dy^T buffers behind the accumulators
       int it = 0;
       for (; c.valid(p); c.next(vw, p, zoff), ++it) {
-        mbar_wait_nocall(ready0 + 8u * (uint32_t)idx, phase);
-        if (ts) mbar_wait_nocall(A_READY(it & 1), (uint32_t)((it >> 1) & 1));
+        mbar_wait_nocall(ready0 + 8u * (uint32_t)idx, phase, 9);
+        if (ts) mbar_wait_nocall(A_READY(it & 1), (uint32_t)((it >> 1) & 1), 10);
         tc_fence_after();
         const uint64_t da0 = dy_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16);
         uint64_t db_tap = a_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16 + dy16 + (uint32_t)(zh0 * HALO_W + zw0));
@@ -428,6 +430,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
         mbar_wait(p.use_tma ? LAND(idx) : FULL(idx), phase, 4);       // dy is never transformed: landed is enough
         mbar_wait(A_FREE(it & 1), (uint32_t)(((it >> 1) & 1) ^ 1), 5);
         if (live) {
+          TC_PROF(16);
           tc_fence_after();
           const uint8_t* src = lane_base + idx * p.stage_bytes;
           const uint32_t dst = tmem_a0 + (uint32_t)((it & 1) * 64);
@@ -536,6 +539,8 @@ bool fill_params(const WgradArgs& a, WgParams& p) {
 
 }  // namespace
 
+TC_PROF_ENTRY(b200seg_wgrad_tc_prof)
+
 bool conv3d_wgrad_tc_supported(const WgradArgs& a, int dtype) {
   if (dtype != B200SEG_F16) return false;
   if (a.kd > 3 || a.kh > 3 || a.kw > 3) return false;
@@ -579,6 +584,7 @@ int conv3d_wgrad_tc(const WgradArgs& a, int dtype, void* /*workspace*/, size_t /
     attr_set = true;
   }
   const int grid = (int)(jobs * p.S);
+  tc_apply_env();
   wgrad_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(p);
   B200_CHECK_LAUNCH("wgrad_tc_kernel");
   return B200SEG_OK;

@@ -29,5 +29,7 @@ def test_workload_table_is_consistent():
         assert len(wl[3]) == wl[2], name                       # one CE weight per class
         if bench.is_medformer(wl):
             assert wl[0]["aux_loss"] and bench.metric_of(wl) == bench.METRIC_MEDFORMER
+        elif wl[0] == "swin":
+            assert wl[1] == 48 and bench.metric_of(wl) == bench.METRIC_SWIN     # feature_size of config/*/swin_unetr_3d.yaml
         else:
             assert len(wl[0]) == 4 and len(wl[1]) == 5, name   # 4 scales, 5 kernel sizes (unet.py:35-45)
