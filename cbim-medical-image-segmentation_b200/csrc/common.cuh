@@ -69,6 +69,14 @@ template <> __device__ __forceinline__ void st8<__half>(__half* p, const float (
 __device__ __forceinline__ float act_apply(float h, int act) {
   return act == B200SEG_ACT_RELU ? fmaxf(h, 0.f) : (act == B200SEG_ACT_LRELU ? (h > 0.f ? h : B200SEG_LRELU_SLOPE * h) : h);
 }
+// Branch-free forms for unrolled per-element loops (a run-time `act` switch inside such a loop compiles to uniform
+// branches per ELEMENT, which serialises the elements' dependency chains — measured 1800 vs ~600 cycles per 16-column
+// epilogue chunk): every supported activation is  h > 0 ? h : slope * h  with slope = 0 (ReLU), 0.01 (LeakyReLU), 1 (none).
+__host__ __device__ __forceinline__ float act_slope(int act) {
+  return act == B200SEG_ACT_RELU ? 0.f : (act == B200SEG_ACT_LRELU ? B200SEG_LRELU_SLOPE : 1.f);
+}
+__device__ __forceinline__ float act_apply_s(float h, float slope) { return h > 0.f ? h : slope * h; }
+__device__ __forceinline__ float act_grad_s(float h, float slope) { return h > 0.f ? 1.f : slope; }
 // derivative of the activation at pre-activation h, as the factor the incoming gradient is multiplied with
 __device__ __forceinline__ float act_grad(float h, int act) {
   return act == B200SEG_ACT_RELU ? (h > 0.f ? 1.f : 0.f) : (act == B200SEG_ACT_LRELU ? (h > 0.f ? 1.f : B200SEG_LRELU_SLOPE) : 1.f);

@@ -160,7 +160,25 @@ struct StageCursor {
 // once per thread; per stage the work is one pointer add per chunk, and the bounds tests vanish for interior tiles.
 constexpr int kMaxChunks = 6;      // ceil(180 halo voxels / (256 threads / (KC/8) planes)) for KC <= 64
 
-template <int P>
+// normalise + activate three 8-channel chunks held in registers.  Straight-line on purpose: the three dependency chains
+// interleave (the bounds tests only predicate the shared-memory load and store around this)
+template <bool RELU>
+__device__ __forceinline__ void transform3(uint4 (&raw)[3], const float (&sc)[8], const float (&sf)[8], float slope) {
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    __half2* hv = reinterpret_cast<__half2*>(&raw[u]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __half22float2(hv[j]);
+      f.x = fmaf(f.x, sc[2 * j], sf[2 * j]); f.y = fmaf(f.y, sc[2 * j + 1], sf[2 * j + 1]);
+      if (RELU) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+      else { f.x = act_apply_s(f.x, slope); f.y = act_apply_s(f.y, slope); }
+      hv[j] = __floats2half2_rn(f.x, f.y);
+    }
+  }
+}
+
+template <int P, bool TMA>
 __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, const float2* s_norm, uint32_t bar0) {
   const ConvArgs& a = p.a;
   const int lt = threadIdx.x - kLoadWarp0 * 32;
@@ -176,6 +194,11 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
   uint8_t* smem_a_gen = smem + p.smem_a_off + c8 * p.plane_stride;
   auto A_FULL = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   auto A_EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(p.SA + i); };
+  auto A_LAND = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.SA + 2 * p.SB + 4 + 1 + i); };
+  // TMA mode: thread 0 stages the halo tile with ONE tensor-TMA box per stage; every thread then transforms exactly
+  // the chunks it would have copied (same table, same code) once the box has landed.  Nobody but thread 0 walks the
+  // issue cursor.
+  const uint32_t stage_tx = (uint32_t)(cpv * p.nvox_h * 16);
 
   // per-thread chunk table
   int rel[kMaxChunks];            // element offset of the chunk's voxel from the (possibly out-of-volume) tile origin
@@ -185,7 +208,7 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
     const int v = v0 + i * vstep;
     const bool have = active && v < p.nvox_h;
     const int hh = v / p.HALO_W, ww = v % p.HALO_W;
-    rel[i] = (hh * a.W + ww) * a.x_ld;
+    rel[i] = TMA ? 0 : (hh * a.W + ww) * a.x_ld;
     hw[i] = have ? ((uint32_t)hh << 16) | (uint32_t)ww : 0xffffffffu;
   }
 
@@ -197,6 +220,15 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
   Ring ri, rd; ri.init(p.SA); rd.init(p.SA);
 
   auto issue = [&]() {
+    if constexpr (TMA) {
+      if (lt == 0) {
+        mbar_wait(A_EMPTY(ri.idx), ri.phase ^ 1, 1);
+        mbar_arrive_expect_tx(A_LAND(ri.idx), stage_tx);
+        tma_load_5d(smem_u32(smem + p.smem_a_off) + (uint32_t)(ri.idx * p.a_stage_bytes), &p.tm_x, A_LAND(ri.idx), 0,
+                    ci.ti.wi * TW - pw, ci.ti.hi * TH - ph, ci.kc * cpv, ci.ti.b * a.D + ci.din);
+        ri.advance(); ci.next(tw, p);
+      }
+    } else {
     mbar_wait(A_EMPTY(ri.idx), ri.phase ^ 1, 1);
     const uint32_t dst = smem_a + (uint32_t)(ri.idx * p.a_stage_bytes) + (uint32_t)v0 * 16u;
     const int hb = ci.ti.hi * TH - ph, wb = ci.ti.wi * TW - pw;
@@ -210,15 +242,19 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
       }
     }
     ri.advance(); ci.next(tw, p);
+    }
   };
 
+  const float slope = act_slope(act);
   float sc[8], sf[8];                              // x*sc + sf == (x - mean) * rstd for this thread's 8 channels
   int norm_key = -1;                               // (b, kc) the constants belong to
 #pragma unroll
-  for (int i = 0; i < P; ++i) { if (ci.valid(tw)) issue(); cp_async_commit(); }
+  for (int i = 0; i < P; ++i) { if (ci.valid(tw)) issue(); if constexpr (!TMA) cp_async_commit(); }
   while (cd.valid(tw)) {
-    { TC_PROF(11); cp_async_wait<P - 1>(); }      // this thread's copies of the oldest stage have landed
+    if constexpr (TMA) mbar_wait(A_LAND(rd.idx), rd.phase, 7);
+    else { TC_PROF(11); cp_async_wait<P - 1>(); }      // this thread's copies of the oldest stage have landed
     if (xform && active) {
+      TC_PROF(12);
       const int key = cd.ti.b * p.NKC + cd.kc;
       if (key != norm_key) {
         norm_key = key;
@@ -242,46 +278,54 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
           const int i = i0 + u;
           ok[u] = i < nch && hw[i] != 0xffffffffu &&
                   (interior || (((unsigned)(hb + (int)(hw[i] >> 16)) < (unsigned)a.H) && ((unsigned)(wb + (int)(hw[i] & 0xffffu)) < (unsigned)a.W)));
+          if constexpr (TMA) raw[u] = make_uint4(0, 0, 0, 0);
           if (ok[u]) raw[u] = *reinterpret_cast<const uint4*>(sp + (i * vstep) * 16);
         }
+        if constexpr (TMA) {
+          if (act == B200SEG_ACT_RELU) transform3<true>(raw, sc, sf, slope);
+          else transform3<false>(raw, sc, sf, slope);
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          if (!ok[u]) continue;
-          __half2* hv = reinterpret_cast<__half2*>(&raw[u]);
+          for (int u = 0; u < 3; ++u)
+            if (ok[u]) *reinterpret_cast<uint4*>(sp + ((i0 + u) * vstep) * 16) = raw[u];
+        } else {      // 64 registers: one chunk at a time
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float2 f = __half22float2(hv[j]);
-            f.x = fmaf(f.x, sc[2 * j], sf[2 * j]); f.y = fmaf(f.y, sc[2 * j + 1], sf[2 * j + 1]);
-            if (act) { f.x = act_apply(f.x, act); f.y = act_apply(f.y, act); }
-            hv[j] = __floats2half2_rn(f.x, f.y);
+          for (int u = 0; u < 3; ++u) {
+            if (!ok[u]) continue;
+            __half2* hv = reinterpret_cast<__half2*>(&raw[u]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f = __half22float2(hv[j]);
+              f.x = fmaf(f.x, sc[2 * j], sf[2 * j]); f.y = fmaf(f.y, sc[2 * j + 1], sf[2 * j + 1]);
+              if (act) { f.x = act_apply(f.x, act); f.y = act_apply(f.y, act); }
+              hv[j] = __floats2half2_rn(f.x, f.y);
+            }
+            *reinterpret_cast<uint4*>(sp + ((i0 + u) * vstep) * 16) = raw[u];
           }
-          *reinterpret_cast<uint4*>(sp + ((i0 + u) * vstep) * 16) = raw[u];
         }
       }
     }
-    fence_proxy_async();            // generic-proxy / cp.async writes -> visible to the tensor core (async proxy)
-    mbar_arrive(A_FULL(rd.idx));
-    rd.advance(); cd.next(tw, p);
-    if (ci.valid(tw)) issue();
-    cp_async_commit();
+    {
+      TC_PROF(17);
+      fence_proxy_async();          // generic-proxy / cp.async writes -> visible to the tensor core (async proxy)
+      mbar_arrive(A_FULL(rd.idx));
+    }
+    { TC_PROF(18); rd.advance(); cd.next(tw, p); }
+    if (ci.valid(tw)) { TC_PROF(15); issue(); }
+    if constexpr (!TMA) cp_async_commit();
   }
-  cp_async_wait<0>();
+  if constexpr (!TMA) cp_async_wait<0>();
 }
 
-// ---- TMA staging (default): one elected loader thread issues ONE tensor-TMA box {8 ch, HALO_W, HALO_H, KC/8 planes}
-// per stage — the TMA unit writes the [plane][halo voxel][8 ch] image and zero-fills conv padding / ragged tiles —
-// running ahead as far as the ring has free slots.  Raw inputs (every data-gradient launch) are consumed by the MMA
-// warp straight off the TMA's barrier: no loader instruction touches the data.  When the input needs InstanceNorm /
-// activation the eight loader warps transform the landed tile in place (warp = 32 consecutive voxels of one plane:
-// conflict-free 16-byte shared-memory accesses) and publish A_FULL.
-__device__ __forceinline__ void loader_role_tma(const TcParams& p, uint8_t* smem, const float2* s_norm, uint32_t bar0) {
+// ---- TMA staging of RAW inputs (every data-gradient launch): one elected loader thread issues ONE tensor-TMA box
+// {8 ch, HALO_W, HALO_H, KC/8 planes} per stage — the TMA unit writes the [plane][halo voxel][8 ch] image and zero-fills
+// conv padding / ragged tiles — and the MMA warp consumes the stage straight off the TMA's transaction barrier: no
+// loader instruction touches the data.  (Inputs that need InstanceNorm / activation go through loader_role<P>, whose TMA
+// mode lands the same box and then transforms it in place with the cp.async path's per-thread chunk table.)
+__device__ __forceinline__ void loader_role_tma(const TcParams& p, uint8_t* smem, uint32_t bar0) {
   const ConvArgs& a = p.a;
-  const int lt = threadIdx.x - kLoadWarp0 * 32, lw = lt >> 5, lane = lt & 31;
+  const int lt = threadIdx.x - kLoadWarp0 * 32;
   const int ph = a.kh / 2, pw = a.kw / 2;
-  const bool xform = (a.x_stats != nullptr) || (a.act != 0);
-  const int act = a.act;
   const uint32_t smem_a = smem_u32(smem + p.smem_a_off);
-  auto A_FULL = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   auto A_EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(p.SA + i); };
   auto A_LAND = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.SA + 2 * p.SB + 4 + 1 + i); };
   TileWalk tw; tw.init(p);
@@ -291,74 +335,14 @@ __device__ __forceinline__ void loader_role_tma(const TcParams& p, uint8_t* smem
     tma_load_5d(smem_a + (uint32_t)(slot * p.a_stage_bytes), &p.tm_x, A_LAND(slot), 0, c.ti.wi * TW - pw, c.ti.hi * TH - ph,
                 c.kc * (p.KC / 8), c.ti.b * a.D + c.din);
   };
-  if (!xform) {
-    if (lt == 0) {
-      StageCursor c; c.init(tw, p);
-      Ring r; r.init(p.SA);
-      for (; c.valid(tw); c.next(tw, p)) {
-        mbar_wait(A_EMPTY(r.idx), r.phase ^ 1, 1);
-        issue(c, r.idx);
-        r.advance();
-      }
+  if (lt == 0) {
+    StageCursor c; c.init(tw, p);
+    Ring r; r.init(p.SA);
+    for (; c.valid(tw); c.next(tw, p)) {
+      mbar_wait(A_EMPTY(r.idx), r.phase ^ 1, 1);
+      issue(c, r.idx);
+      r.advance();
     }
-    return;
-  }
-  // transform work items: (32-voxel group g, plane c8), item = c8 + cpv*g; warp lw takes items lw, lw+8, ...
-  const int cpv = p.KC / 8;
-  const int nitems = cpv * ((p.nvox_h + 31) / 32);
-  const bool fixed_plane = (8 % cpv) == 0;         // then every item of this warp is on plane lw % cpv
-  const uint32_t w_recip = 65536u / (uint32_t)p.HALO_W + 1u;      // v / HALO_W == (v * w_recip) >> 16 exactly for v < 192
-  StageCursor ci, cd;
-  ci.init(tw, p); cd.init(tw, p);
-  Ring ri, rd; ri.init(p.SA); rd.init(p.SA);
-  int ahead = 0;
-  float sc[8], sf[8];
-  int norm_key = -1;
-  while (cd.valid(tw)) {
-    if (lt == 0) {                 // run ahead as far as the ring has free slots; block only when nothing is in flight
-      while (ci.valid(tw) && ahead < p.SA) {
-        if (!mbar_test_wait(A_EMPTY(ri.idx), ri.phase ^ 1)) { if (ahead > 0) break; mbar_wait(A_EMPTY(ri.idx), ri.phase ^ 1, 1); }
-        issue(ci, ri.idx);
-        ri.advance(); ci.next(tw, p); ++ahead;
-      }
-    }
-    mbar_wait(A_LAND(rd.idx), rd.phase, 7);
-    TC_PROF(12);
-    const int hb = cd.ti.hi * TH - ph, wb = cd.ti.wi * TW - pw;
-    const bool interior = hb >= 0 && wb >= 0 && hb + p.HALO_H <= a.H && wb + p.HALO_W <= a.W;
-    uint8_t* stage = smem + p.smem_a_off + rd.idx * p.a_stage_bytes;
-    int c8 = lw % cpv, g = lw / cpv;
-    for (int item = lw; item < nitems; item += 8, c8 += 8) {
-      while (c8 >= cpv) { c8 -= cpv; ++g; }
-      const int key = (cd.ti.b * p.NKC + cd.kc) * 8 + c8;
-      if (!fixed_plane || key != norm_key) {
-        norm_key = key;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 mr = s_norm[cd.ti.b * a.Cin + cd.kc * p.KC + c8 * 8 + j];
-          sc[j] = mr.y; sf[j] = -mr.x * mr.y;
-        }
-      }
-      const uint32_t v = (uint32_t)(g * 32 + lane);
-      const uint32_t hr = (v * w_recip) >> 16, wc = v - hr * (uint32_t)p.HALO_W;
-      // zero-filled padding voxels are left untouched: the conv pads the NORMALISED activation
-      if ((int)v < p.nvox_h && (interior || (((unsigned)(hb + (int)hr) < (unsigned)a.H) && ((unsigned)(wb + (int)wc) < (unsigned)a.W)))) {
-        uint8_t* sp = stage + c8 * p.plane_stride + v * 16;
-        uint4 raw = *reinterpret_cast<const uint4*>(sp);
-        __half2* hv = reinterpret_cast<__half2*>(&raw);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float2 f = __half22float2(hv[j]);
-          f.x = act_apply(fmaf(f.x, sc[2 * j], sf[2 * j]), act); f.y = act_apply(fmaf(f.y, sc[2 * j + 1], sf[2 * j + 1]), act);
-          hv[j] = __floats2half2_rn(f.x, f.y);
-        }
-        *reinterpret_cast<uint4*>(sp) = raw;
-      }
-    }
-    fence_proxy_async();
-    mbar_arrive(A_FULL(rd.idx));
-    rd.advance(); cd.next(tw, p);
-    if (lt == 0) --ahead;
   }
 }
 
@@ -390,11 +374,12 @@ __device__ __forceinline__ void epi_chunk(const ConvArgs& a, bool valid, bool dg
     }
   }
   if (dgrad) {
+    const float gslope = act_slope(a.g_act);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float2 mr = gnorm[j];
       const float hx = (sv[j] - mr.x) * mr.y;
-      float g = r[j] * act_grad(hx, a.g_act);
+      float g = r[j] * act_grad_s(hx, gslope);
       g = __half2float(__float2half_rn(g));
       r[j] = g; s2[j] = g * hx;
     }
@@ -410,6 +395,47 @@ __device__ __forceinline__ void epi_chunk(const ConvArgs& a, bool valid, bool dg
   }
   st8<__half>(yout, reinterpret_cast<const float(&)[8]>(r[0]));
   st8<__half>(yout + 8, reinterpret_cast<const float(&)[8]>(r[8]));
+}
+
+// Eight output columns of this thread's row on the register-statistics path: same arithmetic (and the same fp16 rounding
+// points) as epi_chunk, but the statistics are accumulated at once and nothing but the eight values is kept live —
+// two 16-column chunks per warp (NT = 64) need 64 accumulators, which leaves ~70 registers for everything else.
+__device__ __forceinline__ void epi_piece8(const ConvArgs& a, bool valid, bool dgrad, const uint32_t* v, const uint4& side, bool has_side,
+                                           const float2* gnorm, const float* bias, __half* yout, float gslope, bool want_stats,
+                                           float* as, float* aq) {
+  if (!valid) return;                                   // rows outside the volume: nothing stored, nothing counted
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(v[j]);
+  if (bias) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias)), b1 = __ldg(reinterpret_cast<const float4*>(bias) + 1);
+    r[0] += b0.x; r[1] += b0.y; r[2] += b0.z; r[3] += b0.w; r[4] += b1.x; r[5] += b1.y; r[6] += b1.z; r[7] += b1.w;
+  }
+  const __half2* hs = reinterpret_cast<const __half2*>(&side);
+  if (dgrad) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 mr = *reinterpret_cast<const float4*>(gnorm + 2 * j);      // {mean, rstd} of two channels
+      const float2 sv = __half22float2(hs[j]);
+      const float h0 = (sv.x - mr.x) * mr.y, h1 = (sv.y - mr.z) * mr.w;
+      const float g0 = __half2float(__float2half_rn(r[2 * j] * act_grad_s(h0, gslope)));
+      const float g1 = __half2float(__float2half_rn(r[2 * j + 1] * act_grad_s(h1, gslope)));
+      r[2 * j] = g0; r[2 * j + 1] = g1;
+      if (want_stats) { as[2 * j] += g0; as[2 * j + 1] += g1; aq[2 * j] = fmaf(g0, h0, aq[2 * j]); aq[2 * j + 1] = fmaf(g1, h1, aq[2 * j + 1]); }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float y0 = __half2float(__float2half_rn(r[2 * j])), y1 = __half2float(__float2half_rn(r[2 * j + 1]));
+      if (has_side) {
+        const float2 sv = __half22float2(hs[j]);
+        y0 = __half2float(__float2half_rn(y0 + sv.x)); y1 = __half2float(__float2half_rn(y1 + sv.y));
+      }
+      r[2 * j] = y0; r[2 * j + 1] = y1;
+      if (want_stats) { as[2 * j] += y0; as[2 * j + 1] += y1; aq[2 * j] = fmaf(y0, y0, aq[2 * j]); aq[2 * j + 1] = fmaf(y1, y1, aq[2 * j + 1]); }
+    }
+  }
+  st8<__half>(yout, r);
 }
 
 // REGSTATS: NT <= 64 (at most two chunks per warp); the InstanceNorm sums live in registers across all tiles.
@@ -436,19 +462,17 @@ __device__ __forceinline__ void reg_chunk(const EpiCtx& e, int c, uint32_t trow,
                                           float (&as)[16], float (&aq)[16]) {
   if (c >= e.nchunks) return;
   uint32_t v[16];
-  tmem_ld16(trow + (uint32_t)(16 * c), v);
-  tmem_ld_wait();
+  { TC_PROF(19); tmem_ld16(trow + (uint32_t)(16 * c), v); tmem_ld_wait(); }
   if (c + 2 >= e.nchunks) {       // last chunk of this warp is in registers: hand the TMEM buffer back now
     tc_fence_before();
     mbar_arrive(t_empty);
   }
-  float r[16], s2[16];
-  epi_chunk(e.p->a, valid, e.dgrad, v, sd0, sd1, has_side, !e.dgrad && has_side, gn + 16 * c, bias ? bias + 16 * c : nullptr,
-            yp + 16 * c, r, s2);
-  if (e.want_stats) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { as[j] += r[j]; aq[j] += s2[j]; }
-  }
+  const float gslope = act_slope(e.p->a.g_act);
+  epi_piece8(e.p->a, valid, e.dgrad, v, sd0, has_side, gn + 16 * c, bias ? bias + 16 * c : nullptr, yp + 16 * c, gslope, e.want_stats,
+             as, aq);
+  asm volatile("" ::: "memory");        // keep the two halves sequential (register pressure, see epi_piece8)
+  epi_piece8(e.p->a, valid, e.dgrad, v + 8, sd1, has_side, gn + 16 * c + 8, bias ? bias + 16 * c + 8 : nullptr, yp + 16 * c + 8, gslope,
+             e.want_stats, as + 8, aq + 8);
 }
 
 // Per-row addresses of one tile for this thread
@@ -515,6 +539,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, int warp, int l
       const uint4 s00 = n00, s01 = n01, s10 = n10, s11 = n11;
       const EpiTile t = cur;
       ti.next(tw);
+      TC_PROF(21);
       if (ti.valid(tw)) {                       // request the next tile's side input now
         cur = epi_tile(p, ti.coord(), hl, wl, dgrad);
         if (has_side && cur.valid) {
@@ -652,10 +677,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
   if (warp >= kLoadWarp0 && warp < kWgtWarp) {
     // =========================== A LOADERS ===========================
     setmaxnreg_dec<kRegsLoad>();
-    if (p.use_tma) loader_role_tma(p, smem, s_norm, bar0);
-    else if (p.prefetch >= 3) loader_role<3>(p, smem, s_norm, bar0);
-    else if (p.prefetch == 2) loader_role<2>(p, smem, s_norm, bar0);
-    else loader_role<1>(p, smem, s_norm, bar0);
+    if (p.use_tma && !(a.x_stats || a.act)) loader_role_tma(p, smem, bar0);
+    else if (p.use_tma) loader_role<3, true>(p, smem, s_norm, bar0);
+    else if (p.prefetch >= 3) loader_role<3, false>(p, smem, s_norm, bar0);
+    else loader_role<1, false>(p, smem, s_norm, bar0);
   } else if (warp >= kWgtWarp) {
     setmaxnreg_dec<kRegsMma>();
    if (warp == kWgtWarp) {
@@ -840,11 +865,11 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   p.HALO_H = TH + a.kh - 1; p.HALO_W = TW + a.kw - 1;
   p.nvox_h = p.HALO_H * p.HALO_W;
   int slots = p.nvox_h; if ((slots & 1) == 0) slots += 1;     // odd number of 16-B slots -> conflict-free plane stride
-  // measured (profiles/r2_layer_times.txt): raw inputs (every data-gradient launch) gain 5-25 % from the TMA path; inputs
-  // that need the in-place transform are faster with per-thread cp.async copies (each thread transforms exactly the
-  // chunks it copied, no second barrier round) — so those keep cp.async unless B200SEG_CONV_TMA_ALL is set
+  // measured (profiles/r2_layer_times*.txt): raw inputs (every data-gradient launch) gain 10-25 % from the TMA path; inputs
+  // that need the in-place transform gain 5-12 % while the whole Cin fits one K chunk (Cin <= 64) and LOSE 15-45 % beyond
+  // that (a {8 ch}-wide box moves 16 bytes per TMA request: the unit, not the SM, becomes the limit) — those keep cp.async.
   const bool raw_input = !a.x_stats && a.act == 0;
-  p.use_tma = (!getenv("B200SEG_CONV_NO_TMA") && (raw_input || getenv("B200SEG_CONV_TMA_ALL")) && p.nvox_h <= 192 &&
+  p.use_tma = (!getenv("B200SEG_CONV_NO_TMA") && (raw_input || a.Cin <= 64 || getenv("B200SEG_CONV_TMA_ALL")) && p.nvox_h <= 192 &&
                b200seg_make_act_tmap(&p.tm_x, a.x, a.x_ld, a.x_coff, a.Cin, a.B * a.D, a.H, a.W, p.HALO_W, p.HALO_H, p.KC / 8)) ? 1 : 0;
   p.plane_stride = p.use_tma ? p.nvox_h * 16 : slots * 16;    // a TMA box is written densely
   p.a_stage_bytes = (p.KC / 8) * p.plane_stride;
@@ -879,6 +904,7 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   }
   if (p.SA < 2) return B200SEG_EUNSUPPORTED;
   p.prefetch = p.SA - 1 < 3 ? p.SA - 1 : 3;
+  if (p.use_tma && !raw_input && p.SA < 4) p.use_tma = 0;      // the TMA + transform loader runs three stages ahead
   int off = 0;
   p.smem_a_off = off; off += p.SA * p.a_stage_bytes;
   off = (off + 127) / 128 * 128;

@@ -487,7 +487,7 @@ int pick_ntc(int Cin) {
   return 0;
 }
 
-bool fill_params(const WgradArgs& a, WgParams& p) {
+bool fill_params(const WgradArgs& a, WgParams& p, bool tma = false) {
   memset(&p, 0, sizeof(p));
   p.B = a.B; p.D = a.D; p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout; p.kd = a.kd; p.kh = a.kh; p.kw = a.kw;
   p.NTC = pick_ntc(a.Cin);
@@ -503,7 +503,7 @@ bool fill_params(const WgradArgs& a, WgParams& p) {
   p.gbase = taps_hw / p.ngroups; p.grem = taps_hw % p.ngroups;
   p.HALO_H = TH + a.kh - 1; p.HALO_W = TW + a.kw - 1; p.nvox_h = p.HALO_H * p.HALO_W;
   int slots = p.nvox_h; if ((slots & 1) == 0) ++slots;
-  p.use_tma = getenv("B200SEG_WGRAD_NO_TMA") ? 0 : 1;      // (dense planes: a TMA box is written contiguously)
+  p.use_tma = tma ? 1 : 0;                                     // (dense planes: a TMA box is written contiguously)
   p.a_plane = p.use_tma ? p.nvox_h * 16 : slots * 16;
   p.dy_plane = p.use_tma ? TH * TW * 16 : (TH * TW + 1) * 16;
   p.a_bytes = (p.NTC / 8) * p.a_plane; p.a_bytes = (p.a_bytes + 127) / 128 * 128;
@@ -558,7 +558,10 @@ size_t conv3d_wgrad_tc_workspace(const WgradArgs&) { return 0; }
 int conv3d_wgrad_tc(const WgradArgs& a, int dtype, void* /*workspace*/, size_t /*ws_bytes*/, cudaStream_t st) {
   if (!conv3d_wgrad_tc_supported(a, dtype)) return B200SEG_EUNSUPPORTED;
   WgParams p;
-  fill_params(a, p);
+  // tensor-TMA staging of both operands is opt-in (B200SEG_WGRAD_TMA=1): with 16-byte box rows the TMA unit is slower
+  // than 256 threads of cp.async on all but two layer shapes (profiles/r2_layer_times_wgrad_tma.txt)
+  const bool want_tma = getenv("B200SEG_WGRAD_TMA") != nullptr;
+  fill_params(a, p, want_tma);
   p.x = reinterpret_cast<const __half*>(a.x); p.x_ld = a.x_ld; p.x_coff = a.x_coff;
   p.x_stats = a.x_stats; p.eps = a.eps; p.act = a.act;
   p.dy = reinterpret_cast<const __half*>(a.dy); p.dy_ld = a.dy_ld; p.dy_coff = a.dy_coff;
@@ -567,9 +570,7 @@ int conv3d_wgrad_tc(const WgradArgs& a, int dtype, void* /*workspace*/, size_t /
     const int co_planes = (a.Cout < MT ? a.Cout : MT) / 8;
     if (!b200seg_make_act_tmap(&p.tm_dy, a.dy, a.dy_ld, a.dy_coff, a.Cout, a.B * a.D, a.H, a.W, TW, TH, co_planes) ||
         !b200seg_make_act_tmap(&p.tm_x, a.x, a.x_ld, a.x_coff, a.Cin, a.B * a.D, a.H, a.W, p.HALO_W, p.HALO_H, p.NTC / 8)) {
-      WgradArgs a2 = a;                       // tensor maps unavailable: fall back to the cp.async staging layout
-      setenv("B200SEG_WGRAD_NO_TMA", "1", 1);
-      fill_params(a2, p);
+      fill_params(a, p, false);               // tensor maps unavailable: fall back to the cp.async staging layout
       p.x = reinterpret_cast<const __half*>(a.x); p.x_ld = a.x_ld; p.x_coff = a.x_coff;
       p.x_stats = a.x_stats; p.eps = a.eps; p.act = a.act;
       p.dy = reinterpret_cast<const __half*>(a.dy); p.dy_ld = a.dy_ld; p.dy_coff = a.dy_coff;

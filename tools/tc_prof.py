@@ -15,7 +15,8 @@ LAYERS = [(32, 32, (1, 3, 3), (128, 128, 128)), (32, 32, (3, 3, 3), (128, 128, 1
           (384, 256, (3, 3, 3), (128, 32, 32))]
 CONV = {1: ("loader: wait A_EMPTY", 8), 2: ("weights warp: wait B_EMPTY", 1), 6: ("epilogue: wait T_FULL", 8), 7: ("loader: wait TMA landed", 8),
         8: ("mma: wait T_EMPTY", 1), 9: ("mma: wait A stage", 1), 10: ("mma: wait B stage", 1), 11: ("loader: cp.async wait", 8),
-        12: ("loader: transform (TMA mode)", 8), 13: ("epilogue: chunk body", 8), 31: ("lifetime (all warps)", 20)}
+        12: ("loader: transform", 8), 13: ("epilogue: chunk body", 8), 15: ("loader: issue next stage (incl. A_EMPTY wait)", 8),
+        17: ("loader: fence + arrive", 8), 19: ("epilogue: tcgen05.ld + wait", 8), 21: ("epilogue: whole tile after cursor step", 8), 18: ("loader: cursor advance", 8), 31: ("lifetime (all warps)", 20)}
 WG = {1: ("loader: wait EMPTY", 8), 3: ("epilogue: wait DONE", 4), 4: ("transposer: wait operand", 4), 5: ("transposer: wait A_FREE", 4),
       7: ("loader: wait TMA landed", 8), 9: ("mma: wait operands", 1), 10: ("mma: wait A_READY", 1), 11: ("loader: cp.async wait", 8),
       12: ("loader: transform", 8), 15: ("loader: issue next stage", 8), 16: ("transposer: smem->TMEM", 4), 31: ("lifetime (all warps)", 13)}
