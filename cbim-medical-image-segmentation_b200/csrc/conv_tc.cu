@@ -55,9 +55,10 @@ constexpr int kThreads = 20 * 32;   // 640: five complete warpgroups (setmaxnreg
                                     // warps 18-19 only take part in the block-wide barriers
 // Registers per thread after the role dispatch.  setmaxnreg trades registers inside the CTA's OWN pool — what the
 // launch allotted: 640 threads x 96 = 61440, not the SM's 65536 (an over-subscribed split makes setmaxnreg.inc spin
-// forever: measured the hard way) — so:  2 epilogue warpgroups x 144 + 2 loader warpgroups x 64 + {weights, MMA,
-// 2 idle} x 64 == 61440.
-constexpr int kRegsLaunch = 96, kRegsEpi = 144, kRegsLoad = 64, kRegsMma = 64;
+// forever: measured the hard way).  Split: 2 epilogue warpgroups x 136 (64 statistics accumulators at NT = 64) +
+// 2 loader warpgroups x 80 (three transform chains interleaved: with 64 the compiler serialised them, -15..25 % on the
+// Cin <= 64 forward layers) + {weights, MMA, 2 idle} x 40 (their loops live in uniform registers) = 60416.
+constexpr int kRegsLaunch = 96, kRegsEpi = 136, kRegsLoad = 80, kRegsMma = 40;
 static_assert(2 * 128 * kRegsEpi + 2 * 128 * kRegsLoad + 128 * kRegsMma <= kThreads * kRegsLaunch, "register split exceeds the CTA pool");
 
 struct TcParams {
@@ -71,8 +72,10 @@ struct TcParams {
   int w_resident;          // all weights of the layer live in shared memory for the CTA's lifetime (no B ring)
   int prefetch;            // A stages the loaders keep in flight (1..3, < SA)
   int use_tma;             // halo tiles are staged by ONE tensor-TMA box per stage (else 16-byte cp.async copies)
+  int row;                 // ROW image: one `pitch`-byte swizzled row per halo voxel (K-major SWIZZLE_64B/128B), TMA only
+  int pitch;               // bytes per row (KC * 2 = 64 or 128)
   int smem_a_off, smem_b_off, smem_bar_off, smem_norm_off, smem_gnorm_off, smem_stat_off;
-  alignas(64) CUtensorMap tm_x;      // x as {8 ch, w, h, channel plane, b*D + d}
+  alignas(64) CUtensorMap tm_x;      // x as {8 ch, w, h, channel plane, b*D + d}, or (row image) {channel, w, h, b*D + d}
 };
 
 // Straight-line issue of one staged halo tile against RESIDENT weights: every tap and K step unrolled, descriptor low
@@ -81,7 +84,7 @@ struct TcParams {
 template <int KS, int KH, int KW>
 __device__ __forceinline__ void issue_stage_resident(uint32_t tmem_d, uint64_t da_stage, uint64_t db_stage, uint32_t idesc,
                                                      uint32_t& accumulate, uint32_t a_kstep, uint32_t b_kstep,
-                                                     uint32_t halo_w, uint32_t b_tap_step, uint32_t elected) {
+                                                     uint32_t a_rowstep, uint32_t a_tapstep, uint32_t b_tap_step, uint32_t elected) {
   const uint32_t a_lo = (uint32_t)da_stage, a_hi = (uint32_t)(da_stage >> 32);
   const uint32_t b_lo = (uint32_t)db_stage, b_hi = (uint32_t)(db_stage >> 32);
 #pragma unroll
@@ -90,7 +93,7 @@ __device__ __forceinline__ void issue_stage_resident(uint32_t tmem_d, uint64_t d
     for (int zw = 0; zw < KW; ++zw) {
 #pragma unroll
       for (int j = 0; j < KS; ++j) {
-        const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)zh * halo_w + (uint32_t)zw + (uint32_t)j * a_kstep);
+        const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)zh * a_rowstep + (uint32_t)zw * a_tapstep + (uint32_t)j * a_kstep);
         const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(zh * KW + zw) * b_tap_step + (uint32_t)j * b_kstep);
         if (elected) umma_f16(tmem_d, da, db, idesc, accumulate);
         accumulate = 1;
@@ -208,7 +211,13 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
     const int v = v0 + i * vstep;
     const bool have = active && v < p.nvox_h;
     const int hh = v / p.HALO_W, ww = v % p.HALO_W;
-    rel[i] = TMA ? 0 : (hh * a.W + ww) * a.x_ld;
+    if constexpr (TMA) {
+      // byte offset of the chunk inside a stage: plane image [c8][v][8 ch], or row image (one pitch-byte row per voxel,
+      // 16-byte chunks XOR-swizzled with address bits 7.. exactly as the TMA unit wrote them; stages are 1024-aligned)
+      rel[i] = p.row ? v * p.pitch + ((c8 ^ (p.pitch == 128 ? (v & 7) : ((v >> 1) & 3))) << 4) : c8 * p.plane_stride + v * 16;
+    } else {
+      rel[i] = (hh * a.W + ww) * a.x_ld;
+    }
     hw[i] = have ? ((uint32_t)hh << 16) | (uint32_t)ww : 0xffffffffu;
   }
 
@@ -224,8 +233,9 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
       if (lt == 0) {
         mbar_wait(A_EMPTY(ri.idx), ri.phase ^ 1, 1);
         mbar_arrive_expect_tx(A_LAND(ri.idx), stage_tx);
-        tma_load_5d(smem_u32(smem + p.smem_a_off) + (uint32_t)(ri.idx * p.a_stage_bytes), &p.tm_x, A_LAND(ri.idx), 0,
-                    ci.ti.wi * TW - pw, ci.ti.hi * TH - ph, ci.kc * cpv, ci.ti.b * a.D + ci.din);
+        const uint32_t dst = smem_u32(smem + p.smem_a_off) + (uint32_t)(ri.idx * p.a_stage_bytes);
+        if (p.row) tma_load_4d(dst, &p.tm_x, A_LAND(ri.idx), ci.kc * p.KC, ci.ti.wi * TW - pw, ci.ti.hi * TH - ph, ci.ti.b * a.D + ci.din);
+        else tma_load_5d(dst, &p.tm_x, A_LAND(ri.idx), 0, ci.ti.wi * TW - pw, ci.ti.hi * TH - ph, ci.kc * cpv, ci.ti.b * a.D + ci.din);
         ri.advance(); ci.next(tw, p);
       }
     } else {
@@ -264,7 +274,8 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
           sc[j] = mr.y; sf[j] = -mr.x * mr.y;
         }
       }
-      uint8_t* sp = smem_a_gen + rd.idx * p.a_stage_bytes + v0 * 16;
+      uint8_t* sp = TMA ? smem + p.smem_a_off + rd.idx * p.a_stage_bytes : smem_a_gen + rd.idx * p.a_stage_bytes + v0 * 16;
+      auto chunk = [&](int i) { return TMA ? sp + rel[i] : sp + (i * vstep) * 16; };
       const int hb = cd.ti.hi * TH - ph, wb = cd.ti.wi * TW - pw;
       const bool interior = hb >= 0 && wb >= 0 && hb + p.HALO_H <= a.H && wb + p.HALO_W <= a.W;
       // two batches of three chunks: all loads of a batch are issued before the first use (ILP for the one loader
@@ -279,14 +290,14 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
           ok[u] = i < nch && hw[i] != 0xffffffffu &&
                   (interior || (((unsigned)(hb + (int)(hw[i] >> 16)) < (unsigned)a.H) && ((unsigned)(wb + (int)(hw[i] & 0xffffu)) < (unsigned)a.W)));
           if constexpr (TMA) raw[u] = make_uint4(0, 0, 0, 0);
-          if (ok[u]) raw[u] = *reinterpret_cast<const uint4*>(sp + (i * vstep) * 16);
+          if (ok[u]) raw[u] = *reinterpret_cast<const uint4*>(chunk(i));
         }
         if constexpr (TMA) {
           if (act == B200SEG_ACT_RELU) transform3<true>(raw, sc, sf, slope);
           else transform3<false>(raw, sc, sf, slope);
 #pragma unroll
           for (int u = 0; u < 3; ++u)
-            if (ok[u]) *reinterpret_cast<uint4*>(sp + ((i0 + u) * vstep) * 16) = raw[u];
+            if (ok[u]) *reinterpret_cast<uint4*>(chunk(i0 + u)) = raw[u];
         } else {      // 64 registers: one chunk at a time
 #pragma unroll
           for (int u = 0; u < 3; ++u) {
@@ -299,7 +310,7 @@ __device__ __forceinline__ void loader_role(const TcParams& p, uint8_t* smem, co
               if (act) { f.x = act_apply(f.x, act); f.y = act_apply(f.y, act); }
               hv[j] = __floats2half2_rn(f.x, f.y);
             }
-            *reinterpret_cast<uint4*>(sp + ((i0 + u) * vstep) * 16) = raw[u];
+            *reinterpret_cast<uint4*>(chunk(i0 + u)) = raw[u];
           }
         }
       }
@@ -332,8 +343,12 @@ __device__ __forceinline__ void loader_role_tma(const TcParams& p, uint8_t* smem
   const uint32_t stage_tx = (uint32_t)((p.KC / 8) * p.nvox_h * 16);
   auto issue = [&](const StageCursor& c, int slot) {
     mbar_arrive_expect_tx(A_LAND(slot), stage_tx);
-    tma_load_5d(smem_a + (uint32_t)(slot * p.a_stage_bytes), &p.tm_x, A_LAND(slot), 0, c.ti.wi * TW - pw, c.ti.hi * TH - ph,
-                c.kc * (p.KC / 8), c.ti.b * a.D + c.din);
+    if (p.row)
+      tma_load_4d(smem_a + (uint32_t)(slot * p.a_stage_bytes), &p.tm_x, A_LAND(slot), c.kc * p.KC, c.ti.wi * TW - pw, c.ti.hi * TH - ph,
+                  c.ti.b * a.D + c.din);
+    else
+      tma_load_5d(smem_a + (uint32_t)(slot * p.a_stage_bytes), &p.tm_x, A_LAND(slot), 0, c.ti.wi * TW - pw, c.ti.hi * TH - ph,
+                  c.kc * (p.KC / 8), c.ti.b * a.D + c.din);
   };
   if (lt == 0) {
     StageCursor c; c.init(tw, p);
@@ -617,6 +632,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   TC_PROF(31);
+  if (p.row && (smem_u32(smem) & 1023u)) __trap();      // the row image's swizzle phase assumes 1024-byte aligned stages
   const ConvArgs& a = p.a;
   // canonical warp index: the shuffle makes it provably warp-uniform, so the role branches below are uniform
   // branches and the MMA warp's loop compiles to the uniform datapath (UIADD3 + UTCHMMA, no R2UR per operand)
@@ -728,12 +744,17 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       Ring ra, rb; ra.init(p.SA); rb.init(p.SB);
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint64_t a_tmpl = make_desc(0, (uint32_t)p.plane_stride, (uint32_t)p.HALO_W * 16u);
+      // A operand: plane image = no-swizzle K-major core matrices (LBO = plane, SBO = one halo row of 16-byte slots);
+      // row image = K-major SWIZZLE_64B / 128B rows (SBO = one halo row of pitch-byte rows, 32 bytes per K step)
+      const uint32_t vox16 = p.row ? (uint32_t)p.pitch >> 4 : 1u;                 // 16-byte units per voxel shift
+      const uint64_t a_tmpl = p.row ? make_desc_sw(0, 16u, (uint32_t)(p.HALO_W * p.pitch), p.pitch == 128 ? 2u : 4u)
+                                    : make_desc(0, (uint32_t)p.plane_stride, (uint32_t)p.HALO_W * 16u);
       const uint64_t b_tmpl = make_desc(0, (uint32_t)p.NT * 16u, 128u);
-      const uint32_t a_kstep = (2u * (uint32_t)p.plane_stride) >> 4, b_kstep = (2u * (uint32_t)p.NT * 16u) >> 4;
+      const uint32_t a_kstep = p.row ? 2u : (2u * (uint32_t)p.plane_stride) >> 4, b_kstep = (2u * (uint32_t)p.NT * 16u) >> 4;
       const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
       const uint32_t smem_a16 = smem_a >> 4, smem_b16 = smem_b >> 4;
-      const int kd = a.kd, kh = a.kh, kw = a.kw, NKC = p.NKC, D = a.D, NT = p.NT, HALO_W = p.HALO_W;
+      const int kd = a.kd, kh = a.kh, kw = a.kw, NKC = p.NKC, D = a.D, NT = p.NT;
+      const uint32_t a_rowstep = (uint32_t)p.HALO_W * vox16;                      // next tap row, in 16-byte units
       const int resident = p.w_resident, acc_stages = p.acc_stages;
       const int taps_all = kd * taps_hw;
       const uint32_t res_step = (uint32_t)NKC * b_stage16;
@@ -762,10 +783,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             if (resident && kh == 3 && kw == 3) {
               done = true;
               switch (ksteps) {
-                case 1: issue_stage_resident<1, 3, 3>(tmem_d, da_row, db_res, idesc, accumulate, a_kstep, b_kstep, (uint32_t)HALO_W, res_step, elected); break;
-                case 2: issue_stage_resident<2, 3, 3>(tmem_d, da_row, db_res, idesc, accumulate, a_kstep, b_kstep, (uint32_t)HALO_W, res_step, elected); break;
-                case 3: issue_stage_resident<3, 3, 3>(tmem_d, da_row, db_res, idesc, accumulate, a_kstep, b_kstep, (uint32_t)HALO_W, res_step, elected); break;
-                case 4: issue_stage_resident<4, 3, 3>(tmem_d, da_row, db_res, idesc, accumulate, a_kstep, b_kstep, (uint32_t)HALO_W, res_step, elected); break;
+                case 1: issue_stage_resident<1, 3, 3>(tmem_d, da_row, db_res, idesc, accumulate, a_kstep, b_kstep, a_rowstep, vox16, res_step, elected); break;
+                case 2: issue_stage_resident<2, 3, 3>(tmem_d, da_row, db_res, idesc, accumulate, a_kstep, b_kstep, a_rowstep, vox16, res_step, elected); break;
+                case 3: issue_stage_resident<3, 3, 3>(tmem_d, da_row, db_res, idesc, accumulate, a_kstep, b_kstep, a_rowstep, vox16, res_step, elected); break;
+                case 4: issue_stage_resident<4, 3, 3>(tmem_d, da_row, db_res, idesc, accumulate, a_kstep, b_kstep, a_rowstep, vox16, res_step, elected); break;
                 default: done = false;
               }
             }
@@ -793,9 +814,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                     if (elected) umma_commit(B_EMPTY(rb.idx));   // weights slot free once these MMAs retire
                     rb.advance();
                   }
-                  da_tap += 1;                      // next tap to the right: 16 B
+                  da_tap += (uint64_t)vox16;        // next tap to the right: one voxel
                 }
-                da_row += (uint64_t)HALO_W;         // next tap row: HALO_W voxels
+                da_row += (uint64_t)a_rowstep;      // next tap row: HALO_W voxels
               }
             }
             if (elected) umma_commit(A_EMPTY(ra.idx));         // halo tile free
@@ -854,8 +875,15 @@ bool conv3d_fwd_tc_supported(const ConvArgs& a, int dtype) {
 }
 
 // `a.w` must be the TC weight IMAGE ([ntile][tap][kchunk][KC/8][NT][8], b200seg_pack_weight layout=TC).
+static int conv3d_fwd_tc_plan(const ConvArgs& a, cudaStream_t st, bool allow_row);
+
 int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   if (!conv3d_fwd_tc_supported(a, dtype)) return B200SEG_EUNSUPPORTED;
+  const int rc = conv3d_fwd_tc_plan(a, st, true);
+  return rc == -1 ? conv3d_fwd_tc_plan(a, st, false) : rc;     // -1: the row image does not fit this shape, use planes
+}
+
+static int conv3d_fwd_tc_plan(const ConvArgs& a, cudaStream_t st, bool allow_row) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.a = a;
@@ -865,15 +893,28 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
   p.HALO_H = TH + a.kh - 1; p.HALO_W = TW + a.kw - 1;
   p.nvox_h = p.HALO_H * p.HALO_W;
   int slots = p.nvox_h; if ((slots & 1) == 0) slots += 1;     // odd number of 16-B slots -> conflict-free plane stride
-  // measured (profiles/r2_layer_times*.txt): raw inputs (every data-gradient launch) gain 10-25 % from the TMA path; inputs
-  // that need the in-place transform gain 5-12 % while the whole Cin fits one K chunk (Cin <= 64) and LOSE 15-45 % beyond
-  // that (a {8 ch}-wide box moves 16 bytes per TMA request: the unit, not the SM, becomes the limit) — those keep cp.async.
+  // Operand staging (measured on every layer shape of the benchmark, profiles/r2_layer_times*.txt):
+  //  * RAW inputs (every data-gradient launch) are staged by ONE tensor-TMA box per stage and consumed by the MMA warp
+  //    straight off the TMA barrier — as the ROW image (one 128-byte SWIZZLE_128B row per halo voxel, 128 contiguous
+  //    bytes per TMA request) when Cin is a multiple of 128 (3-9 % faster than planes there), else as the PLANE image
+  //    [KC/8][voxel][8 ch] (16 bytes per request; better while the tile is a single K chunk);
+  //  * inputs that need InstanceNorm / activation: TMA planes + in-place transform by the loader warps while Cin <= 64
+  //    (5-12 % faster than cp.async), per-thread cp.async copies + transform beyond that.  The row image is available
+  //    for them too (B200SEG_CONV_ROW_ALL=1) but measured 25-60 % slower: with the copy off the SM the loader warps'
+  //    transform itself is what the tile waits for.
   const bool raw_input = !a.x_stats && a.act == 0;
-  p.use_tma = (!getenv("B200SEG_CONV_NO_TMA") && (raw_input || a.Cin <= 64 || getenv("B200SEG_CONV_TMA_ALL")) && p.nvox_h <= 192 &&
-               b200seg_make_act_tmap(&p.tm_x, a.x, a.x_ld, a.x_coff, a.Cin, a.B * a.D, a.H, a.W, p.HALO_W, p.HALO_H, p.KC / 8)) ? 1 : 0;
+  const bool tma_ok = !getenv("B200SEG_CONV_NO_TMA") && p.nvox_h <= 192;
+  const bool row_pays = (raw_input && p.KC == 64 && p.NKC >= 2) || getenv("B200SEG_CONV_ROW_ALL");
+  p.row = (tma_ok && allow_row && row_pays && !getenv("B200SEG_CONV_NO_ROW") &&
+           b200seg_make_row_tmap(&p.tm_x, a.x, a.x_ld, a.x_coff, a.Cin, p.KC, a.B * a.D, a.H, a.W, p.HALO_W, p.HALO_H)) ? 1 : 0;
+  p.pitch = p.KC * 2;
+  if (p.row) p.use_tma = 1;
+  else
+    p.use_tma = (tma_ok && (raw_input || a.Cin <= 64 || getenv("B200SEG_CONV_TMA_ALL")) &&
+                 b200seg_make_act_tmap(&p.tm_x, a.x, a.x_ld, a.x_coff, a.Cin, a.B * a.D, a.H, a.W, p.HALO_W, p.HALO_H, p.KC / 8)) ? 1 : 0;
   p.plane_stride = p.use_tma ? p.nvox_h * 16 : slots * 16;    // a TMA box is written densely
-  p.a_stage_bytes = (p.KC / 8) * p.plane_stride;
-  p.a_stage_bytes = (p.a_stage_bytes + 127) / 128 * 128;
+  p.a_stage_bytes = p.row ? p.nvox_h * p.pitch : (p.KC / 8) * p.plane_stride;
+  p.a_stage_bytes = (p.a_stage_bytes + 1023) / 1024 * 1024;   // swizzle atoms are 1024-byte aligned
   p.b_stage_bytes = p.KC * p.NT * 2;
   p.tiles_h = (a.H + TH - 1) / TH; p.tiles_w = (a.W + TW - 1) / TW;
   int64_t nt = (int64_t)a.B * a.D * p.tiles_h * p.tiles_w * p.NTILES;
@@ -899,12 +940,15 @@ int conv3d_fwd_tc(const ConvArgs& a, int dtype, cudaStream_t st) {
     p.SA = 4;
     while (p.SA > 2 && p.SA * p.a_stage_bytes + 3 * p.b_stage_bytes > budget) --p.SA;
     p.SB = (budget - p.SA * p.a_stage_bytes) / p.b_stage_bytes; if (p.SB > 8) p.SB = 8;
-    if (p.SB < 2) return B200SEG_EUNSUPPORTED;
+    if (p.SB < 2) return p.row ? -1 : B200SEG_EUNSUPPORTED;
     b_region = p.SB * p.b_stage_bytes;
   }
-  if (p.SA < 2) return B200SEG_EUNSUPPORTED;
+  if (p.SA < 2) return p.row ? -1 : B200SEG_EUNSUPPORTED;
   p.prefetch = p.SA - 1 < 3 ? p.SA - 1 : 3;
-  if (p.use_tma && !raw_input && p.SA < 4) p.use_tma = 0;      // the TMA + transform loader runs three stages ahead
+  if (p.use_tma && !raw_input && p.SA < 4) {                   // the TMA + transform loader runs three stages ahead
+    if (p.row) return -1;
+    p.use_tma = 0;
+  }
   int off = 0;
   p.smem_a_off = off; off += p.SA * p.a_stage_bytes;
   off = (off + 127) / 128 * 128;

@@ -112,6 +112,10 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint
   asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
@@ -175,6 +179,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;      // descriptor version (Blackwell)
   return d;                    // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+
+// swizzled operand rows (one 64- / 128-byte row per GEMM row resp. K index, as a tensor-TMA box with the matching swizzle
+// writes them): layout_type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B; lbo = distance between swizzle-wide blocks along the
+// leading (contiguous) dimension, sbo = distance between 8-row groups.  The swizzle is a function of the ABSOLUTE
+// shared-memory address bits, so a start address shifted by whole rows (a convolution tap) and an 8-row-group pitch
+// of HALO_W rows are legal (tools/umma_probe.cu, profiles/r1_umma_layout_probe.txt).
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return make_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)(layout_type & 7u) << 61);
 }
 
 __device__ __forceinline__ uint32_t elect_one() {
