@@ -479,11 +479,18 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// Cin tile (GEMM N).  Measured on the benchmark's layers (profiles/r2_layer_times_wgrad_ntc.txt): when Cin is a multiple of
+// 128 a 64-wide tile beats the 128-wide one by 10-30 % (TS mode applies, six taps share one staged tile instead of
+// three or four, 72 jobs x S = 144 CTAs instead of 108, three or four stages fit instead of two); 96 stays best for
+// Cin = 96 / 192 / 576.
 int pick_ntc(int Cin) {
   if (Cin % 16) return 0;
-  if (Cin <= 128) return Cin;
+  int cap = 128;
+  if (const char* e = getenv("B200SEG_WGRAD_NTC_MAX")) { const int v = atoi(e); if (v >= 16) cap = v; }   // tuning knob
+  if (Cin % 128 == 0 && cap >= 64) return 64;
+  if (Cin <= cap) return Cin;
   const int c[] = {128, 96, 64, 48, 32, 16};
-  for (int v : c) if (Cin % v == 0) return v;
+  for (int v : c) if (v <= cap && Cin % v == 0) return v;
   return 0;
 }
 
