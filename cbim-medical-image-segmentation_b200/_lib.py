@@ -32,6 +32,7 @@ _PROTOS = {
     "b200seg_instnorm_bwd_apply": [P, I, I, P, I, I, I, P, P, F, P, I, I, P, I, I, I, L, I, P],
     "b200seg_pack_weight": [P, I, I, I, P, I, I, I, I, I, P],
     "b200seg_pack_chunk_elems": [],
+    "b200seg_pack_tile_ci": [I],
     "b200seg_pack_weights_multi": [P, P, I, P],
     "b200seg_conv3d_algo": [I, I, I, I, I, I, I],
     "b200seg_conv3d_fwd": [P, I, I, P, F, I, P, P, P, I, I, P, I, I, P, P, I, I, P, F, I,

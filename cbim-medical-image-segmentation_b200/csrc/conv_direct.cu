@@ -254,14 +254,60 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
 
 // Multi-tensor variant: every conv weight of a model is re-packed by ONE launch per forward (the per-weight
 // launches were ~90 x 12 us per step).  jobs[j] = {w, out, Cout, Cin, taps, dtype, transpose_flip, co_off, co_total,
-// layout_tc}; chunks[c] = {job, first element}: one block per chunk of kPackChunk elements.
+// layout_tc}; one block per chunk.  chunks[c] = {job, code}:
+//   code >= 0 : ELEMENT chunk — kPackChunk consecutive source elements from `code`, each written to its packed
+//               position (2-byte scattered stores: 580 us per forward for the 40 M-parameter ResUNet, 10x the HBM time);
+//   code <  0 : TILE chunk (Cout, Cin multiples of 8) — -(code+1) = co0 * 65536 + ci0: eight output channels x up to
+//               pack_tile_ci(taps) input channels x all taps are staged through shared memory (coalesced row reads) and
+//               written as 16-byte groups of the packed image's contiguous 8-element runs (8 consecutive ci of one
+//               (co, tap) in the forward image, 8 consecutive co of one (ci, tap) in the flipped-transposed one).
 constexpr int kPackChunk = 4096;
+__host__ __device__ inline int pack_tile_ci(int taps) {       // input channels per tile: largest multiple of 8 with 8*ci*taps <= kPackChunk
+  const int c = kPackChunk / (8 * taps) / 8 * 8;
+  return c;                                                     // 0 -> no tile path for this kernel size
+}
+
+template <typename T>
+__device__ __forceinline__ void pack_tile(const float* __restrict__ w, T* __restrict__ o, int Cout, int Cin, int taps, int tf, int co_off,
+                                          int co_total, int tc, int co0, int ci0, float* tile) {
+  const int cit = min(pack_tile_ci(taps), Cin - ci0), seg = cit * taps;
+  for (int idx = threadIdx.x; idx < 8 * seg; idx += 256) {
+    const int r = idx / seg, k = idx - r * seg;
+    tile[idx] = w[((int64_t)(co0 + r) * Cin + ci0) * taps + k];
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < seg; g += 256) {
+    float v[8];
+    int64_t first;                          // source index of the group's first element (-> its packed position)
+    if (!tf) {                              // 8 consecutive ci of (co0 + r, tap); r fastest: neighbouring threads write neighbouring rows
+      const int r = g & 7, q = g >> 3, tap = q % taps, c8 = q / taps;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = tile[r * seg + (c8 * 8 + e) * taps + tap];
+      first = ((int64_t)(co0 + r) * Cin + ci0 + c8 * 8) * taps + tap;
+    } else {                                // 8 consecutive co of (ci0 + ci, tap); ci fastest
+      const int ci = g % cit, tap = g / cit;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = tile[e * seg + ci * taps + tap];
+      first = ((int64_t)co0 * Cin + ci0 + ci) * taps + tap;
+    }
+    st8<T>(o + pack_index(first, Cout, Cin, taps, tf, co_off, co_total, tc), v);
+  }
+}
+
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const int64_t* __restrict__ jobs, const int64_t* __restrict__ chunks) {
+  __shared__ float tile[kPackChunk];
   const int64_t* c = chunks + 2 * (int64_t)blockIdx.x;
   const int64_t* j = jobs + 10 * c[0];
   const float* w = reinterpret_cast<const float*>(j[0]);
   const int Cout = (int)j[2], Cin = (int)j[3], taps = (int)j[4], dtype = (int)j[5], tf = (int)j[6], co_off = (int)j[7],
             co_total = (int)j[8], tc = (int)j[9];
+  if (c[1] < 0) {
+    const int64_t code = -(c[1] + 1);
+    const int co0 = (int)(code >> 16), ci0 = (int)(code & 65535);
+    if (dtype == B200SEG_F16) pack_tile<__half>(w, reinterpret_cast<__half*>(j[1]), Cout, Cin, taps, tf, co_off, co_total, tc, co0, ci0, tile);
+    else pack_tile<float>(w, reinterpret_cast<float*>(j[1]), Cout, Cin, taps, tf, co_off, co_total, tc, co0, ci0, tile);
+    return;
+  }
   const int64_t n = (int64_t)Cout * Cin * taps, i0 = c[1];
   const int64_t i1 = i0 + kPackChunk < n ? i0 + kPackChunk : n;
   if (dtype == B200SEG_F16) {
@@ -338,6 +384,8 @@ extern "C" int b200seg_pack_weight(const float* w, int Cout, int Cin, int taps, 
 }
 
 extern "C" int b200seg_pack_chunk_elems(void) { return kPackChunk; }
+// input channels per TILE chunk for a `taps`-tap kernel (0: use element chunks); see pack_weights_multi_kernel
+extern "C" int b200seg_pack_tile_ci(int taps) { return taps > 0 ? pack_tile_ci(taps) : 0; }
 
 extern "C" int b200seg_pack_weights_multi(const int64_t* jobs_dev, const int64_t* chunks_dev, int nchunks, void* stream) {
   if (nchunks == 0) return B200SEG_OK;

@@ -259,7 +259,8 @@ class PackRegistry:
             return                      # nothing known yet (first forward): get() packs lazily
         tsig = tuple(h._sig for h in live)
         if self.dirty or tsig != self._table_sig:
-            chunk = _lib.load().b200seg_pack_chunk_elems()
+            lib = _lib.load()
+            chunk = lib.b200seg_pack_chunk_elems()
             jobs, chunks = [], []
             for h in live:
                 for w, out, flip, off, co_total, layout in h._jobs:
@@ -269,7 +270,13 @@ class PackRegistry:
                     j = len(jobs)
                     jobs.append([w.data_ptr(), out.data_ptr(), w.shape[0], w.shape[1], taps, _dt(out),
                                  1 if flip else 0, off, co_total, 1 if layout == ALGO_TC else 0])
-                    chunks.extend([j, e] for e in range(0, w.numel(), chunk))
+                    tile_ci = lib.b200seg_pack_tile_ci(taps)
+                    if tile_ci and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0 and off % 8 == 0 and w.shape[1] < 65536:
+                        # TILE chunks: 8 output channels x tile_ci input channels x all taps per block (16-byte stores)
+                        chunks.extend([j, -(1 + co0 * 65536 + ci0)] for co0 in range(0, w.shape[0], 8)
+                                      for ci0 in range(0, w.shape[1], tile_ci))
+                    else:
+                        chunks.extend([j, e] for e in range(0, w.numel(), chunk))
             dev = live[0]._jobs[0][0].device
             self._tables = (torch.tensor(jobs, dtype=torch.int64).to(dev), torch.tensor(chunks, dtype=torch.int64).to(dev),
                             len(chunks))

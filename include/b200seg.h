@@ -149,9 +149,16 @@ int b200seg_pack_weight(const float* w, int Cout, int Cin, int taps,
  * the reference's EMA, training/utils.py:99-102 — can never leave a stale image).
  *   jobs_dev  : int64 [njobs][10] = {w ptr, out ptr, Cout, Cin, taps, dtype,
  *               transpose_flip, co_off, co_total, layout==TC}
- *   chunks_dev: int64 [nchunks][2] = {job index, first element}; every chunk
- *               covers b200seg_pack_chunk_elems() consecutive elements of w. */
+ *   chunks_dev: int64 [nchunks][2] = {job index, code}, one thread block each:
+ *               code >= 0: ELEMENT chunk, b200seg_pack_chunk_elems() consecutive elements of w
+ *                          starting at `code`;
+ *               code <  0: TILE chunk (Cout and Cin multiples of 8), -(code+1) = co0*65536 + ci0:
+ *                          output channels [co0, co0+8) x input channels [ci0, ci0 +
+ *                          b200seg_pack_tile_ci(taps)) x all taps, staged through shared memory
+ *                          and written as 16-byte runs of the packed image. */
 int b200seg_pack_chunk_elems(void);
+/* input channels per TILE chunk of b200seg_pack_weights_multi for a `taps`-tap kernel (0 = element chunks only) */
+int b200seg_pack_tile_ci(int taps);
 int b200seg_pack_weights_multi(const int64_t* jobs_dev, const int64_t* chunks_dev,
                                int nchunks, void* stream);
 

@@ -161,3 +161,33 @@ def test_small_fwd_special_cases(ops, dtype, tol, Cin, Cout, k, bias):
     assert rel_err(ncdhw(y.float()), ref) < tol
     if yst is not None:
         assert rel_err(yst, stats_of(ncdhw(y.float().cpu()))) < 1e-5
+
+
+@pytest.mark.parametrize("cout,cin,k,flip,off,total,layout_tc", [
+    (32, 32, (1, 3, 3), False, 0, 32, True), (32, 32, (1, 3, 3), True, 0, 32, True),
+    (64, 96, (3, 3, 3), False, 64, 128, True), (64, 96, (3, 3, 3), True, 64, 128, True),     # shortcut half of a fused GEMM
+    (256, 384, (3, 3, 3), True, 0, 256, True), (128, 64, (1, 1, 1), False, 0, 128, True),
+    (32, 16, (3, 3, 3), False, 0, 32, False), (4, 32, (1, 1, 1), False, 0, 4, False),         # direct layout / element chunks
+])
+def test_multi_tensor_pack_matches_single(cout, cin, k, flip, off, total, layout_tc):
+    """b200seg_pack_weights_multi (TILE chunks: 8 co x tile_ci x taps through shared memory, 16-byte stores; ELEMENT chunks
+    for shapes that do not qualify) writes exactly what b200seg_pack_weight writes."""
+    from b200seg import _lib, ops
+    torch.manual_seed(1)
+    w = torch.randn(cout, cin, *k, device="cuda")
+    taps = k[0] * k[1] * k[2]
+    layout = ops.ALGO_TC if layout_tc else ops.ALGO_DIRECT
+    ref = torch.zeros(taps * total * cin, dtype=torch.float16, device="cuda")
+    ops.pack_weight(w, torch.float16, transpose_flip=flip, out=ref, co_off=off, co_total=total, layout=layout)
+    out = torch.zeros_like(ref)
+    lib = _lib.load()
+    chunk, tile_ci = lib.b200seg_pack_chunk_elems(), lib.b200seg_pack_tile_ci(taps)
+    jobs = [[w.data_ptr(), out.data_ptr(), cout, cin, taps, 1, 1 if flip else 0, off, total, 1 if layout_tc else 0]]
+    if tile_ci and cout % 8 == 0 and cin % 8 == 0 and off % 8 == 0:
+        chunks = [[0, -(1 + co0 * 65536 + ci0)] for co0 in range(0, cout, 8) for ci0 in range(0, cin, tile_ci)]
+    else:
+        chunks = [[0, e] for e in range(0, w.numel(), chunk)]
+    jt, ct = torch.tensor(jobs, dtype=torch.int64).cuda(), torch.tensor(chunks, dtype=torch.int64).cuda()
+    _lib.call("b200seg_pack_weights_multi", jt.data_ptr(), ct.data_ptr(), len(chunks), ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
