@@ -71,6 +71,9 @@ _PROTOS = {
     "b200seg_softmax_accumulate": [P, I, L, L, L, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "b200seg_normalize_argmax": [P, P, P, I, I, L, P],
     "b200seg_dice_metric": [P, I, P, I, L, I, P, P],
+    "b200seg_aug_resample": [P, P, I, I, P, P, P, P, P, P, I, P, P, I, P, I, P],
+    "b200seg_aug_pointwise": [P, P, I, L, I, P, P, P, P, P, ctypes.c_uint64, P],
+    "b200seg_aug_gaussian_blur": [P, P, I, I, I, I, P, I, P, I, P],
     "b200seg_biattn_workspace": [I, L, I, I],
     "b200seg_biattn_fwd": [P, I, I, P, I, I, P, I, P, I, I, P, I, I, P, I, I, P, P, I, L, I, I, I, F, I, P],
     "b200seg_biattn_bwd": [P, I, I, P, I, I, P, I, P, I, I, P, I, I, P, P, I, I, P, I, I, P, I, I, P, I, I,

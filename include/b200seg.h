@@ -422,6 +422,44 @@ int b200seg_normalize_argmax(float* prob, const float* counter, uint8_t* label, 
 int b200seg_dice_metric(const void* pred, int pred_bytes, const void* target, int target_bytes,
                         int64_t N, int C, unsigned long long* out, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * GPU augmentation (`aug_device: gpu`, training/augmentation.py, driven per sample by
+ * training/dataset/dim3/dataset_kits.py:116-153).  Images are fp32 [C][D][H][W] (the reference's
+ * [1,C,D,H,W]); label maps uint8 (bytes = 1) or int64 (bytes = 8).  The small geometry / parameter
+ * arrays (`*_dims`, `*_origin`, `theta`, `a`, `b`, `weights`) are HOST pointers read during the call.
+ *
+ * `stats`: one 32-byte row per statistics row of the reference's `view(tmp_C, -1)` (rows = 1, or C for
+ * per_channel): {uint64 min key, uint64 max key, double sum, double sum of squares}; the caller initialises
+ * a row to {0xffffffff, 0, 0.0, 0.0}; kernels ACCUMULATE (atomics).  key(f) = bits(f) ^ (sign ? ~0 : 1<<31).
+ *
+ * aug_resample: crop_3d(random) -> random_scale_rotate_translate_3d -> crop_3d(center) -> mirror x3
+ *   (augmentation.py:226-291,320-343,176-197) as one gather.  The affine grid is defined on the sub-volume
+ *   [sub_origin, sub_origin + sub_dims) of the source (F.affine_grid / F.grid_sample, align_corners=True,
+ *   zeros padding OUTSIDE THE SUB-VOLUME, trilinear image / nearest label); only the patch
+ *   [out_origin, out_origin + out_dims) of that grid is produced; flip_mask bit a mirrors output axis a.
+ *   theta = the 3x4 matrix handed to F.affine_grid (12 floats, row-major), or NULL for the exact-copy branch.
+ *   lab / out_lab may both be NULL; img / out_img may both be NULL with C = 0 (label map only).
+ *   stats (nullable) receives the statistics of out_img.
+ * aug_pointwise: op 0 brightness_multiply y = x*a[r] (:88-101); 1 brightness_additive y = x + a[r] (:66-85);
+ *   2 gamma pow pass y = ((x-min)/rng)^a[r]*rng + min (:123-127, needs stats_in); 3 gamma retain_stats pass
+ *   y = (x - mean_in)/std_in*std_in2 + mean_in2 (:129-131; stats_in = after the pow, stats_in2 = before);
+ *   4 contrast y = (x-mean)*a[r] + mean, clamped to [min,max] when b[r] != 0 (:136-168);
+ *   5 gaussian_noise y = x + N(0,1)*a[r] + b[r] (:14-16; Philox4x32-10 keyed by seed, counter = element / 4);
+ *   6 statistics only (y may be NULL).  rows <= 8, n = elements per row; stats_out (nullable) receives the
+ *   statistics of y, so a chain of ops never needs a separate reduction pass.
+ * aug_gaussian_blur: gaussian_blur (:18-64) with the 1-D weights of the separable kernel (ksize 1..7, odd),
+ *   zero padding like F.conv3d(padding = k//2); x != y.
+ * ------------------------------------------------------------------------- */
+int b200seg_aug_resample(const float* img, const void* lab, int lab_bytes, int C, const int* src_dims,
+                         const int* sub_origin, const int* sub_dims, const float* theta,
+                         const int* out_origin, const int* out_dims, int flip_mask, float* out_img,
+                         void* out_lab, int out_lab_bytes, void* stats, int stats_rows, void* stream);
+int b200seg_aug_pointwise(const float* x, float* y, int rows, int64_t n, int op, const float* a,
+                          const float* b, const void* stats_in, const void* stats_in2, void* stats_out,
+                          uint64_t seed, void* stream);
+int b200seg_aug_gaussian_blur(const float* x, float* y, int C, int D, int H, int W, const float* weights,
+                              int ksize, void* stats_out, int stats_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
