@@ -5,6 +5,7 @@ Importing this package never touches the GPU; every op fails loudly without libb
 from . import _lib
 from . import augmentation
 from ._lib import B200SegError, EXPORTED_SYMBOLS, LIB_PATH
+from .attention_unet import AttentionUNet
 from .factory import get_model
 from .inference import (calculate_dice, calculate_dice_split, get_inference, inference_sliding_window,
                         inference_whole_image)
@@ -14,6 +15,6 @@ from .swin_unetr import SwinUNETR
 from .unet3d import UNet
 from .unetpp import UNetPlusPlus
 
-__all__ = ["augmentation", "get_model", "UNet", "MedFormer", "SwinUNETR", "UNetPlusPlus", "DiceLoss", "DiceCELoss", "CrossEntropyLoss", "B200SegError",
+__all__ = ["augmentation", "get_model", "UNet", "MedFormer", "SwinUNETR", "UNetPlusPlus", "AttentionUNet", "DiceLoss", "DiceCELoss", "CrossEntropyLoss", "B200SegError",
            "EXPORTED_SYMBOLS", "LIB_PATH", "get_inference", "inference_sliding_window", "inference_whole_image",
            "calculate_dice", "calculate_dice_split"]

@@ -74,6 +74,8 @@ _PROTOS = {
     "b200seg_aug_resample": [P, P, I, I, P, P, P, P, P, P, I, P, P, I, P, I, P],
     "b200seg_aug_pointwise": [P, P, I, L, I, P, P, P, P, P, ctypes.c_uint64, P],
     "b200seg_aug_gaussian_blur": [P, P, I, I, I, I, P, I, P, I, P],
+    "b200seg_attn_gate_fwd": [P, I, P, P, I, I, F, P, P, P, I, I, P, I, L, I, I, I, P],
+    "b200seg_attn_gate_bwd": [P, I, I, P, I, I, P, I, P, P, P, F, P, P, P, P, P, I, L, I, I, I, P],
     "b200seg_biattn_workspace": [I, L, I, I],
     "b200seg_biattn_fwd": [P, I, I, P, I, I, P, I, P, I, I, P, I, I, P, I, I, P, P, I, L, I, I, I, F, I, P],
     "b200seg_biattn_bwd": [P, I, I, P, I, I, P, I, P, I, I, P, I, I, P, P, I, I, P, I, I, P, I, I, P, I, I,
@@ -120,7 +122,7 @@ def check(rc, what):
 
 # kernels launched per entry point (dice fwd = reduce + finalize; its memset is not ours)
 _KERNELS = {"b200seg_dice_ce_fwd": 2, "b200seg_biattn_fwd": 2, "b200seg_window_attn_bwd": 2, "b200seg_adamw_ema_step": 2, "b200seg_biattn_bwd": 2,
-            "b200seg_mapgen_fwd": 2}
+            "b200seg_mapgen_fwd": 2, "b200seg_attn_gate_fwd": 2, "b200seg_attn_gate_bwd": 2}
 launch_count = 0
 
 

@@ -17,6 +17,10 @@ def get_model(args, pretrain=False):
                 raise ValueError('No pretrain model available')   # model/utils.py:14-17
             return UNetPlusPlus(args.in_chan, args.base_chan, num_classes=args.classes, scale=args.down_scale,
                                 norm=args.norm, kernel_size=args.kernel_size, block=args.block)   # :87
+        if args.model == 'attention_unet':
+            from .attention_unet import AttentionUNet       # the 3d branch has no pretrain check (model/utils.py:88-90)
+            return AttentionUNet(args.in_chan, args.base_chan, num_classes=args.classes, scale=args.down_scale,
+                                 norm=args.norm, kernel_size=args.kernel_size, block=args.block)
         if args.model == 'medformer':
             from .medformer import MedFormer
             if pretrain:

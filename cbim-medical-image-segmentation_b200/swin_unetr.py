@@ -65,18 +65,20 @@ class DeriveWeightFn(torch.autograd.Function):
 
 
 class ResOutFn(torch.autograd.Function):
-    """y = lrelu(IN(r2) + res): the output stage of monai's UnetResBlock; res = IN(r3) (1x1 projection branch) or the
-    block input itself."""
+    """y = act(IN(r2) + res): the output stage of monai's UnetResBlock (act = LeakyReLU 0.01); res = IN(r3) (1x1
+    projection branch) or the block input itself.  With act = ReLU it is also the `relu(g1 + x1)` of Attention-UNet's
+    gate (attention_unet_utils.py:31-34)."""
 
     @staticmethod
-    def forward(ctx, r2, st2, r3, st3):
+    def forward(ctx, r2, st2, r3, st3, act=ACT_LRELU):
         _need_cuda(r2)
         B, D, H, W, C = r2.shape
         y = torch.empty(B, D, H, W, C, dtype=r2.dtype, device=r2.device)
         r3 = r3.contiguous()
         call("b200seg_resblock_out_fwd", r2.data_ptr(), C, st2.data_ptr(), r3.data_ptr(), r3.shape[-1], 0,
-             None if st3 is None else st3.data_ptr(), IN_EPS, ACT_LRELU, y.data_ptr(), C, B, D * H * W, C, _dt(r2), _stream())
+             None if st3 is None else st3.data_ptr(), IN_EPS, act, y.data_ptr(), C, B, D * H * W, C, _dt(r2), _stream())
         ctx.save_for_backward(r2, st2, r3, st3, y)
+        ctx.act = act
         return y
 
     @staticmethod
@@ -87,7 +89,7 @@ class ResOutFn(torch.autograd.Function):
         g = torch.empty_like(r2)
         sums = torch.zeros(B, C, 3, dtype=torch.float64, device=r2.device)
         call("b200seg_resblock_out_bwd_reduce", dy.data_ptr(), C, y.data_ptr(), C, r2.data_ptr(), C, st2.data_ptr(),
-             r3.data_ptr(), r3.shape[-1], 0, None if st3 is None else st3.data_ptr(), IN_EPS, ACT_LRELU, g.data_ptr(),
+             r3.data_ptr(), r3.shape[-1], 0, None if st3 is None else st3.data_ptr(), IN_EPS, ctx.act, g.data_ptr(),
              sums.data_ptr(), B, D * H * W, C, _dt(r2), _stream())
         b2 = sums[:, :, :2].contiguous()
         dr2 = ops.in_bwd_apply(g, r2, 0, C, st2, b2, eps=IN_EPS)
@@ -96,7 +98,7 @@ class ResOutFn(torch.autograd.Function):
             dr3 = ops.in_bwd_apply(g, r3, 0, C, st3, b3, eps=IN_EPS)
         else:
             dr3 = g
-        return dr2, None, dr3, None
+        return dr2, None, dr3, None, None
 
 
 class WindowAttnFn(torch.autograd.Function):
@@ -246,8 +248,8 @@ class UnetResBlock(nn.Module):
         if self.downsample:
             w3 = self.conv3.conv.weight
             r3, st3 = ConvFn.apply(x, None, None, None, self._p3.get([w3], x.dtype, x.shape[0], 0), (1, 1, 1), ACT_NONE, 0, IN_EPS, True, w3)
-            return ResOutFn.apply(r2, st2, r3, st3)
-        return ResOutFn.apply(r2, st2, x, None)
+            return ResOutFn.apply(r2, st2, r3, st3, ACT_LRELU)
+        return ResOutFn.apply(r2, st2, x, None, ACT_LRELU)
 
 
 class UnetrBasicBlock(nn.Module):

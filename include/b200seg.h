@@ -460,6 +460,26 @@ int b200seg_aug_pointwise(const float* x, float* y, int rows, int64_t n, int op,
 int b200seg_aug_gaussian_blur(const float* x, float* y, int C, int D, int H, int W, const float* weights,
                               int ksize, void* stats_out, int stats_rows, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Attention-UNet gate, model/dim3/attention_unet_utils.py:7-37.  With
+ * t = relu(IN(W_g g) + IN(W_x x)) already formed (conv3d_fwd x2 + resblock_out_fwd, act = RELU):
+ * attn_gate_fwd:  p[b][v] = sum_c w[c] t[b][v][c]          (`psi` Conv3d(int_ch, 1, 1, bias=False), :20)
+ *                 pstats[b] += {sum p, sum p^2}              (InstanceNorm3d(1), :21, eps = 1e-5)
+ *                 out[b][v][o_coff + c] = x[b][v][x_coff + c] * sigmoid(IN(p)[b][v])     (:22,37)
+ *                 ostats[b][c] += {sum, sumsq} of out (nullable; the next conv's loader normalises with them)
+ *   t [B][V][Ct] (leading dimension t_ld), w fp32 [Ct], p fp32 [B][V]; Ct, Cx multiples of 8.
+ * attn_gate_bwd:  dx = dout * psi (dense [B][V][Cx]); dt = dp * w (dense [B][V][Ct], before t's ReLU mask, which
+ *   resblock_out_bwd_reduce applies); dw[c] += sum dp * t; dz fp32 [B][V] and bsums double [B][2] are scratch
+ *   (bsums zeroed by the caller, like pstats / ostats / dw).
+ * ------------------------------------------------------------------------- */
+int b200seg_attn_gate_fwd(const void* t, int t_ld, const float* w, const void* x, int x_ld, int x_coff,
+                          float eps, float* p, double* pstats, void* out, int o_ld, int o_coff,
+                          double* ostats, int B, int64_t V, int Ct, int Cx, int dtype, void* stream);
+int b200seg_attn_gate_bwd(const void* dout, int d_ld, int d_coff, const void* x, int x_ld, int x_coff,
+                          const void* t, int t_ld, const float* w, const float* p, const double* pstats,
+                          float eps, void* dx, void* dt, float* dw, float* dz, double* bsums, int B,
+                          int64_t V, int Ct, int Cx, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
