@@ -61,7 +61,7 @@ class AttnGateFn(torch.autograd.Function):
         V = D * H * W
         w = w_psi.detach().reshape(-1).float().contiguous()
         p = torch.empty(B, V, dtype=torch.float32, device=x.device)
-        pst = torch.zeros(B, 2, dtype=torch.float64, device=x.device)
+        pst = ops.zeros_scratch((B, 2), torch.float64, x.device)
         out = torch.empty_like(x)
         ost = ops.new_stats(B, Cx, x.device)
         call("b200seg_attn_gate_fwd", t.data_ptr(), Ct, w.data_ptr(), x.data_ptr(), Cx, 0, GATE_EPS, p.data_ptr(), pst.data_ptr(),
@@ -81,7 +81,7 @@ class AttnGateFn(torch.autograd.Function):
         dx, dt = torch.empty_like(x), torch.empty_like(t)
         dw = torch.zeros(Ct, dtype=torch.float32, device=x.device)
         dz = torch.empty(B, V, dtype=torch.float32, device=x.device)
-        bs = torch.zeros(B, 2, dtype=torch.float64, device=x.device)
+        bs = ops.zeros_scratch((B, 2), torch.float64, x.device)
         call("b200seg_attn_gate_bwd", dout.data_ptr(), Cx, 0, x.data_ptr(), Cx, 0, t.data_ptr(), Ct, w.data_ptr(), p.data_ptr(),
              pst.data_ptr(), GATE_EPS, dx.data_ptr(), dt.data_ptr(), dw.data_ptr(), dz.data_ptr(), bs.data_ptr(), B, V, Ct, Cx,
              _dt(x), _stream())

@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._lib import ACT_NONE, call
 from .ops import (_dt, _need_cuda, _stream, conv3d_fwd, conv3d_wgrad, copy_channels, dwconv3d, dwconv3d_wgrad,
-                  in_bwd_apply, in_bwd_reduce, instnorm_stats)
+                  in_bwd_apply, in_bwd_reduce, instnorm_stats, zeros_scratch)
 
 
 class ConvFn(torch.autograd.Function):
@@ -192,7 +192,7 @@ class SEScaleFn(torch.autograd.Function):
         V = D * H * W
         R = s1[0]
         dev = x.device
-        dgate = torch.zeros(B, C, dtype=torch.float32, device=dev)
+        dgate = zeros_scratch((B, C), torch.float32, dev)
         call("b200seg_channel_scale_bwd_reduce", dy.data_ptr(), x.data_ptr(), dgate.data_ptr(), B, V, C, _dt(x), _stream())
         dw1 = torch.zeros(R, C, dtype=torch.float32, device=dev)
         db1 = torch.zeros(R, dtype=torch.float32, device=dev)

@@ -87,7 +87,7 @@ class ResOutFn(torch.autograd.Function):
         dy = dy.contiguous()
         B, D, H, W, C = r2.shape
         g = torch.empty_like(r2)
-        sums = torch.zeros(B, C, 3, dtype=torch.float64, device=r2.device)
+        sums = ops.zeros_scratch((B, C, 3), torch.float64, r2.device)
         call("b200seg_resblock_out_bwd_reduce", dy.data_ptr(), C, y.data_ptr(), C, r2.data_ptr(), C, st2.data_ptr(),
              r3.data_ptr(), r3.shape[-1], 0, None if st3 is None else st3.data_ptr(), IN_EPS, ctx.act, g.data_ptr(),
              sums.data_ptr(), B, D * H * W, C, _dt(r2), _stream())
