@@ -18,7 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 DST = os.path.join(HERE, "_ref")
 FILES = ["model/dim3/unet.py", "model/dim3/unet_utils.py", "model/dim3/utils.py", "model/dim3/conv_layers.py",
          "model/dim3/trans_layers.py", "model/dim3/medformer.py", "model/dim3/medformer_utils.py", "model/dim3/unetpp.py",
-         "model/dim3/swin_unetr.py", "training/losses.py", "training/utils.py"]
+         "model/dim3/swin_unetr.py", "model/dim3/attention_unet.py", "model/dim3/attention_unet_utils.py",
+         "training/losses.py", "training/utils.py", "training/augmentation.py"]
 
 
 def main():

@@ -124,3 +124,43 @@ def test_swin_unetr_forward_backward(amp):
         assert e < 5e-2 and agree > 0.97 and abs(loss.item() - g["loss"]) < 3e-2 and l2 < 0.25
     else:
         assert e < 2e-3 and agree > 0.9995 and abs(loss.item() - g["loss"]) < 1e-4 and l2 < 5e-3
+
+
+@pytest.mark.parametrize("dims,heads,dh,window,shift", [((9, 14, 8), 3, 16, (7, 7, 7), (3, 3, 3)),      # SwinUNETR fs48 head size, clamped + shifted
+                                                        ((7, 7, 7), 2, 16, (7, 7, 7), (0, 0, 0)),      # one full window, no mask
+                                                        ((5, 6, 9), 2, 32, (4, 4, 4), (2, 2, 2)),
+                                                        ((8, 8, 8), 3, 8, (4, 4, 4), (2, 0, 2))])
+def test_window_attention_mma_path(dims, heads, dh, window, shift):
+    """The tensor-core kernels (swin_mma.cu, fp16) against the CUDA-core kernels (swin.cu) — which the block fixtures
+    above pin to the reference — on the same inputs: fp16 CUDA-core (same rounding of the inputs) and fp32."""
+    import os
+    from b200seg.swin_unetr import WindowAttnFn
+    g = torch.Generator().manual_seed(dh * 100 + heads)
+    C = heads * dh
+    B = 2
+    qkv = (torch.randn(B, *dims, 3 * C, generator=g) * 0.8)
+    bias = torch.randn(3 * C, generator=g) * 0.3
+    table = torch.randn((2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1), heads, generator=g) * 0.5
+    dout = torch.randn(B, *dims, C, generator=g)
+
+    def run(dtype, mma):
+        os.environ["B200SEG_WINATTN_MMA"] = "1" if mma else "0"
+        try:
+            x = qkv.cuda().to(dtype).requires_grad_(True)
+            b = bias.cuda().requires_grad_(True)
+            t = table.cuda().requires_grad_(True)
+            y = WindowAttnFn.apply(x, b, t, heads, window, shift)
+            y.backward(dout.cuda().to(dtype))
+            torch.cuda.synchronize()
+            return [v.detach().float().cpu() for v in (y, x.grad, t.grad, b.grad)]
+        finally:
+            os.environ.pop("B200SEG_WINATTN_MMA", None)
+    ref32 = run(torch.float32, False)
+    cc16 = run(torch.float16, False)
+    mma16 = run(torch.float16, True)
+    names = ("out", "dqkv", "dtable", "dbias")
+    for nme, a, c, r in zip(names, mma16, cc16, ref32):
+        e_ref, e_cc, floor = rel_err(a, r), rel_err(a, c), rel_err(c, r)
+        print("win-attn mma %s dh=%d: vs fp32 %.2e, vs fp16 CUDA-core %.2e (fp16 CUDA-core vs fp32 %.2e)" % (nme, dh, e_ref, e_cc, floor))
+        assert e_ref < max(2e-2, 3 * floor), nme
+    assert not torch.equal(mma16[0], cc16[0]) or dh not in (8, 16, 32)       # the two paths really are different kernels
