@@ -31,9 +31,13 @@ gate_rowdot_fwd_kernel(const T* __restrict__ t, int t_ld, const float* __restric
   const int64_t v0 = (int64_t)blockIdx.x * vpb, v1 = (v0 + vpb < V) ? v0 + vpb : V;
   const T* tb = t + (int64_t)b * V * t_ld;
   float s1 = 0.f, s2 = 0.f;
-  for (int64_t v = v0 + slot; v < v1; v += kThreads / 8) {
+  // the trip count is uniform over the block (the four voxels of a warp may straddle v1: predicate, do not diverge —
+  // the shuffles below need every lane)
+  for (int64_t vb = v0; vb < v1; vb += kThreads / 8) {
+    const int64_t v = vb + slot;
+    const bool live = v < v1;
     float acc = 0.f;
-    for (int j = l8; j < C / 8; j += 8) {
+    for (int j = l8; live && j < C / 8; j += 8) {
       float a[8];
       ld8<T>(tb + v * t_ld + j * 8, a);
       const float4 w0 = *reinterpret_cast<const float4*>(w + j * 8), w1 = *reinterpret_cast<const float4*>(w + j * 8 + 4);
@@ -42,7 +46,7 @@ gate_rowdot_fwd_kernel(const T* __restrict__ t, int t_ld, const float* __restric
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    if (l8 == 0) {
+    if (live && l8 == 0) {
       const float r = Elem<T>::round(acc);          // the conv output is a storage-dtype tensor in the reference
       p[(int64_t)b * V + v] = r;
       s1 += r; s2 += r * r;
@@ -125,11 +129,13 @@ gate_apply_bwd_kernel(const T* __restrict__ dout, int d_ld, int d_coff, const T*
   const T* xb = x + (int64_t)b * V * x_ld + x_coff;
   T* dxb = dx + (int64_t)b * V * C;
   float s1 = 0.f, s2 = 0.f;
-  for (int64_t v = v0 + slot; v < v1; v += kThreads / 8) {
-    const float ph = (p[(int64_t)b * V + v] - mean) * rstd;
+  for (int64_t vb = v0; vb < v1; vb += kThreads / 8) {          // block-uniform trip count, see gate_rowdot_fwd_kernel
+    const int64_t v = vb + slot;
+    const bool live = v < v1;
+    const float ph = live ? (p[(int64_t)b * V + v] - mean) * rstd : 0.f;
     const float s = sigmoidf(ph);
     float dot = 0.f;
-    for (int j = l8; j < C / 8; j += 8) {
+    for (int j = l8; live && j < C / 8; j += 8) {
       float g[8], a[8];
       ld8<T>(db + v * d_ld + j * 8, g);
       ld8<T>(xb + v * x_ld + j * 8, a);
@@ -140,7 +146,7 @@ gate_apply_bwd_kernel(const T* __restrict__ dout, int d_ld, int d_coff, const T*
     dot += __shfl_xor_sync(0xffffffffu, dot, 1);
     dot += __shfl_xor_sync(0xffffffffu, dot, 2);
     dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-    if (l8 == 0) {
+    if (live && l8 == 0) {
       const float z = dot * s * (1.f - s);
       dz[(int64_t)b * V + v] = z;
       s1 += z; s2 += z * ph;
