@@ -20,6 +20,12 @@ def pytest_collection_modifyitems(config, items):
     except Exception:
         have = False
     if have:
+        # a hung kernel must cost one test, not the whole GPU session: every gpu test gets a wall-clock limit
+        # (pytest-timeout, thread method: the process is torn down even if the main thread sits in a CUDA sync)
+        if config.pluginmanager.hasplugin("timeout"):
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(240, method="thread"))
         return
     skip = pytest.mark.skip(reason="needs a CUDA device (B200); run through gpurun with -m gpu")
     for item in items:
