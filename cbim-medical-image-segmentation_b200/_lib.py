@@ -45,7 +45,7 @@ _PROTOS = {
     "b200seg_upsample_trilinear_bwd": [P, I, I, P, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "b200seg_copy_channels": [P, I, I, I, P, I, I, I, I, L, I, P],
     "b200seg_dwconv3d_fwd": [P, I, I, P, F, I, P, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P],
-    "b200seg_dwconv3d_wgrad": [P, I, I, P, F, I, P, I, I, P, I, I, I, I, I, I, I, I, I, P],
+    "b200seg_dwconv3d_wgrad": [P, I, I, P, F, I, P, I, I, P, I, I, I, I, I, I, I, I, I, I, P],
     "b200seg_space_to_depth": [P, P, I, I, I, I, I, I, I, I, I, I, P],
     "b200seg_mapgen_workspace": [I, L, I, I],
     "b200seg_mapgen_fwd": [P, I, I, P, I, I, P, P, P, I, L, I, I, I, P],

@@ -68,6 +68,56 @@ extern "C" int b200seg_conv3d_fwd(const void* x, int x_ld, int x_coff, const dou
   return conv3d_fwd_direct(a, dtype, st);
 }
 
+
+// ---- bias gradient db[c] += sum_v dy[v][c] as its own column-sum pass, so that convolutions / Linears WITH a bias
+// (every nn.Linear of SwinUNETR: qkv, proj, fc1, fc2 — 32 per step) can take the tcgen05 weight-gradient kernel, which has
+// no bias path.  HBM-bound: dy is read once (16-byte loads), block partials in shared memory, fp32 atomics.
+namespace {
+constexpr int kBgThreads = 256, kBgChan = 512;      // channels per block column (grid.y)
+template <typename T>
+__global__ void __launch_bounds__(kBgThreads) bias_grad_kernel(const T* __restrict__ dy, int ld, int coff, float* __restrict__ db,
+                                                               int64_t nvox, int C, int64_t vpb) {
+  __shared__ float sm[kBgThreads * 8];
+  const int c0 = blockIdx.y * kBgChan, cn = (C - c0 < kBgChan) ? C - c0 : kBgChan;
+  const int cpv = cn / 8, vpp = kBgThreads / cpv, cchunk = threadIdx.x % cpv, vloc = threadIdx.x / cpv;
+  const bool active = vloc < vpp;
+  const int64_t v0 = (int64_t)blockIdx.x * vpb, v1 = (v0 + vpb < nvox) ? v0 + vpb : nvox;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (active) {
+    const T* p = dy + coff + c0 + cchunk * 8;
+    for (int64_t v = v0 + vloc; v < v1; v += vpp) {
+      float a[8];
+      ld8<T>(p + v * ld, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += a[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[threadIdx.x * 8 + i] = active ? acc[i] : 0.f;
+  __syncthreads();
+  for (int o = threadIdx.x; o < cn; o += kBgThreads) {
+    float s = 0.f;
+    for (int vl = 0; vl < vpp; ++vl) s += sm[(vl * cpv + o / 8) * 8 + (o & 7)];
+    atomicAdd(&db[c0 + o], s);
+  }
+}
+
+int launch_bias_grad(const WgradArgs& a, int dtype, cudaStream_t st) {
+  const int64_t nvox = (int64_t)a.B * a.D * a.H * a.W;
+  int64_t blocks = (B200SEG_NUM_SMS * 4) / ((a.Cout + kBgChan - 1) / kBgChan);
+  if (blocks < 1) blocks = 1;
+  int64_t vpb = (nvox + blocks - 1) / blocks;
+  if (vpb < 64) vpb = 64;
+  dim3 grid(ceil_div(nvox, vpb), (a.Cout + kBgChan - 1) / kBgChan);
+  if (dtype == B200SEG_F16) bias_grad_kernel<__half><<<grid, kBgThreads, 0, st>>>((const __half*)a.dy, a.dy_ld, a.dy_coff, a.dbias, nvox, a.Cout, vpb);
+  else bias_grad_kernel<float><<<grid, kBgThreads, 0, st>>>((const float*)a.dy, a.dy_ld, a.dy_coff, a.dbias, nvox, a.Cout, vpb);
+  B200_CHECK_LAUNCH("bias_grad_kernel");
+  return B200SEG_OK;
+}
+}  // namespace
+
 static int wgrad_args(WgradArgs& a, const void* x, int x_ld, int x_coff, const double* x_stats, float eps, int act,
                       const void* dy, int dy_ld, int dy_coff, float* dw, float* dbias, int B, int D, int H, int W,
                       int Cin, int Cout, int kd, int kh, int kw, int dtype) {
@@ -109,6 +159,16 @@ extern "C" int b200seg_conv3d_wgrad(const void* x, int x_ld, int x_coff, const d
   if (algo == B200SEG_ALGO_AUTO) {
     rc = conv3d_wgrad_small(a, dtype, st);
     if (rc != B200SEG_EUNSUPPORTED) return rc;
+  }
+  if (algo == B200SEG_ALGO_AUTO && a.dbias && a.Cout % 8 == 0) {
+    // the tcgen05 kernel has no bias path: take the bias gradient in its own pass and let it do the weight gradient
+    WgradArgs nb = a;
+    nb.dbias = nullptr;
+    if (conv3d_wgrad_tc_supported(nb, dtype)) {
+      rc = launch_bias_grad(a, dtype, st);
+      if (rc) return rc;
+      return conv3d_wgrad_tc(nb, dtype, workspace, ws_bytes, st);
+    }
   }
   return conv3d_wgrad_direct(a, dtype, st);
 }

@@ -16,6 +16,7 @@ constexpr int MAXK = 3;      // kernel extent per axis (1 or 3 in every referenc
 struct DwArgs {
   const void* x; int x_ld, x_coff; const double* x_stats; float eps; int act;
   const float* w; int flip;
+  int wlay;                  // 0: weights / weight gradient as [taps][Ctot]; 1: [Ctot][taps] (the module's own [C,1,kd,kh,kw] parameter)
   void* y; int y_ld, y_coff; double* y_stats;
   const void* dy; int dy_ld, dy_coff; float* dw;
   int B, D, H, W, C, kd, kh, kw;
@@ -73,7 +74,8 @@ __global__ void __launch_bounds__(256, 2) dwconv_fwd_kernel(DwArgs a) {
   for (int o = tid; o < taps * C; o += blockDim.x) {
     const int t = o / C, c = o % C;
     // [tap][half][cg][4]: a warp's float4 reads (lane = channel group) are contiguous -> no bank conflicts
-    s_w[((t * 2 + ((c & 7) >> 2)) * (C >> 3) + (c >> 3)) * 4 + (c & 3)] = a.w[(a.flip ? taps - 1 - t : t) * a.Ctot + c0 + c];
+    s_w[((t * 2 + ((c & 7) >> 2)) * (C >> 3) + (c >> 3)) * 4 + (c & 3)] = a.wlay ? a.w[(int64_t)(c0 + c) * taps + (a.flip ? taps - 1 - t : t)]
+                                                                                    : a.w[(a.flip ? taps - 1 - t : t) * a.Ctot + c0 + c];
   }
   for (int c = tid; c < C; c += blockDim.x) {
     float mean = 0.f, rstd = 1.f;
@@ -274,7 +276,8 @@ __global__ void __launch_bounds__(256, 2) dwconv_wgrad_kernel(DwArgs a) {
       }
   __syncthreads();
   for (int o = tid; o < thw * C; o += blockDim.x)
-    atomicAdd(&a.dw[((int64_t)zd * thw + o / C) * a.Ctot + c0 + o % C], s_acc[o]);
+    atomicAdd(a.wlay ? &a.dw[(int64_t)(c0 + o % C) * (a.kd * thw) + zd * thw + o / C]
+                     : &a.dw[((int64_t)zd * thw + o / C) * a.Ctot + c0 + o % C], s_acc[o]);
 }
 
 int check(const DwArgs& a, int dtype) {
@@ -297,7 +300,7 @@ extern "C" int b200seg_dwconv3d_fwd(const void* x, int x_ld, int x_coff, const d
                                     const float* w, int flip, void* y, int y_ld, int y_coff, double* y_stats,
                                     int B, int D, int H, int W, int C, int kd, int kh, int kw, int dtype, void* stream) {
   DwArgs a; memset(&a, 0, sizeof(a));
-  a.x = x; a.x_ld = x_ld; a.x_coff = x_coff; a.x_stats = x_stats; a.eps = eps; a.act = act; a.w = w; a.flip = flip;
+  a.x = x; a.x_ld = x_ld; a.x_coff = x_coff; a.x_stats = x_stats; a.eps = eps; a.act = act; a.w = w; a.flip = flip & 1; a.wlay = (flip >> 1) & 1;
   a.y = y; a.y_ld = y_ld; a.y_coff = y_coff; a.y_stats = y_stats;
   a.B = B; a.D = D; a.H = H; a.W = W; a.C = C; a.kd = kd; a.kh = kh; a.kw = kw;
   int rc = check(a, dtype);
@@ -341,9 +344,10 @@ extern "C" int b200seg_dwconv3d_fwd(const void* x, int x_ld, int x_coff, const d
 }
 
 extern "C" int b200seg_dwconv3d_wgrad(const void* x, int x_ld, int x_coff, const double* x_stats, float eps, int act,
-                                      const void* dy, int dy_ld, int dy_coff, float* dw,
+                                      const void* dy, int dy_ld, int dy_coff, float* dw, int dw_layout,
                                       int B, int D, int H, int W, int C, int kd, int kh, int kw, int dtype, void* stream) {
   DwArgs a; memset(&a, 0, sizeof(a));
+  a.wlay = dw_layout ? 1 : 0;
   a.x = x; a.x_ld = x_ld; a.x_coff = x_coff; a.x_stats = x_stats; a.eps = eps; a.act = act;
   a.dy = dy; a.dy_ld = dy_ld; a.dy_coff = dy_coff; a.dw = dw; a.Ctot = C; a.c0 = 0;
   a.B = B; a.D = D; a.H = H; a.W = W; a.C = C; a.kd = kd; a.kh = kh; a.kw = kw;

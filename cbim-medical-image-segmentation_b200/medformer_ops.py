@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import ACT_NONE, call
-from .ops import (_dt, _need_cuda, _stream, conv3d_fwd, conv3d_wgrad, copy_channels, dwconv3d, dwconv3d_wgrad,
+from .ops import (_dt, _need_cuda, _stream, conv3d_fwd, conv3d_wgrad, copy_channels, dw_weight, dwconv3d, dwconv3d_wgrad,
                   in_bwd_apply, in_bwd_reduce, instnorm_stats, zeros_scratch)
 
 
@@ -71,9 +71,9 @@ class DwConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, x_stats, weight, act, eps, want_stats=True):
         ks = tuple(weight.shape[2:])
-        wt = weight.detach().reshape(weight.shape[0], -1).t().contiguous().float()
+        wt = dw_weight(weight)              # the [C,1,kd,kh,kw] parameter itself: no per-call transposed copy
         x = x.contiguous()
-        y, y_stats = dwconv3d(x, wt, ks, x_stats=x_stats, act=act, want_stats=want_stats, eps=eps)
+        y, y_stats = dwconv3d(x, wt, ks, x_stats=x_stats, act=act, want_stats=want_stats, eps=eps, cmajor=True)
         ctx.save_for_backward(x, x_stats, wt)
         ctx.meta = (ks, act, weight.dtype, eps)
         if y_stats is not None:
@@ -86,14 +86,14 @@ class DwConvFn(torch.autograd.Function):
         ks, act, wdtype, eps = ctx.meta
         dy = dy.contiguous()
         C = x.shape[-1]
-        dw = dwconv3d_wgrad(x, dy, ks, x_stats=x_stats, act=act, eps=eps)
-        g, _ = dwconv3d(dy, wt, ks, flip=True)
+        dw = dwconv3d_wgrad(x, dy, ks, x_stats=x_stats, act=act, eps=eps, cmajor=True)
+        g, _ = dwconv3d(dy, wt, ks, flip=True, cmajor=True)
         if x_stats is not None:
             g2, bst = in_bwd_reduce(g, x, C, x_stats, act, eps=eps)
             dx = in_bwd_apply(g2, x, 0, C, x_stats, bst, eps=eps)
         else:
             dx = g
-        return dx, None, dw.t().reshape(C, 1, *ks).to(wdtype), None, None, None
+        return dx, None, dw.to(wdtype), None, None, None
 
 
 class SpaceToDepthFn(torch.autograd.Function):

@@ -647,23 +647,35 @@ class BiAttnFn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------- depthwise conv (MedFormer)
-def dwconv3d(x, w_taps, ksize, x_stats=None, act=ACT_NONE, flip=False, want_stats=False, eps=IN_EPS):
-    """x [B,D,H,W,C] channels-last; w_taps float32 [taps][C].  Returns (y, y_stats or None)."""
+def dwconv3d(x, w_taps, ksize, x_stats=None, act=ACT_NONE, flip=False, want_stats=False, eps=IN_EPS, cmajor=False):
+    """x [B,D,H,W,C] channels-last; w_taps float32 [taps][C], or with cmajor the module's own [C,1,kd,kh,kw] parameter
+    read in place (no transposed copy per call).  Returns (y, y_stats or None)."""
     _need_cuda(x)
     B, D, H, W, C = x.shape
     y = torch.empty_like(x)
     st = new_stats(B, C, x.device) if want_stats else None
-    call("b200seg_dwconv3d_fwd", x.data_ptr(), C, 0, _p(x_stats), eps, act, w_taps.data_ptr(), 1 if flip else 0,
+    call("b200seg_dwconv3d_fwd", x.data_ptr(), C, 0, _p(x_stats), eps, act, w_taps.data_ptr(), (1 if flip else 0) | (2 if cmajor else 0),
          y.data_ptr(), C, 0, _p(st), B, D, H, W, C, ksize[0], ksize[1], ksize[2], _dt(x), _stream())
     return y, st
 
 
-def dwconv3d_wgrad(x, dy, ksize, x_stats=None, act=ACT_NONE, eps=IN_EPS):
+def dwconv3d_wgrad(x, dy, ksize, x_stats=None, act=ACT_NONE, eps=IN_EPS, cmajor=False):
+    """dw as [taps][C], or with cmajor as [C,1,kd,kh,kw] — directly the parameter's gradient."""
     B, D, H, W, C = x.shape
-    dw = torch.zeros(ksize[0] * ksize[1] * ksize[2], C, dtype=torch.float32, device=x.device)
-    call("b200seg_dwconv3d_wgrad", x.data_ptr(), C, 0, _p(x_stats), eps, act, dy.data_ptr(), C, 0, dw.data_ptr(),
+    taps = ksize[0] * ksize[1] * ksize[2]
+    dw = torch.zeros((C, 1, *ksize) if cmajor else (taps, C), dtype=torch.float32, device=x.device)
+    call("b200seg_dwconv3d_wgrad", x.data_ptr(), C, 0, _p(x_stats), eps, act, dy.data_ptr(), C, 0, dw.data_ptr(), 1 if cmajor else 0,
          B, D, H, W, C, ksize[0], ksize[1], ksize[2], _dt(x), _stream())
     return dw
+
+
+def dw_weight(weight):
+    """The depthwise parameter as the kernels take it: in place when it is a contiguous fp32 tensor (every module of the
+    package), otherwise one fp32 copy.  Always [C,1,kd,kh,kw] (cmajor)."""
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    return w
 
 
 class DepthwiseConvFn(torch.autograd.Function):
@@ -673,9 +685,9 @@ class DepthwiseConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight):
         ks = tuple(weight.shape[2:])
-        wt = weight.detach().reshape(weight.shape[0], -1).t().contiguous().float()      # [taps][C]
+        wt = dw_weight(weight)
         x = x.contiguous()
-        y, _ = dwconv3d(x, wt, ks)
+        y, _ = dwconv3d(x, wt, ks, cmajor=True)
         ctx.save_for_backward(x, wt)
         ctx.ks = ks
         ctx.wdtype = weight.dtype
@@ -685,6 +697,6 @@ class DepthwiseConvFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, wt = ctx.saved_tensors
         dy = dy.contiguous()
-        dx, _ = dwconv3d(dy, wt, ctx.ks, flip=True)
-        dw = dwconv3d_wgrad(x, dy, ctx.ks)
-        return dx, dw.t().reshape(x.shape[-1], 1, *ctx.ks).to(ctx.wdtype)
+        dx, _ = dwconv3d(dy, wt, ctx.ks, flip=True, cmajor=True)
+        dw = dwconv3d_wgrad(x, dy, ctx.ks, cmajor=True)
+        return dx, dw.to(ctx.wdtype)

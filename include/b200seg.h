@@ -276,16 +276,19 @@ int b200seg_biattn_bwd(const void* fq, int fq_ld, int fq_coff, const void* fv, i
  * Depthwise 3-D convolution (groups == C), stride 1, "same" padding, no bias:
  * DepthwiseSeparableConv.depthwise conv_layers.py:135-143 (MedFormer attention
  * projections medformer_utils.py:30-31, MBConv).  Channels-last, C % 8 == 0,
- * kernel extents 1 or 3.  w: float[kd*kh*kw][C] (tap-major; flip != 0 reads the
- * taps reversed = the data-gradient of the same layer).  Optional fused prologue
- * a = act(IN(x)) from x_stats (NULL: raw x), optional IN sums of y (y_stats).
- * wgrad: dw[tap][c] += sum dy * a   (float, caller zeroes / accumulates).
+ * kernel extents 1 or 3.  flip is a bit set: bit 0 reads the taps reversed (= the
+ * data-gradient of the same layer); bit 1 says w is float[C][kd*kh*kw] — the
+ * module's own [C,1,kd,kh,kw] parameter, consumed in place — instead of the
+ * tap-major float[kd*kh*kw][C].  Optional fused prologue a = act(IN(x)) from
+ * x_stats (NULL: raw x), optional IN sums of y (y_stats).
+ * wgrad: dw += sum dy * a (float, caller zeroes / accumulates), laid out
+ * [tap][c] (dw_layout 0) or [c][tap] = the parameter's layout (dw_layout 1).
  * ------------------------------------------------------------------------- */
 int b200seg_dwconv3d_fwd(const void* x, int x_ld, int x_coff, const double* x_stats, float eps, int act,
                          const float* w, int flip, void* y, int y_ld, int y_coff, double* y_stats,
                          int B, int D, int H, int W, int C, int kd, int kh, int kw, int dtype, void* stream);
 int b200seg_dwconv3d_wgrad(const void* x, int x_ld, int x_coff, const double* x_stats, float eps, int act,
-                           const void* dy, int dy_ld, int dy_coff, float* dw,
+                           const void* dy, int dy_ld, int dy_coff, float* dw, int dw_layout,
                            int B, int D, int H, int W, int C, int kd, int kh, int kw, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------

@@ -27,26 +27,29 @@ def install(monkeypatch):
     for name in ("conv3d_fwd", "conv3d_wgrad", "in_bwd_apply", "in_bwd_reduce", "instnorm_stats", "copy_channels"):
         monkeypatch.setattr(mo, name, getattr(ops, name))
 
-    def _dw_weight(w_taps, ksize, flip):
-        C = w_taps.shape[1]
-        w = w_taps.t().reshape(C, 1, *ksize).double()
+    def _dw_weight(w_taps, ksize, flip, cmajor):
+        if cmajor:                                   # the module's own [C,1,kd,kh,kw] parameter
+            w = w_taps.reshape(-1, 1, *ksize).double()
+        else:
+            C = w_taps.shape[1]
+            w = w_taps.t().reshape(C, 1, *ksize).double()
         return w.flip(2, 3, 4) if flip else w
 
-    def dwconv3d(x, w_taps, ksize, x_stats=None, act=0, flip=False, want_stats=False, eps=ops.IN_EPS):
+    def dwconv3d(x, w_taps, ksize, x_stats=None, act=0, flip=False, want_stats=False, eps=ops.IN_EPS, cmajor=False):
         C = x.shape[-1]
         a = _ncdhw(x, 0, C)
         a = _normalise(a, x_stats, act, eps) if x_stats is not None else (F.relu(a) if act else a)
-        y = F.conv3d(a.double(), _dw_weight(w_taps, ksize, flip), padding=[k // 2 for k in ksize], groups=C)
+        y = F.conv3d(a.double(), _dw_weight(w_taps, ksize, flip, cmajor), padding=[k // 2 for k in ksize], groups=C)
         return _cl(y.to(x.dtype)), (_stats(y) if want_stats else None)
 
-    def dwconv3d_wgrad(x, dy, ksize, x_stats=None, act=0, eps=ops.IN_EPS):
+    def dwconv3d_wgrad(x, dy, ksize, x_stats=None, act=0, eps=ops.IN_EPS, cmajor=False):
         C = x.shape[-1]
         a = _ncdhw(x, 0, C)
         a = (_normalise(a, x_stats, act, eps) if x_stats is not None else (F.relu(a) if act else a)).double()
         w = torch.zeros(C, 1, *ksize, dtype=torch.float64, requires_grad=True)
         with torch.enable_grad():
             F.conv3d(a, w, padding=[k // 2 for k in ksize], groups=C).backward(_ncdhw(dy, 0, C).double())
-        return w.grad.reshape(C, -1).t().contiguous().float()
+        return w.grad.float() if cmajor else w.grad.reshape(C, -1).t().contiguous().float()
 
     def _core(fqv, mqv, heads):
         f = fqv.permute(0, 4, 1, 2, 3).double()

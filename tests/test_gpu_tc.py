@@ -88,3 +88,27 @@ def test_tc_wgrad_matches_direct_and_torch(Cin, Cout, k, shape, normed):
     w = torch.zeros(Cout, Cin, *k, device="cuda", requires_grad=True)
     F.conv3d(a, w, padding=[i // 2 for i in k]).backward(dy.float().permute(0, 4, 1, 2, 3))
     assert rel_err(dwt, w.grad) < 3e-3
+
+
+@pytest.mark.parametrize("Cin,Cout,k,shape", [(48, 144, (1, 1, 1), (1, 8, 16, 16)),        # qkv Linear of SwinUNETR stage 1
+                                              (192, 48, (1, 1, 1), (2, 4, 16, 8)),         # fc2
+                                              (768, 3072, (1, 1, 1), (1, 4, 4, 4)),        # fc1 of the last stage: > 512 output channels
+                                              (32, 24, (3, 3, 3), (1, 3, 16, 16))])
+def test_biased_wgrad_takes_tensor_cores(Cin, Cout, k, shape):
+    """A weight gradient WITH a bias gradient (every nn.Linear of SwinUNETR) = the column-sum pass + the tcgen05 kernel
+    (ALGO_AUTO), against the CUDA-core kernel that computes both (ALGO_DIRECT) and PyTorch."""
+    from b200seg import ops, _lib
+    B, D, H, W = shape
+    torch.manual_seed(13)
+    x = torch.randn(B, D, H, W, Cin, device="cuda").half()
+    dy = torch.randn(B, D, H, W, Cout, device="cuda").half()
+    c0 = _lib.launch_count
+    dwa, dba = ops.conv3d_wgrad(x, 0, Cin, None, ops.ACT_NONE, dy, 0, Cout, k, want_bias=True, algo=_lib.ALGO_AUTO)
+    dwd, dbd = ops.conv3d_wgrad(x, 0, Cin, None, ops.ACT_NONE, dy, 0, Cout, k, want_bias=True, algo=_lib.ALGO_DIRECT)
+    torch.cuda.synchronize()
+    assert rel_err(dwa, dwd) < 2e-3 and rel_err(dba, dbd) < 2e-3
+    w = torch.zeros(Cout, Cin, *k, device="cuda", requires_grad=True)
+    b = torch.zeros(Cout, device="cuda", requires_grad=True)
+    F.conv3d(x.float().permute(0, 4, 1, 2, 3), w, b, padding=[i // 2 for i in k]).backward(dy.float().permute(0, 4, 1, 2, 3))
+    assert rel_err(dwa, w.grad) < 3e-3 and rel_err(dba, b.grad) < 1e-3
+    assert not torch.equal(dwa, dwd)           # different kernels (split-K order), not the same code path twice
