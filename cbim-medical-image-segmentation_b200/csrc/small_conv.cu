@@ -274,24 +274,25 @@ __device__ __forceinline__ float col_sum16(float (&v)[16], int lane) {   // see 
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-// ---- stem forward: y[v][0..31] = sum_tap w[tap][co] * x[v+tap]  (Cin == 1, Cout == 32), + IN sums of the stored y.
-// One thread per voxel (64 B of output), weights in shared memory.  HBM-bound: writes 32 channels per voxel.
-template <typename T, int KD, int KH, int KW>
+// ---- stem forward: y[v][0..CO) = sum_tap w[tap][co] * x[v+tap]  (Cin == 1, CO = 16*NG in {32, 48, 64}), + IN sums of the
+// stored y.  One thread per voxel (2*CO bytes of output), weights in shared memory.  HBM-bound: writes CO channels per
+// voxel.  (32 = the UNet / MedFormer stem; 48 = SwinUNETR's encoder1 at feature_size 48, 3x3x3 and its 1x1x1 projection.)
+template <typename T, int KD, int KH, int KW, int NG>
 __global__ void __launch_bounds__(256)
 stem_fwd_kernel(ConvArgs a) {
-  constexpr int TAPS = KD * KH * KW;
-  __shared__ float s_w[TAPS][32];
-  __shared__ float s_red[8][32][2];
+  constexpr int TAPS = KD * KH * KW, CO = 16 * NG;
+  __shared__ float s_w[TAPS][CO];
+  __shared__ float s_red[8][CO][2];
   const int64_t V = (int64_t)a.D * a.H * a.W;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < TAPS * 32; i += 256) s_w[i / 32][i % 32] = Elem<T>::ld((const T*)a.w + i);   // packed [tap][co][1]
+  for (int i = threadIdx.x; i < TAPS * CO; i += 256) s_w[i / CO][i % CO] = Elem<T>::ld((const T*)a.w + i);   // packed [tap][co][1]
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const bool valid = v < V;
-  float acc[32];
+  float acc[CO];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  for (int c = 0; c < CO; ++c) acc[c] = 0.f;
   if (valid) {
     const int w0 = (int)(v % a.W); const int64_t t = v / a.W; const int h0 = (int)(t % a.H); const int d0 = (int)(t / a.H);
     const T* xb = (const T*)a.x + (int64_t)b * V * a.x_ld + a.x_coff;
@@ -307,31 +308,35 @@ stem_fwd_kernel(ConvArgs a) {
             xv = Elem<T>::ld(xb + (((int64_t)d * a.H + h) * a.W + w) * a.x_ld);
           const float* wt = s_w[(zd * KH + zh) * KW + zw];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) acc[c] = fmaf(xv, wt[c], acc[c]);
+          for (int c = 0; c < CO; ++c) acc[c] = fmaf(xv, wt[c], acc[c]);
         }
   }
-  float sq[32];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) { acc[c] = valid ? Elem<T>::round(acc[c]) : 0.f; sq[c] = acc[c] * acc[c]; }
+  for (int c = 0; c < CO; ++c) acc[c] = valid ? Elem<T>::round(acc[c]) : 0.f;
   if (valid) {
     T* yp = (T*)a.y + ((int64_t)b * V + v) * a.y_ld + a.y_coff;
 #pragma unroll
-    for (int c = 0; c < 32; c += 8) st8<T>(yp + c, reinterpret_cast<const float(&)[8]>(acc[c]));
+    for (int c = 0; c < CO; c += 8) st8<T>(yp + c, reinterpret_cast<const float(&)[8]>(acc[c]));
   }
   if (a.y_stats) {
-    const float u0 = col_sum16(reinterpret_cast<float(&)[16]>(acc[0]), lane), u1 = col_sum16(reinterpret_cast<float(&)[16]>(acc[16]), lane);
-    const float q0 = col_sum16(reinterpret_cast<float(&)[16]>(sq[0]), lane), q1 = col_sum16(reinterpret_cast<float(&)[16]>(sq[16]), lane);
-    if ((lane & 1) == 0) {
-      const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-      s_red[wid][col][0] = u0; s_red[wid][col][1] = q0; s_red[wid][16 + col][0] = u1; s_red[wid][16 + col][1] = q1;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      float sq[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) sq[c] = acc[16 * g + c] * acc[16 * g + c];
+      const float u = col_sum16(reinterpret_cast<float(&)[16]>(acc[16 * g]), lane), q = col_sum16(sq, lane);
+      if ((lane & 1) == 0) {
+        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        s_red[wid][16 * g + col][0] = u; s_red[wid][16 * g + col][1] = q;
+      }
     }
     __syncthreads();
-    if (threadIdx.x < 64) {
+    if (threadIdx.x < 2 * CO) {
       const int c = threadIdx.x >> 1, k = threadIdx.x & 1;
       double s = 0.0;
 #pragma unroll
       for (int w = 0; w < 8; ++w) s += (double)s_red[w][c][k];
-      atomicAdd(&a.y_stats[((int64_t)b * 32 + c) * 2 + k], s);
+      atomicAdd(&a.y_stats[((int64_t)b * CO + c) * 2 + k], s);
     }
   }
 }
@@ -395,10 +400,20 @@ int conv3d_fwd_small(const ConvArgs& a, int dtype, cudaStream_t st) {
   const int64_t V = (int64_t)a.D * a.H * a.W;
   const bool plain = !a.x_stats && !a.act && !a.res && !a.gx;
   const bool k133 = (a.kd == 1 && a.kh == 3 && a.kw == 3), k333 = (a.kd == 3 && a.kh == 3 && a.kw == 3);
-  if (plain && !a.bias && a.Cin == 1 && a.Cout == 32 && (k133 || k333) && (a.y_ld % 8 == 0) && (a.y_coff % 8 == 0)) {
+  const bool k111s = (a.kd == 1 && a.kh == 1 && a.kw == 1);
+  if (plain && !a.bias && a.Cin == 1 && (a.Cout == 32 || a.Cout == 48 || a.Cout == 64) && (k133 || k333 || k111s) && (a.y_ld % 8 == 0) &&
+      (a.y_coff % 8 == 0)) {
     dim3 grid(ceil_div(V, 256), a.B);
-    if (dtype == B200SEG_F16) { if (k133) stem_fwd_kernel<__half, 1, 3, 3><<<grid, 256, 0, st>>>(a); else stem_fwd_kernel<__half, 3, 3, 3><<<grid, 256, 0, st>>>(a); }
-    else { if (k133) stem_fwd_kernel<float, 1, 3, 3><<<grid, 256, 0, st>>>(a); else stem_fwd_kernel<float, 3, 3, 3><<<grid, 256, 0, st>>>(a); }
+#define STEM(TT, NG)                                                                   \
+  do {                                                                                 \
+    if (k133) stem_fwd_kernel<TT, 1, 3, 3, NG><<<grid, 256, 0, st>>>(a);               \
+    else if (k333) stem_fwd_kernel<TT, 3, 3, 3, NG><<<grid, 256, 0, st>>>(a);          \
+    else stem_fwd_kernel<TT, 1, 1, 1, NG><<<grid, 256, 0, st>>>(a);                    \
+  } while (0)
+#define STEM_T(TT) do { if (a.Cout == 32) STEM(TT, 2); else if (a.Cout == 48) STEM(TT, 3); else STEM(TT, 4); } while (0)
+    if (dtype == B200SEG_F16) STEM_T(__half); else STEM_T(float);
+#undef STEM_T
+#undef STEM
     B200_CHECK_LAUNCH("stem_fwd_kernel");
     return B200SEG_OK;
   }

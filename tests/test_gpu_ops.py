@@ -145,7 +145,8 @@ def test_small_wgrad_special_cases(ops, dtype, tol, Cin, Cout, k, normed, bias):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.float16, 3e-3)])
 @pytest.mark.parametrize("Cin,Cout,k,bias", [(1, 32, (1, 3, 3), False), (1, 32, (3, 3, 3), False), (32, 4, (1, 1, 1), True),
-                                             (4, 32, (1, 1, 1), False), (16, 12, (1, 1, 1), True)])
+                                             (4, 32, (1, 1, 1), False), (16, 12, (1, 1, 1), True),
+                                             (1, 48, (3, 3, 3), False), (1, 48, (1, 1, 1), False), (1, 64, (1, 3, 3), False)])
 def test_small_fwd_special_cases(ops, dtype, tol, Cin, Cout, k, bias):
     """The stem (Cin=1 -> 32) and few-channel 1x1x1 convs (classifier head fwd / dgrad) run HBM-bound special kernels."""
     torch.manual_seed(6)
