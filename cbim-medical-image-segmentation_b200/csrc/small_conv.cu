@@ -234,9 +234,11 @@ int conv3d_wgrad_small(const WgradArgs& a, int dtype, cudaStream_t st) {
   const int taps = a.kd * a.kh * a.kw;
   const int grid = B200SEG_NUM_SMS * kSmallGridPerSM;
   const bool k133 = (a.kd == 1 && a.kh == 3 && a.kw == 3), k333 = (a.kd == 3 && a.kh == 3 && a.kw == 3);
-  if (a.Cin == 1 && a.Cout <= 64 && (k133 || k333) && !a.x_stats && !a.act && !a.dbias) {
+  const bool k111 = taps == 1;         // the 1x1x1 projection of SwinUNETR's encoder1 residual block (Cin = 1)
+  if (a.Cin == 1 && a.Cout <= 64 && (k133 || k333 || k111) && !a.x_stats && !a.act && !a.dbias) {
     const int th = kWarpsPerBlock * 32;
-#define CIN1(TT, KDD, TWO_) wgrad_cin1_kernel<TT, KDD, 3, 3, TWO_><<<grid, th, 0, st>>>(a)
+#define CIN1(TT, KDD, TWO_) do { if (k111) wgrad_cin1_kernel<TT, 1, 1, 1, TWO_><<<grid, th, 0, st>>>(a); \
+                                 else wgrad_cin1_kernel<TT, KDD, 3, 3, TWO_><<<grid, th, 0, st>>>(a); } while (0)
 #define CIN1_T(TT) do { if (a.Cout > 32) { if (k133) CIN1(TT, 1, true); else CIN1(TT, 3, true); } \
                         else { if (k133) CIN1(TT, 1, false); else CIN1(TT, 3, false); } } while (0)
     if (dtype == B200SEG_F16) CIN1_T(__half); else CIN1_T(float);

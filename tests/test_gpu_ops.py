@@ -123,7 +123,7 @@ def test_upsample_cat(ops, dtype, tol, shp):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.float16, 2e-3)])
 @pytest.mark.parametrize("Cin,Cout,k,normed,bias", [(1, 32, (1, 3, 3), False, False), (1, 32, (3, 3, 3), False, False),
-                                                    (1, 48, (3, 3, 3), False, False), (32, 4, (1, 1, 1), False, True),
+                                                    (1, 48, (3, 3, 3), False, False), (1, 48, (1, 1, 1), False, False), (32, 4, (1, 1, 1), False, True),
                                                     (64, 14, (1, 1, 1), True, True)])
 def test_small_wgrad_special_cases(ops, dtype, tol, Cin, Cout, k, normed, bias):
     """AUTO routes the Cin=1 stem and the 1x1x1 few-class head to the HBM-bound special kernels (small_conv.cu)."""
