@@ -164,18 +164,20 @@ def config_of(args, wl, world, peak_mem=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions (B200_PROFILING.md).  The poller is started
+    ahead of time (nvidia-smi needs ~0.2 s before its first line) and every line is stamped on arrival; only lines that
+    arrived inside a `window()` — the device-resident and the end-to-end timed loops — are summarised."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.windows = [], None, index, []
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -185,7 +187,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window(self):
+        sampler = self
+
+        class _W:
+            def __enter__(self_w):
+                self_w.t0 = time.time()
+
+            def __exit__(self_w, *a):
+                sampler.windows.append((self_w.t0, time.time()))
+        return _W()
 
     def __exit__(self, *a):
         if self.proc:
@@ -198,7 +211,10 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for stamp, r in self.rows:
+            # a line printed at time t describes the GPU a few ms earlier: accept up to 60 ms past the window's end
+            if self.windows and not any(a <= stamp <= b + 0.06 for a, b in self.windows):
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -485,21 +501,23 @@ def run_b200(args, wl):
             ms = t.item()
         return ms
 
-    for _ in range(max(args.warmup, 3)):
-        ts(img, lab)
-    torch.cuda.synchronize()
-    c0 = _lib.launch_count
-    with ClockSampler(local) as cs:
-        ms = timed(lambda: ts(img, lab), args.steps)
-    launches = (_lib.launch_count - c0) // args.steps
-    clocks = cs.summary()
-
     def e2e_step():
         i = img_h.to(dev, non_blocking=True)                 # train_ddp.py:173-174
         l = lab_h.to(dev, non_blocking=True)
         return ts(i, l).item()                               # train_ddp.py:213
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+
+    with ClockSampler(local) as cs:                          # polling starts during the warm-up; only the two timed loops count
+        for _ in range(max(args.warmup, 3)):
+            ts(img, lab)
+        torch.cuda.synchronize()
+        c0 = _lib.launch_count
+        with cs.window():
+            ms = timed(lambda: ts(img, lab), args.steps)
+        launches = (_lib.launch_count - c0) // args.steps
+        e2e_step()
+        with cs.window():
+            ms_e2e = timed(e2e_step, args.steps)
+    clocks = cs.summary()
     peak_mem = torch.cuda.max_memory_allocated() / 2**30
 
     out = {"metric": metric_of(wl), "value": world * vox * args.steps / (ms / 1e3), "unit": "voxels/s", "n_gpus": world,
