@@ -53,10 +53,13 @@ struct WgParams {
   int tmem_cols;
   int ts;                                  // A operand (dy^T) is fed from TENSOR MEMORY (narrow Cin: see file header)
   int use_tma;                             // operand tiles are staged by tensor-TMA boxes (else 16-byte cp.async)
+  int dy_rows;                             // TS mode only: the dy tile arrives by tensor-TMA as 128-byte swizzled ROWS (see wg_loader)
   int smem_bar_off, smem_norm_off;
   alignas(64) CUtensorMap tm_dy;           // dy  as {8 ch, w, h, plane, b*D+d}
   alignas(64) CUtensorMap tm_x;            // x   likewise
+  alignas(64) CUtensorMap tm_dyrow;        // dy  as {channel, w, h, b*D+d}, box {64, 8, 16, 1}, SWIZZLE_128B
 };
+constexpr int kDyRowBox = TH * TW * 128;   // bytes of one 64-channel row-image box (128 voxels x 128 B)
 
 struct Job { int co_tile, ci_tile, zd, grp, tap0, ntaps, s; };
 __device__ __forceinline__ Job decode_job(const WgParams& p, int bid) {
@@ -127,16 +130,28 @@ __device__ __forceinline__ void wg_loader(const WgParams& p, const Job& job, uin
   const bool xform = (p.x_stats != nullptr) || (p.act != 0);
   auto FULL = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   auto EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(p.NS + i); };
+  auto LAND = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.NS + 5 + i); };
   VtWalk vw; vw.init(p);
   VtCursor ci, cd;
   ci.init(vw, p, job.s, zoff); cd.init(vw, p, job.s, zoff);
   Ring ri, rd; ri.init(p.NS); rd.init(p.NS);
+  const int dy_rows = p.dy_rows, nbox = co_real / 64;
 
   auto issue = [&]() {
     mbar_wait(EMPTY(ri.idx), ri.phase ^ 1, 1);
     const uint32_t sdy = smem_u32(smem + ri.idx * p.stage_bytes);
     const uint32_t sa = sdy + (uint32_t)p.dy_bytes;
-    if (act_d) {
+    if (dy_rows) {
+      // dy is raw and (in TS mode) only ever read by the transposer warps: one thread hands it to the TMA unit as one or
+      // two {64 ch, 8, 16} boxes of 128-byte swizzled rows (ragged tiles zero-filled) — 32 KB per stage that no longer
+      // pass through 2 048 16-byte cp.async requests of the loader warps (role profile: the loaders' issue loop,
+      // 3 700 cycles per stage, was what the MMA warp waited for).  Completion is signalled on the stage's LAND barrier.
+      if (lt == 0) {
+        mbar_arrive_expect_tx(LAND(ri.idx), (uint32_t)(nbox * kDyRowBox));
+        for (int hb = 0; hb < nbox; ++hb)
+          tma_load_4d(sdy + (uint32_t)(hb * kDyRowBox), &p.tm_dyrow, LAND(ri.idx), co0 + hb * 64, ci.w0(), ci.h0(), ci.b * p.D + ci.d);
+      }
+    } else if (act_d) {
       const __half* src = p.dy + ((int64_t)(ci.b * p.D + ci.d) * p.H * p.W) * p.dy_ld + p.dy_coff + co0 + c8_d * 8;
       const uint32_t dst = sdy + (uint32_t)(c8_d * p.dy_plane);
 #pragma unroll 4
@@ -424,10 +439,14 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
       const uint32_t tmem_a0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(gmax * p.NTC);
       const int col = warp * 32 + lane;         // this thread's GEMM row = output channel within the M tile
       const bool live = warp * 32 < co_real;     // warp-uniform
-      const uint8_t* lane_base = smem + (col >> 3) * p.dy_plane + (col & 7) * 2;
+      const int dy_rows = p.dy_rows;
+      // plane image: element (co, voxel) at plane co/8, slot voxel, channel co%8; row image: 128-byte row per voxel, its
+      // 16-byte chunk (co%64)/8 stored at chunk position ((co%64)/8) ^ (voxel & 7) (SWIZZLE_128B), one 16 KB box per 64 co
+      const uint8_t* lane_base = dy_rows ? smem + (col >> 6) * kDyRowBox + (col & 7) * 2 : smem + (col >> 3) * p.dy_plane + (col & 7) * 2;
+      const int rchunk = (col & 63) >> 3;
       int idx = 0; uint32_t phase = 0; int it = 0;
       for (; c.valid(p); c.next(vw, p, zoff), ++it) {
-        mbar_wait(p.use_tma ? LAND(idx) : FULL(idx), phase, 4);       // dy is never transformed: landed is enough
+        mbar_wait((p.use_tma || dy_rows) ? LAND(idx) : FULL(idx), phase, 4);       // dy is never transformed: landed is enough
         mbar_wait(A_FREE(it & 1), (uint32_t)(((it >> 1) & 1) ^ 1), 5);
         if (live) {
           TC_PROF(16);
@@ -439,8 +458,16 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
             uint32_t w[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const uint32_t lo = *reinterpret_cast<const uint16_t*>(src + (16 * kb + 2 * i) * 16);
-              const uint32_t hi = *reinterpret_cast<const uint16_t*>(src + (16 * kb + 2 * i + 1) * 16);
+              uint32_t lo, hi;
+              if (dy_rows) {
+                // voxels 16kb+2i and +1: same 8-row swizzle group (2i and 2i+1 < 16 never straddle it), (v & 7) = (2i)&7, +1
+                const int v = 16 * kb + 2 * i;
+                lo = *reinterpret_cast<const uint16_t*>(src + v * 128 + ((rchunk ^ (v & 7)) << 4));
+                hi = *reinterpret_cast<const uint16_t*>(src + (v + 1) * 128 + ((rchunk ^ ((v + 1) & 7)) << 4));
+              } else {
+                lo = *reinterpret_cast<const uint16_t*>(src + (16 * kb + 2 * i) * 16);
+                hi = *reinterpret_cast<const uint16_t*>(src + (16 * kb + 2 * i + 1) * 16);
+              }
               w[i] = lo | (hi << 16);
             }
             tmem_st8(dst + (uint32_t)(kb * 8), w);
@@ -494,7 +521,7 @@ int pick_ntc(int Cin) {
   return 0;
 }
 
-bool fill_params(const WgradArgs& a, WgParams& p, bool tma = false) {
+bool fill_params(const WgradArgs& a, WgParams& p, bool tma = false, bool dyrows = false) {
   memset(&p, 0, sizeof(p));
   p.B = a.B; p.D = a.D; p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout; p.kd = a.kd; p.kh = a.kh; p.kw = a.kw;
   p.NTC = pick_ntc(a.Cin);
@@ -518,6 +545,14 @@ bool fill_params(const WgradArgs& a, WgParams& p, bool tma = false) {
   // them falls on the `a` tile / the next stage / the tail slack (allocated below), whose values feed rows never read
   const int co_max = a.Cout < MT ? a.Cout : MT;
   p.dy_bytes = (co_max / 8) * p.dy_plane; p.dy_bytes = (p.dy_bytes + 127) / 128 * 128;
+  if (dyrows) {
+    // row image of dy (TS mode, output-channel tiles that are multiples of 64): 16 KB boxes at 1024-byte aligned
+    // addresses (SWIZZLE_128B is a function of the shared-memory address), so every stage is a multiple of 1 KB
+    if (!p.ts || p.use_tma || (a.Cout % 64)) return false;
+    p.dy_rows = 1;
+    p.dy_bytes = (co_max / 64) * kDyRowBox;
+    p.a_bytes = (p.a_bytes + 1023) / 1024 * 1024;
+  }
   p.stage_bytes = p.a_bytes + p.dy_bytes;
   const int norm_bytes = a.B * p.NTC * 8;
   const int budget = 227 * 1024 - 2048 - 16 * p.dy_plane - norm_bytes;
@@ -582,6 +617,17 @@ int conv3d_wgrad_tc(const WgradArgs& a, int dtype, void* /*workspace*/, size_t /
       p.x_stats = a.x_stats; p.eps = a.eps; p.act = a.act;
       p.dy = reinterpret_cast<const __half*>(a.dy); p.dy_ld = a.dy_ld; p.dy_coff = a.dy_coff;
       p.dw = a.dw;
+    }
+  }
+  // TS-mode layers with 64-multiple output-channel tiles: dy by tensor-TMA as swizzled rows (B200SEG_WGRAD_DYROWS=0: A/B switch)
+  if (!p.use_tma && p.ts && a.Cout % 64 == 0) {
+    const char* e = getenv("B200SEG_WGRAD_DYROWS");
+    WgParams q;
+    if (!(e && e[0] == '0') && fill_params(a, q, false, true) &&
+        b200seg_make_row_tmap(&q.tm_dyrow, a.dy, a.dy_ld, a.dy_coff, a.Cout, 64, a.B * a.D, a.H, a.W, TW, TH)) {
+      q.x = p.x; q.x_ld = p.x_ld; q.x_coff = p.x_coff; q.x_stats = p.x_stats; q.eps = p.eps; q.act = p.act;
+      q.dy = p.dy; q.dy_ld = p.dy_ld; q.dy_coff = p.dy_coff; q.dw = p.dw;
+      p = q;
     }
   }
   const int64_t jobs = (int64_t)p.co_tiles * p.ci_tiles * a.kd * p.ngroups;
