@@ -54,7 +54,8 @@ static inline bool b200seg_make_act_tmap(CUtensorMap* m, const void* base_fp16, 
 static inline bool b200seg_make_row_tmap(CUtensorMap* m, const void* base_fp16, int ld, int coff, int C, int KC, int BD, int H, int W,
                                          int box_w, int box_h) {
   b200seg_encode_tiled_fn enc = b200seg_encode_tiled();
-  if (!enc || (KC != 32 && KC != 64) || (C % KC) || (ld % 8) || (coff % 8)) return false;
+  // C need not be a multiple of KC: channels of a box beyond the tensor's extent are zero-filled like any out-of-range element
+  if (!enc || (KC != 32 && KC != 64) || (C % 8) || (ld % 8) || (coff % 8)) return false;
   const char* base = reinterpret_cast<const char*>(base_fp16) + (size_t)coff * 2;
   if (reinterpret_cast<uintptr_t>(base) & 15) return false;
   if (box_w > 256 || box_h > 256) return false;

@@ -135,7 +135,7 @@ __device__ __forceinline__ void wg_loader(const WgParams& p, const Job& job, uin
   VtCursor ci, cd;
   ci.init(vw, p, job.s, zoff); cd.init(vw, p, job.s, zoff);
   Ring ri, rd; ri.init(p.NS); rd.init(p.NS);
-  const int dy_rows = p.dy_rows, nbox = co_real / 64;
+  const int dy_rows = p.dy_rows, nbox = (co_real + 63) / 64;       // a 32- / 48-channel tile is one box whose upper channels are zero-filled
 
   auto issue = [&]() {
     mbar_wait(EMPTY(ri.idx), ri.phase ^ 1, 1);
@@ -548,9 +548,9 @@ bool fill_params(const WgradArgs& a, WgParams& p, bool tma = false, bool dyrows 
   if (dyrows) {
     // row image of dy (TS mode, output-channel tiles that are multiples of 64): 16 KB boxes at 1024-byte aligned
     // addresses (SWIZZLE_128B is a function of the shared-memory address), so every stage is a multiple of 1 KB
-    if (!p.ts || p.use_tma || (a.Cout % 64)) return false;
+    if (!p.ts || p.use_tma) return false;
     p.dy_rows = 1;
-    p.dy_bytes = (co_max / 64) * kDyRowBox;
+    p.dy_bytes = ((co_max + 63) / 64) * kDyRowBox;
     p.a_bytes = (p.a_bytes + 1023) / 1024 * 1024;
   }
   p.stage_bytes = p.a_bytes + p.dy_bytes;
@@ -619,8 +619,8 @@ int conv3d_wgrad_tc(const WgradArgs& a, int dtype, void* /*workspace*/, size_t /
       p.dw = a.dw;
     }
   }
-  // TS-mode layers with 64-multiple output-channel tiles: dy by tensor-TMA as swizzled rows (B200SEG_WGRAD_DYROWS=0: A/B switch)
-  if (!p.use_tma && p.ts && a.Cout % 64 == 0) {
+  // TS-mode layers: dy by tensor-TMA as swizzled rows (B200SEG_WGRAD_DYROWS=0: A/B switch)
+  if (!p.use_tma && p.ts) {
     const char* e = getenv("B200SEG_WGRAD_DYROWS");
     WgParams q;
     if (!(e && e[0] == '0') && fill_params(a, q, false, true) &&
