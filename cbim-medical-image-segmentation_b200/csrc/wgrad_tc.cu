@@ -371,7 +371,13 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
       const uint32_t dy_lbo = 128u, dy_sbo = (uint32_t)p.dy_plane;
       const uint32_t a_lbo = (uint32_t)p.HALO_W * 16u, a_sbo = (uint32_t)p.a_plane;
       // lean issue loop (this one thread feeds the tensor core): descriptor templates + constant adds
-      const uint64_t dy_tmpl = make_desc(0, dy_lbo, dy_sbo), a_tmpl = make_desc(0, a_lbo, a_sbo);
+      // dy as the A operand read from shared memory (non-TS mode): plane image = MN-major no-swizzle core matrices; row
+      // image (dy_rows) = the canonical MN-major SWIZZLE_128B operand — lbo = pitch of the 64-channel blocks (one TMA box
+      // each), sbo = pitch of the 8-voxel row groups (tools/umma_probe.cu, "mn=1 A=SW128": validated on hardware)
+      const int dy_rows = p.dy_rows;
+      const uint64_t dy_tmpl = dy_rows ? make_desc_sw(0, (uint32_t)kDyRowBox, 1024u, 2u) : make_desc(0, dy_lbo, dy_sbo);
+      const uint64_t dy_kstep = dy_rows ? (uint64_t)((16 * 128) >> 4) : 16;    // 16 voxels: 16 rows of 128 B / two 128-byte voxel groups per plane
+      const uint64_t a_tmpl = make_desc(0, a_lbo, a_sbo);
       const uint32_t a_kstep = (2u * (uint32_t)p.HALO_W * 16u) >> 4;    // two voxel rows per K=16 step
       const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, dy16 = (uint32_t)p.dy_bytes >> 4;
       const uint32_t smem16 = smem_u32(smem) >> 4;
@@ -390,6 +396,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
       for (; c.valid(p); c.next(vw, p, zoff), ++it) {
         mbar_wait_nocall(ready0 + 8u * (uint32_t)idx, phase, 9);
         if (ts) mbar_wait_nocall(A_READY(it & 1), (uint32_t)((it >> 1) & 1), 10);
+        else if (dy_rows) mbar_wait_nocall(LAND(idx), phase, 10);      // the MMAs read the TMA-landed dy rows themselves
         tc_fence_after();
         const uint64_t da0 = dy_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16);
         uint64_t db_tap = a_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16 + dy16 + (uint32_t)(zh0 * HALO_W + zw0));
@@ -408,7 +415,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
 #pragma unroll
             for (int j = 0; j < (TH * TW) / 16; ++j) {
               if (elected) umma_f16(tmem_d, da, db, idesc, (accumulate | (uint32_t)(j > 0)));
-              da += 16;            // 2 voxel rows of the dy tile = 256 B
+              da += dy_kstep;      // plane image: 2 voxel rows of the dy tile = 256 B; row image: 16 rows = 2 KB
               db += a_kstep;
             }
           }
@@ -548,7 +555,7 @@ bool fill_params(const WgradArgs& a, WgParams& p, bool tma = false, bool dyrows 
   if (dyrows) {
     // row image of dy (TS mode, output-channel tiles that are multiples of 64): 16 KB boxes at 1024-byte aligned
     // addresses (SWIZZLE_128B is a function of the shared-memory address), so every stage is a multiple of 1 KB
-    if (!p.ts || p.use_tma) return false;
+    if (p.use_tma) return false;
     p.dy_rows = 1;
     p.dy_bytes = ((co_max + 63) / 64) * kDyRowBox;
     p.a_bytes = (p.a_bytes + 1023) / 1024 * 1024;
@@ -619,8 +626,8 @@ int conv3d_wgrad_tc(const WgradArgs& a, int dtype, void* /*workspace*/, size_t /
       p.dw = a.dw;
     }
   }
-  // TS-mode layers: dy by tensor-TMA as swizzled rows (B200SEG_WGRAD_DYROWS=0: A/B switch)
-  if (!p.use_tma && p.ts) {
+  // dy by tensor-TMA as swizzled rows (B200SEG_WGRAD_DYROWS=0: A/B switch)
+  if (!p.use_tma) {
     const char* e = getenv("B200SEG_WGRAD_DYROWS");
     WgParams q;
     if (!(e && e[0] == '0') && fill_params(a, q, false, true) &&
