@@ -53,11 +53,13 @@ struct WgParams {
   int tmem_cols;
   int ts;                                  // A operand (dy^T) is fed from TENSOR MEMORY (narrow Cin: see file header)
   int use_tma;                             // operand tiles are staged by tensor-TMA boxes (else 16-byte cp.async)
-  int dy_rows;                             // TS mode only: the dy tile arrives by tensor-TMA as 128-byte swizzled ROWS (see wg_loader)
+  int dy_rows;                             // the dy tile arrives by tensor-TMA as 128-byte swizzled ROWS (see wg_loader)
+  int a_rows;                              // NTC == 64: so does the halo tile of x (one {64, HALO_W, HALO_H} box), transformed in place
   int smem_bar_off, smem_norm_off;
   alignas(64) CUtensorMap tm_dy;           // dy  as {8 ch, w, h, plane, b*D+d}
   alignas(64) CUtensorMap tm_x;            // x   likewise
   alignas(64) CUtensorMap tm_dyrow;        // dy  as {channel, w, h, b*D+d}, box {64, 8, 16, 1}, SWIZZLE_128B
+  alignas(64) CUtensorMap tm_arow;         // x   as {channel, w, h, b*D+d}, box {64, HALO_W, HALO_H, 1}, SWIZZLE_128B
 };
 constexpr int kDyRowBox = TH * TW * 128;   // bytes of one 64-channel row-image box (128 voxels x 128 B)
 
@@ -310,6 +312,85 @@ __device__ __forceinline__ void wg_loader_tma(const WgParams& p, const Job& job,
   }
 }
 
+// ---- row-image staging of BOTH operands (NTC == 64): one loader thread hands the stage to the TMA unit — the dy boxes and one
+// {64 ch, HALO_W, HALO_H} box of x, each voxel a 128-byte SWIZZLE_128B row, conv padding and ragged tiles zero-filled — and
+// the loader warps only apply InstanceNorm / activation to the landed halo tile: thread = fixed 8-channel chunk c (its
+// constants stay in registers), the chunk of voxel row v sits at chunk position c ^ (v & 7).  No cp.async at all: the
+// 3 700-cycle issue loop of the role profile is gone, what remains per stage is the ~1 600-cycle transform.
+__device__ __forceinline__ void wg_loader_rows(const WgParams& p, const Job& job, uint8_t* smem, const float2* s_norm, uint32_t bar0) {
+  const int lt = threadIdx.x - kLoadWarp0 * 32;
+  const int ph = p.kh / 2, pw = p.kw / 2, zoff = job.zd - p.kd / 2;
+  const int co0 = job.co_tile * MT, ci0 = job.ci_tile * p.NTC;
+  const int co_real = min(MT, p.Cout - co0), nbox = (co_real + 63) / 64;
+  const bool xform = (p.x_stats != nullptr) || (p.act != 0);
+  auto FULL = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  auto EMPTY = [&](int i) { return bar0 + 8u * (uint32_t)(p.NS + i); };
+  auto LAND = [&](int i) { return bar0 + 8u * (uint32_t)(2 * p.NS + 5 + i); };
+  VtWalk vw; vw.init(p);
+  const uint32_t stage_tx = (uint32_t)(nbox * kDyRowBox + p.nvox_h * 128);
+  constexpr int cpv = 8;                                   // 16-byte chunks per 128-byte row
+  const int vstep = kLoadThreads / cpv;                    // 32 voxel rows per pass
+  const int c8 = lt % cpv, v0 = lt / cpv;
+  const int sh = vstep / p.HALO_W, sw = vstep % p.HALO_W;
+  const int hh0 = v0 / p.HALO_W, ww0 = v0 % p.HALO_W;
+  const int act = p.act;
+  VtCursor ci, cd;
+  ci.init(vw, p, job.s, zoff); cd.init(vw, p, job.s, zoff);
+  Ring ri, rd; ri.init(p.NS); rd.init(p.NS);
+  int ahead = 0;
+  float sc[8], sf[8];
+  int norm_b = -1;
+  while (cd.valid(p)) {
+    if (lt == 0) {                 // run ahead as far as the ring has free slots; block only when nothing is in flight
+      while (ci.valid(p) && ahead < p.NS) {
+        if (!mbar_test_wait(EMPTY(ri.idx), ri.phase ^ 1)) { if (ahead > 0) break; mbar_wait(EMPTY(ri.idx), ri.phase ^ 1, 1); }
+        const uint32_t sdy = smem_u32(smem + ri.idx * p.stage_bytes);
+        mbar_arrive_expect_tx(LAND(ri.idx), stage_tx);
+        for (int hb = 0; hb < nbox; ++hb)
+          tma_load_4d(sdy + (uint32_t)(hb * kDyRowBox), &p.tm_dyrow, LAND(ri.idx), co0 + hb * 64, ci.w0(), ci.h0(), ci.b * p.D + ci.d);
+        tma_load_4d(sdy + (uint32_t)p.dy_bytes, &p.tm_arow, LAND(ri.idx), ci0, ci.w0() - pw, ci.h0() - ph, ci.b * p.D + ci.din);
+        ri.advance(); ci.next(vw, p, zoff); ++ahead;
+      }
+    }
+    mbar_wait(LAND(rd.idx), rd.phase, 7);
+    if (xform) {
+      TC_PROF(12);
+      if (cd.b != norm_b) {
+        norm_b = cd.b;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 mr = s_norm[cd.b * p.NTC + c8 * 8 + j];
+          sc[j] = mr.y; sf[j] = -mr.x * mr.y;
+        }
+      }
+      uint8_t* sp = smem + rd.idx * p.stage_bytes + p.dy_bytes;
+      int hh = hh0, ww = ww0;
+#pragma unroll 2
+      for (int v = v0; v < p.nvox_h; v += vstep) {
+        const int h = cd.h0() - ph + hh, w = cd.w0() - pw + ww;
+        if ((unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W) {      // zero-filled padding voxels stay zero
+          uint4* q = reinterpret_cast<uint4*>(sp + v * 128 + ((c8 ^ (v & 7)) << 4));
+          uint4 raw = *q;
+          __half2* hv = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f = __half22float2(hv[j]);
+            f.x = act_apply(fmaf(f.x, sc[2 * j], sf[2 * j]), act); f.y = act_apply(fmaf(f.y, sc[2 * j + 1], sf[2 * j + 1]), act);
+            hv[j] = __floats2half2_rn(f.x, f.y);
+          }
+          *q = raw;
+        }
+        hh += sh; ww += sw;
+        if (ww >= p.HALO_W) { ww -= p.HALO_W; ++hh; }
+      }
+    }
+    fence_proxy_async();
+    mbar_arrive(FULL(rd.idx));
+    rd.advance(); cd.next(vw, p, zoff);
+    if (lt == 0) --ahead;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -358,7 +439,8 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
 
   if (warp >= kLoadWarp0 && warp < kMmaWarp) {
     // =========================== LOADERS ===========================
-    if (p.use_tma) wg_loader_tma(p, job, smem, s_norm, bar0);
+    if (p.a_rows) wg_loader_rows(p, job, smem, s_norm, bar0);
+    else if (p.use_tma) wg_loader_tma(p, job, smem, s_norm, bar0);
     else if (p.prefetch >= 3) wg_loader<3>(p, job, smem, s_norm, bar0);
     else if (p.prefetch == 2) wg_loader<2>(p, job, smem, s_norm, bar0);
     else wg_loader<1>(p, job, smem, s_norm, bar0);
@@ -377,8 +459,13 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
       const int dy_rows = p.dy_rows;
       const uint64_t dy_tmpl = dy_rows ? make_desc_sw(0, (uint32_t)kDyRowBox, 1024u, 2u) : make_desc(0, dy_lbo, dy_sbo);
       const uint64_t dy_kstep = dy_rows ? (uint64_t)((16 * 128) >> 4) : 16;    // 16 voxels: 16 rows of 128 B / two 128-byte voxel groups per plane
-      const uint64_t a_tmpl = make_desc(0, a_lbo, a_sbo);
-      const uint32_t a_kstep = (2u * (uint32_t)p.HALO_W * 16u) >> 4;    // two voxel rows per K=16 step
+      // x halo tile as the B operand: plane image (tap = start shifted by whole 16-byte voxel slots) or row image
+      // (MN-major SWIZZLE_128B, tap = start shifted by whole 128-byte rows, 8-row groups HALO_W rows apart: the
+      // "shift / gw = 10" cases of tools/umma_probe.cu)
+      const int a_rows = p.a_rows;
+      const uint32_t vunit = a_rows ? 8u : 1u;                  // 16-byte units per voxel step of the start address
+      const uint64_t a_tmpl = a_rows ? make_desc_sw(0, 16384u, (uint32_t)p.HALO_W * 128u, 2u) : make_desc(0, a_lbo, a_sbo);
+      const uint32_t a_kstep = (2u * (uint32_t)p.HALO_W * 16u * (p.a_rows ? 8u : 1u)) >> 4;    // two halo rows of voxels per K=16 step
       const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, dy16 = (uint32_t)p.dy_bytes >> 4;
       const uint32_t smem16 = smem_u32(smem) >> 4;
       const int zh0 = job.tap0 / p.kw, zw0 = job.tap0 % p.kw;
@@ -399,7 +486,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
         else if (dy_rows) mbar_wait_nocall(LAND(idx), phase, 10);      // the MMAs read the TMA-landed dy rows themselves
         tc_fence_after();
         const uint64_t da0 = dy_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16);
-        uint64_t db_tap = a_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16 + dy16 + (uint32_t)(zh0 * HALO_W + zw0));
+        uint64_t db_tap = a_tmpl + (uint64_t)(smem16 + (uint32_t)idx * stage16 + dy16 + (uint32_t)(zh0 * HALO_W + zw0) * vunit);
         const uint32_t ta0 = tmem_a0 + (uint32_t)((it & 1) * 64);
         int zw = zw0;
         uint32_t tmem_d = tmem_u;
@@ -421,7 +508,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p) {
           }
           tmem_d += (uint32_t)NTC;
           // next in-plane tap: one voxel to the right, or wrap to the next halo row
-          if (++zw == kw) { zw = 0; db_tap += (uint64_t)(HALO_W - (kw - 1)); } else db_tap += 1;
+          if (++zw == kw) { zw = 0; db_tap += (uint64_t)((uint32_t)(HALO_W - (kw - 1)) * vunit); } else db_tap += vunit;
         }
         accumulate = 1;
         if (elected) {
@@ -528,7 +615,7 @@ int pick_ntc(int Cin) {
   return 0;
 }
 
-bool fill_params(const WgradArgs& a, WgParams& p, bool tma = false, bool dyrows = false) {
+bool fill_params(const WgradArgs& a, WgParams& p, bool tma = false, bool dyrows = false, bool arows = false) {
   memset(&p, 0, sizeof(p));
   p.B = a.B; p.D = a.D; p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout; p.kd = a.kd; p.kh = a.kh; p.kw = a.kw;
   p.NTC = pick_ntc(a.Cin);
@@ -559,6 +646,11 @@ bool fill_params(const WgradArgs& a, WgParams& p, bool tma = false, bool dyrows 
     p.dy_rows = 1;
     p.dy_bytes = ((co_max + 63) / 64) * kDyRowBox;
     p.a_bytes = (p.a_bytes + 1023) / 1024 * 1024;
+    if (arows) {
+      if (p.NTC != 64) return false;
+      p.a_rows = 1;
+      p.a_bytes = (p.nvox_h * 128 + 1023) / 1024 * 1024;
+    }
   }
   p.stage_bytes = p.a_bytes + p.dy_bytes;
   const int norm_bytes = a.B * p.NTC * 8;
@@ -630,8 +722,18 @@ int conv3d_wgrad_tc(const WgradArgs& a, int dtype, void* /*workspace*/, size_t /
   if (!p.use_tma) {
     const char* e = getenv("B200SEG_WGRAD_DYROWS");
     WgParams q;
-    if (!(e && e[0] == '0') && fill_params(a, q, false, true) &&
-        b200seg_make_row_tmap(&q.tm_dyrow, a.dy, a.dy_ld, a.dy_coff, a.Cout, 64, a.B * a.D, a.H, a.W, TW, TH)) {
+    const char* ea = getenv("B200SEG_WGRAD_AROWS");
+    bool done = false;
+    // both operands as rows when the Cin tile is 64 wide (A/B, profiles/r2g_layer_times_*: 128->128 k333 233 -> 181 us,
+    // 384->256 1170 -> 963 us); B200SEG_WGRAD_AROWS=0 keeps the cp.async plane image for x
+    if (!(e && e[0] == '0') && !(ea && ea[0] == '0') && fill_params(a, q, false, true, true) &&
+        b200seg_make_row_tmap(&q.tm_dyrow, a.dy, a.dy_ld, a.dy_coff, a.Cout, 64, a.B * a.D, a.H, a.W, TW, TH) &&
+        b200seg_make_row_tmap(&q.tm_arow, a.x, a.x_ld, a.x_coff, a.Cin, 64, a.B * a.D, a.H, a.W, q.HALO_W, q.HALO_H))
+      done = true;
+    if (!done && !(e && e[0] == '0') && fill_params(a, q, false, true) &&
+        b200seg_make_row_tmap(&q.tm_dyrow, a.dy, a.dy_ld, a.dy_coff, a.Cout, 64, a.B * a.D, a.H, a.W, TW, TH))
+      done = true;
+    if (done) {
       q.x = p.x; q.x_ld = p.x_ld; q.x_coff = p.x_coff; q.x_stats = p.x_stats; q.eps = p.eps; q.act = p.act;
       q.dy = p.dy; q.dy_ld = p.dy_ld; q.dy_coff = p.dy_coff; q.dw = p.dw;
       p = q;
