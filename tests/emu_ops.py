@@ -28,7 +28,17 @@ def _normalise(x_ncdhw, stats, act, eps):
     n = x_ncdhw[0, 0].numel()
     m, r = _mean_rstd(stats, n, eps)
     h = (x_ncdhw.double() - m[:, :, None, None, None]) * r[:, :, None, None, None]
-    return (F.relu(h) if act else h).to(x_ncdhw.dtype)
+    return _act(h, act).to(x_ncdhw.dtype)
+
+
+def _act(h, act):
+    """B200SEG_ACT_NONE / RELU / LRELU(0.01)"""
+    return F.relu(h) if act == 1 else (F.leaky_relu(h, 0.01) if act == 2 else h)
+
+
+def _act_grad(h, act):
+    one = torch.ones_like(h)
+    return (h > 0).to(h.dtype) if act == 1 else (torch.where(h > 0, one, 0.01 * one) if act == 2 else one)
 
 
 def install(monkeypatch):
@@ -70,7 +80,7 @@ def install(monkeypatch):
             m, r = _mean_rstd(gstats, n, eps)
             hx = (xg.double() - m[:, :, None, None, None]) * r[:, :, None, None, None]
             if gact:
-                y = y * (hx > 0)
+                y = y * _act_grad(hx, gact)
             if want_stats:
                 st = torch.stack([y.flatten(2).sum(-1), (y * hx).flatten(2).sum(-1)], -1).contiguous()
         else:
@@ -121,7 +131,7 @@ def install(monkeypatch):
         hx = (xs - m[:, :, None, None, None]) * r[:, :, None, None, None]
         g = _ncdhw(dy, 0, C).double()
         if act:
-            g = g * (hx > 0)
+            g = g * _act_grad(hx, act)
         bst = torch.stack([g.flatten(2).sum(-1), (g * hx).flatten(2).sum(-1)], -1).contiguous()
         return g.to(x.dtype).permute(0, 2, 3, 4, 1).contiguous(), bst
 
